@@ -1,0 +1,93 @@
+// ref_shim.cc -- TEST INFRASTRUCTURE.  extern "C" doorway into the UNMODIFIED reference library.
+//
+// oracle/Makefile compiles this file together with the reference's own sources, taken where they lie under
+// /root/reference (never copied into the repo), into oracle/_ref/libicref.so.  tests/ use it to pin the C
+// restatement (texblock_oracle.c) and tools/gen_golden.py uses it to produce tests/golden/.  bench.py may time it
+// as the "reference" CPU baseline.  The product never links it.
+#include <cstring>
+#include <vector>
+
+#include "image_compression/public/compressed_image.h"
+#include "image_compression/public/dxtc_compressor.h"
+#include "image_compression/public/etc_compressor.h"
+#include "image_compression/public/pvrtc_compressor.h"
+
+using image_codec_compression::CompressedImage;
+using image_codec_compression::Compressor;
+using image_codec_compression::DxtcCompressor;
+using image_codec_compression::EtcCompressor;
+using image_codec_compression::PvrtcCompressor;
+
+namespace {
+
+// Runs Compress / CompressAndPad into caller storage.  Returns bytes produced, 0 when the reference said false,
+// and reports the metadata the reference filled in (7 uint32: format, uh, uw, ch, cw, padding, name length).
+long run(Compressor *c, int format, unsigned h, unsigned w, int pad_mode, unsigned ph, unsigned pw, unsigned padding,
+         const unsigned char *src, unsigned char *dst, size_t dst_cap, unsigned *meta) {
+  CompressedImage image;
+  const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);
+  const bool ok = pad_mode ? c->CompressAndPad(f, h, w, ph, pw, padding, src, &image)
+                           : c->Compress(f, h, w, padding, src, &image);
+  if (!ok) return 0;
+  if (image.GetDataSize() > dst_cap) return -1;
+  std::memcpy(dst, image.GetData(), image.GetDataSize());
+  if (meta) {
+    const CompressedImage::Metadata &m = image.GetMetadata();
+    meta[0] = m.format;
+    meta[1] = m.uncompressed_height;
+    meta[2] = m.uncompressed_width;
+    meta[3] = m.compressed_height;
+    meta[4] = m.compressed_width;
+    meta[5] = m.padding_bytes_per_row;
+    meta[6] = static_cast<unsigned>(m.compressor_name.size());
+  }
+  return static_cast<long>(image.GetDataSize());
+}
+
+}  // namespace
+
+extern "C" {
+
+long icref_dxt(int format, unsigned h, unsigned w, int pad_mode, unsigned ph, unsigned pw, unsigned padding,
+               const unsigned char *src, unsigned char *dst, size_t dst_cap, unsigned *meta) {
+  DxtcCompressor c;
+  return run(&c, format, h, w, pad_mode, ph, pw, padding, src, dst, dst_cap, meta);
+}
+
+long icref_etc(int strategy, int format, unsigned h, unsigned w, int pad_mode, unsigned ph, unsigned pw,
+               unsigned padding, const unsigned char *src, unsigned char *dst, size_t dst_cap, unsigned *meta) {
+  EtcCompressor c;
+  c.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  return run(&c, format, h, w, pad_mode, ph, pw, padding, src, dst, dst_cap, meta);
+}
+
+long icref_pvrtc(int format, unsigned h, unsigned w, unsigned padding, const unsigned char *src, unsigned char *dst,
+                 size_t dst_cap, unsigned *meta) {
+  PvrtcCompressor c;
+  return run(&c, format, h, w, 0, 0, 0, padding, src, dst, dst_cap, meta);
+}
+
+// Compress straight into external storage (public/compressed_image.h:94-100): used for the multi-threaded
+// row-stripe CPU baseline and to test the size-mismatch error path.
+int icref_dxt_external(int format, unsigned h, unsigned w, unsigned padding, const unsigned char *src,
+                       unsigned char *dst, size_t dst_size) {
+  DxtcCompressor c;
+  CompressedImage image(dst_size, dst);
+  return c.Compress(static_cast<CompressedImage::Format>(format), h, w, padding, src, &image) ? 1 : 0;
+}
+
+int icref_etc_external(int strategy, unsigned h, unsigned w, unsigned padding, const unsigned char *src,
+                       unsigned char *dst, size_t dst_size) {
+  EtcCompressor c;
+  c.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  CompressedImage image(dst_size, dst);
+  return c.Compress(CompressedImage::kRGB, h, w, padding, src, &image) ? 1 : 0;
+}
+
+size_t icref_size(int codec, int format, unsigned h, unsigned w) {
+  if (codec == 0) return DxtcCompressor().ComputeCompressedDataSize(static_cast<CompressedImage::Format>(format), h, w);
+  if (codec == 1) return EtcCompressor().ComputeCompressedDataSize(static_cast<CompressedImage::Format>(format), h, w);
+  return PvrtcCompressor().ComputeCompressedDataSize(static_cast<CompressedImage::Format>(format), h, w);
+}
+
+}  // extern "C"

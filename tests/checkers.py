@@ -1,0 +1,168 @@
+"""ctypes doors to the two CPU checkers (TEST INFRASTRUCTURE): oracle/liboracle.so (plain-C restatement) and,
+when it was built in the container that has /root/reference, oracle/_ref/libicref.so (the unmodified reference).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+RGB, BGR, RGBA, BGRA = 0, 1, 2, 3
+ETC_SPLIT_H, ETC_SPLIT_V, ETC_SMALLER_ERROR, ETC_HEURISTIC = 0, 1, 2, 3
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_u8p)
+
+
+def build_oracle():
+    """(Re)builds liboracle.so and, if the reference is mounted, _ref/libicref.so."""
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True, stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        for name in ("orc_dxt_compress", "orc_dxt1_compress_rgba", "orc_etc1_compress"):
+            getattr(lib, name).restype = C.c_size_t
+            getattr(lib, name).argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_pvrtc2_compress.restype = C.c_size_t
+        lib.orc_pvrtc2_compress.argtypes = [C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_fill_synthetic.restype = None
+        lib.orc_fill_synthetic.argtypes = [_u8p, C.c_size_t, C.c_uint64, C.c_uint64]
+        lib.orc_fnv1a64.restype = C.c_uint64
+        lib.orc_fnv1a64.argtypes = [_u8p, C.c_size_t]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libicref.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libicref.so"))
+        u32p = C.POINTER(C.c_uint32)
+        lib.icref_dxt.restype = C.c_long
+        lib.icref_dxt.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t, u32p]
+        lib.icref_etc.restype = C.c_long
+        lib.icref_etc.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t, u32p]
+        lib.icref_pvrtc.restype = C.c_long
+        lib.icref_pvrtc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t, u32p]
+        lib.icref_dxt_external.restype = C.c_int
+        lib.icref_dxt_external.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
+        lib.icref_etc_external.restype = C.c_int
+        lib.icref_etc_external.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
+        lib.icref_size.restype = C.c_size_t
+        lib.icref_size.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint]
+        _ref = lib
+    return _ref
+
+
+def ncomp(fmt):
+    return 3 if fmt in (RGB, BGR) else 4
+
+
+def nblocks(n):
+    return (n + 3) // 4
+
+
+# ---- plain-C oracle -------------------------------------------------------------------------------------------
+
+def oracle_dxt(fmt, img, h, w, coded_h=None, coded_w=None, padding=0):
+    coded_h = h if coded_h is None else max(h, coded_h)
+    coded_w = w if coded_w is None else max(w, coded_w)
+    out = np.zeros(nblocks(coded_h) * nblocks(coded_w) * (8 if ncomp(fmt) == 3 else 16), np.uint8)
+    n = oracle().orc_dxt_compress(fmt, h, w, coded_h, coded_w, padding, _ptr(img), _ptr(out))
+    assert n == out.size
+    return out
+
+
+def oracle_dxt1_rgba(img, h, w, swap_rb=0, coded_h=None, coded_w=None, padding=0):
+    coded_h = h if coded_h is None else max(h, coded_h)
+    coded_w = w if coded_w is None else max(w, coded_w)
+    out = np.zeros(nblocks(coded_h) * nblocks(coded_w) * 8, np.uint8)
+    n = oracle().orc_dxt1_compress_rgba(swap_rb, h, w, coded_h, coded_w, padding, _ptr(img), _ptr(out))
+    assert n == out.size
+    return out
+
+
+def oracle_etc1(strategy, img, h, w, coded_h=None, coded_w=None, padding=0):
+    coded_h = h if coded_h is None else max(h, coded_h)
+    coded_w = w if coded_w is None else max(w, coded_w)
+    out = np.zeros(nblocks(coded_h) * nblocks(coded_w) * 8, np.uint8)
+    n = oracle().orc_etc1_compress(strategy, h, w, coded_h, coded_w, padding, _ptr(img), _ptr(out))
+    assert n == out.size
+    return out
+
+
+def oracle_pvrtc(img, h, w):
+    out = np.zeros(h * w // 4, np.uint8)
+    n = oracle().orc_pvrtc2_compress(h, w, _ptr(img), _ptr(out))
+    assert n == out.size
+    return out
+
+
+def synthetic(nbytes, seed, offset=0):
+    out = np.zeros(nbytes, np.uint8)
+    oracle().orc_fill_synthetic(_ptr(out), nbytes, seed, offset)
+    return out
+
+
+def fnv1a64(a):
+    a = np.ascontiguousarray(a, np.uint8)
+    return int(oracle().orc_fnv1a64(_ptr(a), a.size))
+
+
+# ---- compiled reference ---------------------------------------------------------------------------------------
+
+def _meta_dict(meta):
+    return dict(format=int(meta[0]), uncompressed_height=int(meta[1]), uncompressed_width=int(meta[2]),
+                compressed_height=int(meta[3]), compressed_width=int(meta[4]), padding_bytes_per_row=int(meta[5]),
+                name_len=int(meta[6]))
+
+
+def _run_ref(fn, args, cap):
+    out = np.zeros(max(cap, 16), np.uint8)
+    meta = (C.c_uint32 * 7)()
+    n = fn(*args, _ptr(out), out.size, meta)
+    if n <= 0:
+        return None, None
+    return out[:n].copy(), _meta_dict(meta)
+
+
+def ref_dxt(fmt, img, h, w, padded=None, padding=0, want_meta=False):
+    ph, pw = padded if padded else (0, 0)
+    ch, cw = (max(h, ph), max(w, pw)) if padded else (h, w)
+    cap = nblocks(ch) * nblocks(cw) * 16
+    out, meta = _run_ref(ref().icref_dxt, (fmt, h, w, 1 if padded else 0, ph, pw, padding, _ptr(img)), cap)
+    return (out, meta) if want_meta else out
+
+
+def ref_etc(strategy, img, h, w, padded=None, padding=0, fmt=RGB, want_meta=False):
+    ph, pw = padded if padded else (0, 0)
+    ch, cw = (max(h, ph), max(w, pw)) if padded else (h, w)
+    cap = nblocks(ch) * nblocks(cw) * 8
+    out, meta = _run_ref(ref().icref_etc, (strategy, fmt, h, w, 1 if padded else 0, ph, pw, padding, _ptr(img)), cap)
+    return (out, meta) if want_meta else out
+
+
+def ref_pvrtc(img, h, w, padding=0, fmt=RGBA, want_meta=False):
+    out, meta = _run_ref(ref().icref_pvrtc, (fmt, h, w, padding, _ptr(img)), h * w // 4 + 16)
+    return (out, meta) if want_meta else out
