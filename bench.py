@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpixels/s of the B200 texture-block encoder on BASELINE.json's headline configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dxt1_rgba8] [--impl reference]
+
+Default workload (config.workload): DXT1 encode of an 8192x8192 synthetic RGBA8 image (BASELINE.json configs[1]),
+input resident in HBM.  One "step" = one pass of the encoder over the image (one kernel launch).  At N > 1
+(torchrun, one rank per GPU) the image grows to 8192 x (8192*N) and is sharded by block-row stripes -- fixed work
+per GPU, "scaling": "weak", no data-path collective; the NCCL gather of the packed stream the north star names is
+timed separately and reported under "gather".  Prints ONE JSON line (rank 0).
+
+Keys beyond the base contract: "roofline" (dominant kernel vs MEASURED_PEAKS.json HBM copy bandwidth),
+"cpu_baseline" (the unmodified reference, or the oracle port, timed on this box's host cores on a bounded sample),
+"e2e" (same metric through icb_compress_host with pinned host buffers: H2D + kernels + D2H inside the timed region),
+"clocks", "gpu_launches".
+
+--impl reference times the reference's own CPU implementation (oracle/_ref when it was built, else the oracle
+port) with all host threads on the same metric; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (codec, format, ncomp, image size, bytes out per pixel, description)
+    "dxt1_rgba8": dict(codec=0, fmt=2, nc=4, n=8192, out_bpp=0.5, seed=2, desc="DXT1 8192x8192 RGBA8 (alpha ignored)"),
+    "dxt1_rgb8": dict(codec=0, fmt=0, nc=3, n=8192, out_bpp=0.5, seed=1, desc="DXT1 8192x8192 RGB888"),
+    "dxt5_rgba8": dict(codec=1, fmt=2, nc=4, n=8192, out_bpp=1.0, seed=2, desc="DXT5 8192x8192 RGBA8"),
+    "etc1_rgb8": dict(codec=2, fmt=0, nc=3, n=4096, out_bpp=0.5, seed=1, desc="ETC1 4096x4096 RGB888, kSmallerError"),
+    "pvrtc2_rgba8": dict(codec=3, fmt=2, nc=4, n=4096, out_bpp=0.25, seed=2, desc="PVRTC1 2bpp 4096x4096 RGBA8"),
+}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+
+def cpu_reference_throughput(workload, steps, warmup):
+    """Times the reference CPU encoder (oracle/_ref, unmodified, -O2) or, when that was not built, the oracle port,
+    on T row stripes from T threads (zero-copy external-storage outputs).  The sample is a
+    WIDTH x (256*T) stripe stack of the workload's synthetic image; Mpix/s does not depend on the sample height."""
+    import numpy as np
+
+    import checkers as ck
+    wl = WORKLOADS[workload]
+    n = wl["n"]
+    threads = os.cpu_count() or 1
+    use_ref = ck.have_ref()
+    if workload == "pvrtc2_rgba8":
+        threads = 1  # wrap-around + Z-order: cannot be stripe-split through the public API
+        side = 1024
+    rows_per_thread = 1024
+    # The reference's DXT1 takes RGB888: feed it the alpha-stripped image (what a caller must do today).
+    ref_nc = 3 if workload in ("dxt1_rgba8", "dxt1_rgb8", "etc1_rgb8") else 4
+    if workload == "etc1_rgb8":
+        rows_per_thread = 128  # exhaustive search: ~2 Mpix/s per core
+    if workload == "pvrtc2_rgba8":
+        src = ck.synthetic(side * side * 4, wl["seed"])
+        sample_px = side * side
+    else:
+        # one stripe of input shared by all threads (each writes its own output slice): same work per thread as
+        # a T-stripe image without generating T stripes of input
+        raw = ck.synthetic(n * rows_per_thread * wl["nc"], wl["seed"])
+        if wl["nc"] == 4 and ref_nc == 3:
+            raw = np.ascontiguousarray(raw.reshape(-1, 4)[:, :3]).reshape(-1)
+        src = raw
+        sample_px = n * rows_per_thread * threads
+    block_bytes = 16 if workload == "dxt5_rgba8" else 8
+    out = np.zeros(sample_px // 16 * block_bytes if workload != "pvrtc2_rgba8" else sample_px // 4, np.uint8)
+
+    def stripe_job(t):
+        h = rows_per_thread
+        s = src
+        o = out[t * (h // 4) * (n // 4) * block_bytes:(t + 1) * (h // 4) * (n // 4) * block_bytes]
+        if use_ref:
+            L = ck.ref()
+            if workload == "etc1_rgb8":
+                ok = L.icref_etc_external(2, h, n, 0, ck._ptr(s), ck._ptr(o), o.size)
+            else:
+                fmt = ck.RGB if ref_nc == 3 else ck.RGBA
+                ok = L.icref_dxt_external(fmt, h, n, 0, ck._ptr(s), ck._ptr(o), o.size)
+            assert ok == 1
+        else:
+            L = ck.oracle()
+            if workload == "etc1_rgb8":
+                L.orc_etc1_compress(2, h, n, h, n, 0, ck._ptr(s), ck._ptr(o))
+            else:
+                L.orc_dxt_compress(ck.RGB if ref_nc == 3 else ck.RGBA, h, n, h, n, 0, ck._ptr(s), ck._ptr(o))
+
+    def one_step():
+        if workload == "pvrtc2_rgba8":
+            if use_ref:
+                res = ck.ref_pvrtc(src, side, side)
+                assert res is not None
+            else:
+                ck.oracle_pvrtc(src, side, side)
+            return
+        ts = [threading.Thread(target=stripe_job, args=(t,)) for t in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    for _ in range(max(1, warmup)):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    if workload == "pvrtc2_rgba8":
+        sample = "%dx%d image, 1 thread (PVRTC cannot be stripe-split)" % (side, side)
+    else:
+        sample = "%d x %d px per step: %d threads x one %d-row stripe each%s" % (
+            n, rows_per_thread * threads, threads, rows_per_thread, ", alpha stripped to RGB888" if wl["nc"] == 4 and ref_nc == 3 else "")
+    return dict(value=sample_px / dt / 1e6, unit="Mpixels/s", cores=threads, kind="reference" if use_ref else "port",
+                sample=sample, ms_per_step=dt * 1e3, flags="-O2 -std=c++14 -DIS_LITTLE_ENDIAN" if use_ref else "-O2 -std=c99")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    cpu = cpu_reference_throughput(args.workload, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if args.workload == "dxt1_rgba8" else "Mpixels/sec " + wl["desc"],
+        "value": cpu["value"], "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "image": "%dx%d" % (wl["n"], wl["n"]), "where": "host CPU, %d threads" % cpu["cores"]},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")},
+        "e2e": {"value": cpu["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import image_compression_b200 as icb
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOADS[args.workload]
+    n, nc, codec, fmt = wl["n"], wl["nc"], wl["codec"], wl["fmt"]
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    # Weak scaling: the job is an n-wide image of n*world rows, sharded by block-row stripes; this rank owns
+    # block rows [r0, r1) and holds only those pixel rows.  PVRTC does not shard (toroidal wrap): replicas.
+    pitch = n * nc
+    total_rows = n * world
+    grid_rows = total_rows // 4
+    r0, r1 = icb.stripe_rows(grid_rows, rank, world)
+    my_px_rows = (r1 - r0) * 4
+    in_bytes = my_px_rows * pitch
+    out_bytes = int(my_px_rows * n * wl["out_bpp"])
+    nbuf = 2  # rotate so that consecutive steps never re-read lines still in the 126 MB L2
+    srcs = [torch.empty(in_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    dsts = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    for i, s in enumerate(srcs):
+        icb.fill_synthetic(s, wl["seed"] + 16 * i, byte_offset=r0 * 4 * pitch)
+    scratch = torch.empty(icb.lib().icb_pvrtc2_scratch_size(n, n), dtype=torch.uint8, device="cuda") if codec == 3 else None
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        s, d = srcs[i % nbuf], dsts[i % nbuf]
+        if codec == 3:
+            icb.pvrtc_encode_device(s, n, n, out=d, scratch=scratch, stream=stream)
+        else:
+            # virtual address of pixel (0,0) of the whole tall image; rows outside the stripe are never touched
+            base = s.data_ptr() - r0 * 4 * pitch
+            icb.encode_stripe_device(codec, fmt, base, total_rows, n, pitch, total_rows, n, r0, r1, d, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches_before = icb.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for i in range(steps):
+        ev[i][0].record(stream)
+        step(i)
+        ev[i][1].record(stream)
+    t_end.record(stream)
+    barrier()
+    launches = icb.launch_count() - launches_before
+    total_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+    job_px = n * total_rows if codec != 3 else n * n * world
+    value = job_px / (ms_per_step * 1e-3) / 1e6
+
+    # ---- NCCL gather of the packed block stream to rank 0 (reported separately, not part of `value`)
+    gather = None
+    if world > 1 and codec != 3:
+        parts = [torch.empty_like(dsts[0]) for _ in range(world)] if rank == 0 else None
+        for _ in range(3):
+            dist.gather(dsts[0], parts, dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        reps = 10
+        for _ in range(reps):
+            dist.gather(dsts[0], parts, dst=0)
+        g1.record(stream)
+        barrier()
+        g_ms = torch.tensor([g0.elapsed_time(g1) / reps], device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(g_ms.item()), "bytes_into_root": out_bytes * (world - 1), "backend": "nccl gather",
+                  "encode_plus_gather_mpix_s": job_px / ((ms_per_step + float(g_ms.item())) * 1e-3) / 1e6}
+
+    # ---- end to end through the host-buffer entry point (pinned buffers; H2D + kernels + D2H per step)
+    L = icb.lib()
+    e2e_rows = my_px_rows if codec != 3 else n
+    h_in_ptr = L.icb_host_alloc(in_bytes)
+    h_out_ptr = L.icb_host_alloc(out_bytes)
+    if not h_in_ptr or not h_out_ptr:
+        raise SystemExit("pinned allocation failed")
+    h_in = np.ctypeslib.as_array(C.cast(h_in_ptr, C.POINTER(C.c_uint8)), shape=(in_bytes,))
+    h_out = np.ctypeslib.as_array(C.cast(h_out_ptr, C.POINTER(C.c_uint8)), shape=(out_bytes,))
+    h_in[:] = srcs[0].cpu().numpy()
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        icb.compress_host(codec, fmt, h_in, e2e_rows, n, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        icb.compress_host(codec, fmt, h_in, e2e_rows, n, out=h_out)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = job_px / (e2e_ms * 1e-3) / 1e6
+    e2e_check = bool(np.array_equal(h_out, dsts[0].cpu().numpy()))
+    L.icb_host_free(h_in_ptr)
+    L.icb_host_free(h_out_ptr)
+
+    if rank == 0:
+        clocks = sampler.stop()
+        peak, peak_src = measured_peak_gbs()
+        algo_bytes = in_bytes + out_bytes  # read every source byte once, write every block once
+        k_med = kernel_ms[len(kernel_ms) // 2]
+        k_avg = sum(kernel_ms) / len(kernel_ms)
+        achieved = algo_bytes / (k_avg * 1e-3) / 1e9
+        cpu = cpu_reference_throughput(args.workload, 2, 1) if not args.no_cpu_baseline else None
+        line = {
+            "metric": "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if args.workload == "dxt1_rgba8" else "Mpixels/sec " + wl["desc"],
+            "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "image": "%dx%d per GPU (%dx%d job, block-row stripes)" % (n, n, n, total_rows),
+                       "input": "splitmix64 byte stream, resident in HBM", "l2": "%d MB input per step > 126 MB L2, %d rotating buffers" % (in_bytes >> 20, nbuf),
+                       "parallelism": "stripe%d" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": k_avg, "kernel_ms_median": k_med,
+                         "kernel_ms_min": kernel_ms[0], "read_only_frac": (in_bytes / (k_avg * 1e-3) / 1e9) / peak},
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "icb_compress_host (pinned host buffers)", "output_equals_device_path": e2e_check},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")}
+        if gather:
+            line["gather"] = gather
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dxt1_rgba8", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

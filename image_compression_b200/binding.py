@@ -1,0 +1,172 @@
+"""ctypes binding of include/icb200.h plus thin helpers over torch tensors (device memory and streams only)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+RGB, BGR, RGBA, BGRA = 0, 1, 2, 3
+CODEC_DXT1, CODEC_DXT5, CODEC_ETC1, CODEC_PVRTC2 = 0, 1, 2, 3
+ETC_SPLIT_HORIZONTALLY, ETC_SPLIT_VERTICALLY, ETC_SMALLER_ERROR, ETC_HEURISTIC = 0, 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libicb200.so")
+
+
+class IcbError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__("icb status %d: %s" % (status, text))
+        self.status = status
+
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/icb200.h one to one (tests check the header against this table)
+PROTOTYPES = {
+    "icb_abi_version": (C.c_int, []),
+    "icb_last_error": (C.c_char_p, []),
+    "icb_device_count": (C.c_int, []),
+    "icb_compressed_size": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32]),
+    "icb_dxt1_encode_rgb8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "icb_dxt1_encode_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "icb_dxt5_encode_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "icb_etc1_encode_rgb8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "icb_encode4x4_stripe": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "icb_pvrtc2_scratch_size": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "icb_pvrtc2_encode_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "icb_compress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "icb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "icb_host_free": (None, [C.c_void_p]),
+    "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "icb_launch_count": (C.c_uint64, []),
+    "icb_set_tma_mode": (C.c_int, [C.c_int]),
+}
+
+
+def lib():
+    """Loads lib/libicb200.so.  Raises if it is missing -- there is nothing to fall back to."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a); there is no CPU fallback" % path)
+        handle = C.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise IcbError(status, lib().icb_last_error().decode())
+
+
+def compressed_size(codec, coded_h, coded_w):
+    return lib().icb_compressed_size(codec, coded_h, coded_w)
+
+
+def launch_count():
+    return int(lib().icb_launch_count())
+
+
+def set_tma_mode(mode):
+    return lib().icb_set_tma_mode(mode)
+
+
+def _stream_ptr(stream):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def ncomp_of(fmt):
+    return 3 if fmt in (RGB, BGR) else 4
+
+
+def encode_device(codec, fmt, src, h, w, pitch=None, coded_h=None, coded_w=None, strategy=ETC_SMALLER_ERROR,
+                  out=None, stream=None):
+    """Device-resident encode of a uint8 CUDA tensor `src` (flat or [h, pitch]) -> uint8 CUDA tensor of blocks.
+
+    codec DXT1 with a 4-component format uses the RGBA8 extension entry point (alpha ignored)."""
+    import torch
+    nc = ncomp_of(fmt)
+    pitch = w * nc if pitch is None else pitch
+    coded_h = h if coded_h is None else coded_h
+    coded_w = w if coded_w is None else coded_w
+    size = compressed_size(codec, coded_h, coded_w)
+    if out is None:
+        out = torch.empty(size, dtype=torch.uint8, device=src.device)
+    assert out.numel() == size and src.is_cuda and src.dtype == torch.uint8
+    swap = 1 if fmt in (BGR, BGRA) else 0
+    L = lib()
+    sp = _stream_ptr(stream)
+    with torch.cuda.device(src.device):
+        if codec == CODEC_DXT1 and nc == 3:
+            _check(L.icb_dxt1_encode_rgb8(src.data_ptr(), h, w, pitch, coded_h, coded_w, swap, out.data_ptr(), sp))
+        elif codec == CODEC_DXT1:
+            _check(L.icb_dxt1_encode_rgba8(src.data_ptr(), h, w, pitch, coded_h, coded_w, swap, out.data_ptr(), sp))
+        elif codec == CODEC_DXT5:
+            if nc != 4:
+                raise IcbError(-1, "DXT5 needs a 4-component format")
+            _check(L.icb_dxt5_encode_rgba8(src.data_ptr(), h, w, pitch, coded_h, coded_w, swap, out.data_ptr(), sp))
+        elif codec == CODEC_ETC1:
+            if fmt != RGB:
+                raise IcbError(-1, "ETC1 supports kRGB only")
+            _check(L.icb_etc1_encode_rgb8(src.data_ptr(), h, w, pitch, coded_h, coded_w, strategy, out.data_ptr(), sp))
+        elif codec == CODEC_PVRTC2:
+            return pvrtc_encode_device(src, h, w, out=out, stream=stream)
+        else:
+            raise IcbError(-1, "unknown codec")
+    return out
+
+
+def stripe_rows(grid_rows, rank, world):
+    """Block-row range [r0, r1) of rank `rank` when a grid of `grid_rows` block rows is split over `world` ranks
+    (contiguous stripes, the first grid_rows % world ranks take one extra row)."""
+    base, extra = divmod(grid_rows, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def encode_stripe_device(codec, fmt, src_base_ptr, h, w, pitch, coded_h, coded_w, r0, r1, out, strategy=ETC_SMALLER_ERROR,
+                         stream=None):
+    """Encodes block rows [r0, r1).  src_base_ptr is the (possibly virtual) address of pixel (0,0) of the whole
+    image; only the rows the stripe reads must be resident.  `out` receives the stripe's blocks."""
+    swap = 1 if fmt in (BGR, BGRA) else 0
+    _check(lib().icb_encode4x4_stripe(codec, ncomp_of(fmt), C.c_void_p(src_base_ptr), h, w, pitch, coded_h, coded_w, swap,
+                                      strategy, r0, r1, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def pvrtc_encode_device(src, h, w, out=None, scratch=None, stream=None):
+    import torch
+    if out is None:
+        out = torch.empty(w * h // 4, dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        _check(lib().icb_pvrtc2_encode_rgba8(src.data_ptr(), h, w, out.data_ptr(),
+                                             scratch.data_ptr() if scratch is not None else None, _stream_ptr(stream)))
+    return out
+
+
+def fill_synthetic(dst, seed, byte_offset=0, stream=None):
+    import torch
+    with torch.cuda.device(dst.device):
+        _check(lib().icb_fill_synthetic(dst.data_ptr(), dst.numel(), seed, byte_offset, _stream_ptr(stream)))
+    return dst
+
+
+def compress_host(codec, fmt, src, h, w, padded=None, padding=0, strategy=ETC_SMALLER_ERROR, out=None):
+    """Host path: numpy uint8 in, numpy uint8 out, through icb_compress_host (H2D + kernels + D2H inside)."""
+    ph, pw = padded if padded else (0, 0)
+    coded_h, coded_w = max(h, ph), max(w, pw)
+    size = compressed_size(codec, coded_h, coded_w) if codec != CODEC_PVRTC2 else w * h // 4
+    if out is None:
+        out = np.empty(size, np.uint8)
+    _check(lib().icb_compress_host(codec, fmt, h, w, ph, pw, padding, strategy, src.ctypes.data, out.ctypes.data, out.size))
+    return out

@@ -1,0 +1,261 @@
+// block4x4_kernels.cuh -- image-level drivers for the 4x4-block codecs (DXT1, DXT5, ETC1).
+//
+// These kernels ARE the reference's block loop, Compressor4x4Helper::Compress / CompressAndPad
+// (/root/reference/image_compression/internal/compressor4x4_helper.h:175-216, 479-520): one 4x4 window per
+// block in raster order, window gather with clamp-to-edge replication as in Pixel4x4
+// (internal/pixel4x4.h:45-67, internal/pixel4x4.cc:24-59).
+//
+// Two drivers:
+//   encode4x4_tma_kernel      the fast path.  Persistent CTAs; one elected producer thread streams 2-D pixel
+//                             tiles HBM -> shared memory with TMA (cp.async.bulk.tensor) through a ring of
+//                             mbarrier-guarded stages; consumer warps read their block's four rows with 128-bit
+//                             (or 3x32-bit for RGB888) conflict-free shared loads, encode in registers and write
+//                             8/16 B per lane, coalesced.  Needs a 16-byte aligned base and pitch.
+//   encode4x4_generic_kernel  any pointer / pitch / size, and the pad region of CompressAndPad: byte loads with
+//                             clamped coordinates straight from global memory.
+#pragma once
+#include <cuda.h>
+#include <cstdint>
+
+#include "dxt_encode.cuh"
+#include "etc1_encode.cuh"
+
+namespace icb {
+
+enum Codec4x4 : int { kCodecDxt1 = 0, kCodecDxt5 = 1, kCodecEtc1 = 2 };
+
+struct Encode4x4Params {
+  const uint8_t *src;     // pixel (0,0)
+  uint8_t *dst;           // block (0,0) of the full output grid
+  uint32_t height, width; // source image size in pixels
+  uint32_t pitch;         // source bytes per row
+  uint32_t grid_cols;     // blocks per output row (ceil(coded_w / 4))
+  uint32_t row0, row1;    // block-row range [row0, row1) this launch encodes
+  uint32_t col0, col1;    // block-column range [col0, col1)
+  int swap_rb;            // kBGR / kBGRA
+  int etc_strategy;
+};
+
+template <int kCodec>
+struct CodecTraits;
+template <>
+struct CodecTraits<kCodecDxt1> {
+  static constexpr int kBlockBytes = 8;
+};
+template <>
+struct CodecTraits<kCodecDxt5> {
+  static constexpr int kBlockBytes = 16;
+};
+template <>
+struct CodecTraits<kCodecEtc1> {
+  static constexpr int kBlockBytes = 8;
+};
+
+// Encodes 16 gathered pixels and stores the block.  px bytes are (c0,c1,c2,c3) in memory order; for 3-component
+// sources c3 is zero.
+template <int kCodec, typename Fetch>
+__device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch fetch, bool one_pixel, int swap_rb,
+                                                 int etc_strategy, uint8_t *out) {
+  if constexpr (kCodec == kCodecDxt1) {
+    const uint2 c = dxt1_encode_block(px, swap_rb != 0, false, fetch);
+    *reinterpret_cast<uint2 *>(out) = c;
+  } else if constexpr (kCodec == kCodecDxt5) {
+    const uint2 a = dxt5_encode_alpha(px, one_pixel);
+    const uint2 c = dxt1_encode_block(px, swap_rb != 0, true, fetch);
+    *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
+  } else {
+    const uint2 e = etc1_encode_block(px, etc_strategy);
+    *reinterpret_cast<uint2 *>(out) = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic driver
+// ---------------------------------------------------------------------------------------------------------
+
+template <int kNcomp>
+__device__ __forceinline__ uint32_t load_pixel_clamped(const Encode4x4Params &p, uint32_t y, uint32_t x) {
+  y = min(y, p.height - 1u);
+  x = min(x, p.width - 1u);
+  const uint8_t *q = p.src + static_cast<size_t>(y) * p.pitch + static_cast<size_t>(x) * kNcomp;
+  uint32_t v = q[0] | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
+  if (kNcomp == 4) v |= static_cast<uint32_t>(q[3]) << 24;
+  return v;
+}
+
+template <int kCodec, int kNcomp>
+__global__ void __launch_bounds__(128) encode4x4_generic_kernel(const Encode4x4Params p) {
+  const uint32_t ncols = p.col1 - p.col0;
+  const uint64_t total = static_cast<uint64_t>(p.row1 - p.row0) * ncols;
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t br = p.row0 + static_cast<uint32_t>(t / ncols);
+    const uint32_t bc = p.col0 + static_cast<uint32_t>(t % ncols);
+    uint32_t px[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) px[i] = load_pixel_clamped<kNcomp>(p, 4u * br + (i >> 2), 4u * bc + (i & 3));
+    auto fetch = [&](uint32_t i) { return load_pixel_clamped<kNcomp>(p, 4u * br + (i >> 2), 4u * bc + (i & 3u)); };
+    const bool one_pixel = 4u * br >= p.height && 4u * bc >= p.width;  // pixel4x4.cc:58
+    uint8_t *out = p.dst + (static_cast<size_t>(br) * p.grid_cols + bc) * CodecTraits<kCodec>::kBlockBytes;
+    encode_and_store<kCodec>(px, fetch, one_pixel, p.swap_rb, p.etc_strategy, out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA driver
+// ---------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 2-D tiled bulk tensor load, global -> shared, completion on an mbarrier; streaming (evict-first) L2 policy.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t x, int32_t y,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+
+// Tile geometry.  A tile is kTileBlocksX x kTileBlocksY blocks; the TMA box is (kTileBlocksX*4*kNcomp/4) 32-bit
+// words wide (the image row is described to TMA as 32-bit words so that RGB888 rows fit the 256-element box
+// limit) and kTileBlocksY*4 rows tall.
+template <int kNcomp>
+struct TileShape {
+  static constexpr int kBlocksX = 64;                       // 256 pixels
+  static constexpr int kBlocksY = 4;                        // 16 pixel rows
+  static constexpr int kRowWords = kBlocksX * kNcomp;       // 32-bit words per tile row (256 or 192)
+  static constexpr int kRows = kBlocksY * 4;
+  static constexpr int kBytes = kRowWords * 4 * kRows;      // 16384 or 12288
+  static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
+};
+
+constexpr int kTmaStages = 4;
+
+template <int kCodec, int kNcomp>
+__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
+    encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
+                         uint32_t num_tiles) {
+  using Shape = TileShape<kNcomp>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t *tiles = smem_raw;  // kTmaStages * Shape::kBytes
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + kTmaStages * Shape::kBytes);
+  uint64_t *empty_bar = full_bar + kTmaStages;
+  constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t warp = threadIdx.x >> 5;
+  if (warp == kConsumerWarps) {
+    // ---- producer warp: one lane streams this CTA's tiles through the ring
+    if ((threadIdx.x & 31) == 0) {
+      const uint64_t policy = l2_evict_first_policy();
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], Shape::kBytes);
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        tma_load_2d(tiles + stage * Shape::kBytes, &src_map, &full_bar[stage],
+                    static_cast<int32_t>((p.col0 + tx * Shape::kBlocksX) * kNcomp),
+                    static_cast<int32_t>((p.row0 + ty * Shape::kBlocksY) * 4u), policy);
+        if (++stage == kTmaStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps: thread t owns block (t / kBlocksX, t % kBlocksX) of every tile
+  const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
+  uint32_t stage = 0, phase = 0;
+  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const uint32_t br = p.row0 + ty * Shape::kBlocksY + lby, bc = p.col0 + tx * Shape::kBlocksX + lbx;
+    const uint32_t *tile_words = reinterpret_cast<const uint32_t *>(tiles + stage * Shape::kBytes);
+    mbar_wait(&full_bar[stage], phase);
+
+    if (br < p.row1 && bc < p.col1) {
+      uint32_t px[16];
+      const bool interior = 4u * br + 4u <= p.height && 4u * bc + 4u <= p.width;
+      if (interior) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const uint32_t *row = tile_words + (lby * 4 + y) * Shape::kRowWords + lbx * kNcomp;
+          if constexpr (kNcomp == 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(row);
+            px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
+          } else {
+            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];  // 12 bytes = four packed RGB pixels
+            px[4 * y + 0] = w0 & 0x00ffffffu;
+            px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+            px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
+            px[4 * y + 3] = w2 >> 8;
+          }
+        }
+      }
+      // Pixel i of this thread's window, read back from the tile with clamp-to-edge replication.  The clamped
+      // coordinate never leaves the tile because the window's origin is inside the image.
+      const uint32_t ymax = p.height - 1u - (p.row0 + ty * Shape::kBlocksY) * 4u;  // last valid row, tile-relative
+      const uint32_t xmax = p.width - 1u - (p.col0 + tx * Shape::kBlocksX) * 4u;
+      auto fetch = [&](uint32_t i) {
+        const uint32_t y = min(lby * 4u + (i >> 2), ymax), x = min(lbx * 4u + (i & 3u), xmax);
+        if constexpr (kNcomp == 4) {
+          return tile_words[y * Shape::kRowWords + x];
+        } else {
+          const uint8_t *q = reinterpret_cast<const uint8_t *>(tile_words) + y * (Shape::kRowWords * 4) + x * 3u;
+          return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
+        }
+      };
+      if (!interior) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) px[i] = fetch(i);
+      }
+      uint8_t *out = p.dst + (static_cast<size_t>(br) * p.grid_cols + bc) * CodecTraits<kCodec>::kBlockBytes;
+      encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, out);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == kTmaStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+}  // namespace icb

@@ -1,0 +1,482 @@
+// icb_api.cu -- the extern "C" boundary (include/icb200.h): argument checking, path selection (TMA fast path vs
+// generic driver), launches, and the host-buffer pipeline.  No CPU fallback exists: without a CUDA device every
+// compute entry point fails with ICB_ERR_CUDA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/icb200.h"
+#include "block4x4_kernels.cuh"
+#include "pvrtc_kernels.cuh"
+
+namespace {
+
+thread_local std::string t_last_error;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_tma_mode{-1};
+
+int fail(int status, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return status;
+}
+
+#define ICB_CUDA(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(ICB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+// ---- per-device facts ------------------------------------------------------------------------------------
+
+struct DeviceInfo {
+  int sm_count = 0;
+  bool ok = false;
+};
+
+int device_info(DeviceInfo *out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  int dev = 0;
+  ICB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!cache[dev].ok) {
+    cudaDeviceProp prop;
+    ICB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+      return fail(ICB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    cache[dev].sm_count = prop.multiProcessorCount;
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return ICB_OK;
+}
+
+// cuTensorMapEncodeTiled comes from the driver; resolve it through the runtime so we need not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// ---- 4x4 codecs ------------------------------------------------------------------------------------------
+
+using icb::Encode4x4Params;
+
+template <int kCodec, int kNcomp>
+int launch_generic(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
+  const uint64_t total = static_cast<uint64_t>(p.row1 - p.row0) * (p.col1 - p.col0);
+  if (total == 0) return ICB_OK;
+  const uint64_t want = (total + 127) / 128;
+  const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(sm_count) * 32 ? want : sm_count * 32);
+  icb::encode4x4_generic_kernel<kCodec, kNcomp><<<grid, 128, 0, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+template <int kCodec, int kNcomp>
+int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
+  using Shape = icb::TileShape<kNcomp>;
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled not available from this driver");
+  // The image rows as 32-bit words: width words for RGBA8888, 3*width/4 for RGB888 (width % 4 == 0 here).
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p.width) * kNcomp / 4, p.height};
+  const cuuint64_t strides[1] = {p.pitch};
+  const cuuint32_t box[2] = {Shape::kRowWords, Shape::kRows};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(p.src), dims, strides, box,
+                            elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+
+  auto kernel = icb::encode4x4_tma_kernel<kCodec, kNcomp>;
+  constexpr int kThreads = Shape::kConsumerThreads + 32;
+  constexpr size_t kSmem = static_cast<size_t>(icb::kTmaStages) * Shape::kBytes + 2 * icb::kTmaStages * sizeof(uint64_t);
+  static thread_local int ctas_per_sm[64] = {0};
+  int dev = 0;
+  ICB_CUDA(cudaGetDevice(&dev));
+  if (ctas_per_sm[dev] == 0) {
+    ICB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+    int occ = 0;
+    ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, kSmem));
+    ctas_per_sm[dev] = occ > 0 ? occ : 1;
+  }
+  const uint32_t tiles_x = (p.col1 - p.col0 + Shape::kBlocksX - 1) / Shape::kBlocksX;
+  const uint32_t tiles_y = (p.row1 - p.row0 + Shape::kBlocksY - 1) / Shape::kBlocksY;
+  const uint64_t num_tiles64 = static_cast<uint64_t>(tiles_x) * tiles_y;
+  if (num_tiles64 == 0) return ICB_OK;
+  if (num_tiles64 > 0xffffffffull) return fail(ICB_ERR_INVALID, "image too large");
+  const uint32_t num_tiles = static_cast<uint32_t>(num_tiles64);
+  const uint32_t max_ctas = static_cast<uint32_t>(sm_count * ctas_per_sm[dev]);
+  const uint32_t grid = num_tiles < max_ctas ? num_tiles : max_ctas;
+  kernel<<<grid, kThreads, kSmem, stream>>>(map, p, tiles_x, num_tiles);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+template <int kCodec, int kNcomp>
+int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint32_t r0, uint32_t r1,
+                    cudaStream_t stream) {
+  DeviceInfo info;
+  if (int s = device_info(&info)) return s;
+  const uint32_t rows_in = (p.height + 3) / 4, cols_in = (p.width + 3) / 4;  // blocks whose origin is inside
+  const uint32_t grid_rows = (coded_h + 3) / 4, grid_cols = (coded_w + 3) / 4;
+  if (r1 > grid_rows || r0 > r1) return fail(ICB_ERR_INVALID, "block row range [%u,%u) outside grid of %u rows", r0, r1, grid_rows);
+  p.grid_cols = grid_cols;
+  // d_dst is the stripe's first block: rebase so kernels can index by absolute block row.
+  p.dst -= static_cast<size_t>(r0) * grid_cols * icb::CodecTraits<kCodec>::kBlockBytes;
+
+  const int mode = g_tma_mode.load(std::memory_order_relaxed);
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.src) % 16 == 0) && (p.pitch % 16 == 0) &&
+                       (kNcomp == 4 || p.width % 4 == 0);
+  if (mode == 1 && !aligned) return fail(ICB_ERR_INVALID, "TMA path forced but source base/pitch is not 16-byte aligned");
+  const bool use_tma = aligned && mode != 0;
+
+  const uint32_t in_r1 = r1 < rows_in ? r1 : rows_in;
+  if (r0 < in_r1) {  // windows whose origin lies inside the image
+    p.row0 = r0; p.row1 = in_r1; p.col0 = 0; p.col1 = cols_in;
+    if (int s = use_tma ? launch_tma<kCodec, kNcomp>(p, info.sm_count, stream)
+                        : launch_generic<kCodec, kNcomp>(p, info.sm_count, stream))
+      return s;
+    if (grid_cols > cols_in) {  // CompressAndPad: columns to the right of the image
+      p.col0 = cols_in; p.col1 = grid_cols;
+      if (int s = launch_generic<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
+    }
+  }
+  const uint32_t below_r0 = r0 > rows_in ? r0 : rows_in;
+  if (below_r0 < r1) {  // CompressAndPad: rows below the image
+    p.row0 = below_r0; p.row1 = r1; p.col0 = 0; p.col1 = grid_cols;
+    if (int s = launch_generic<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
+  }
+  return ICB_OK;
+}
+
+int encode4x4(int codec, int ncomp, const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t coded_h,
+              uint32_t coded_w, int swap_rb, int strategy, uint32_t r0, uint32_t r1, void *d_dst, void *stream) {
+  if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero image dimension");
+  if (coded_h < h || coded_w < w) return fail(ICB_ERR_INVALID, "coded size %ux%u smaller than image %ux%u", coded_h, coded_w, h, w);
+  if (pitch < static_cast<size_t>(w) * ncomp || pitch > 0xffffffffull) return fail(ICB_ERR_INVALID, "bad source pitch %zu", pitch);
+  if (strategy < 0 || strategy > 3) return fail(ICB_ERR_INVALID, "unknown ETC strategy %d", strategy);
+  Encode4x4Params p{};
+  p.src = static_cast<const uint8_t *>(d_src);
+  p.dst = static_cast<uint8_t *>(d_dst);
+  p.height = h;
+  p.width = w;
+  p.pitch = static_cast<uint32_t>(pitch);
+  p.swap_rb = swap_rb ? 1 : 0;
+  p.etc_strategy = strategy;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (codec == ICB_CODEC_DXT1 && ncomp == 3) return encode4x4_typed<icb::kCodecDxt1, 3>(p, coded_h, coded_w, r0, r1, s);
+  if (codec == ICB_CODEC_DXT1 && ncomp == 4) return encode4x4_typed<icb::kCodecDxt1, 4>(p, coded_h, coded_w, r0, r1, s);
+  if (codec == ICB_CODEC_DXT5 && ncomp == 4) return encode4x4_typed<icb::kCodecDxt5, 4>(p, coded_h, coded_w, r0, r1, s);
+  if (codec == ICB_CODEC_ETC1 && ncomp == 3) return encode4x4_typed<icb::kCodecEtc1, 3>(p, coded_h, coded_w, r0, r1, s);
+  return fail(ICB_ERR_INVALID, "codec %d does not take %d-component pixels", codec, ncomp);
+}
+
+// ---- synthetic stream ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t splitmix_word(uint64_t seed, uint64_t k) {
+  uint64_t z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void fill_synthetic_kernel(uint8_t *dst, size_t bytes, uint64_t seed, uint64_t byte_offset) {
+  // One 64-bit stream word per thread-iteration; unaligned head/tail bytes handled bytewise.
+  const uint64_t first_word = byte_offset >> 3, last_word = (byte_offset + bytes + 7) >> 3;
+  for (uint64_t k = first_word + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < last_word;
+       k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t v = splitmix_word(seed, k);
+    const uint64_t pos = k << 3;  // stream position of byte 0 of this word
+    if (pos >= byte_offset && pos + 8 <= byte_offset + bytes && ((reinterpret_cast<uintptr_t>(dst) + (pos - byte_offset)) & 7) == 0) {
+      *reinterpret_cast<uint64_t *>(dst + (pos - byte_offset)) = v;
+    } else {
+      for (int b = 0; b < 8; ++b) {
+        const uint64_t q = pos + b;
+        if (q >= byte_offset && q < byte_offset + bytes) dst[q - byte_offset] = static_cast<uint8_t>(v >> (8 * b));
+      }
+    }
+  }
+}
+
+// ---- host-buffer pipeline --------------------------------------------------------------------------------
+
+struct HostPipe {  // per host thread, per device: streams, events and grow-only device buffers
+  int device = -1;
+  cudaStream_t copy_in = nullptr, compute = nullptr, copy_out = nullptr;
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t in_done[kMaxChunks] = {}, enc_done[kMaxChunks] = {};
+  void *d_src = nullptr, *d_dst = nullptr, *d_scratch = nullptr;
+  size_t src_cap = 0, dst_cap = 0, scratch_cap = 0;
+
+  int prepare() {
+    int dev = 0;
+    ICB_CUDA(cudaGetDevice(&dev));
+    if (device == dev) return ICB_OK;
+    release();
+    ICB_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+    ICB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    ICB_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; ++i) {
+      ICB_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+      ICB_CUDA(cudaEventCreateWithFlags(&enc_done[i], cudaEventDisableTiming));
+    }
+    device = dev;
+    return ICB_OK;
+  }
+  static int grow(void **ptr, size_t *cap, size_t need) {
+    if (*cap >= need) return ICB_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    ICB_CUDA(cudaMalloc(ptr, need));
+    *cap = need;
+    return ICB_OK;
+  }
+  void release() {
+    if (device < 0) return;
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(d_scratch);
+    d_src = d_dst = d_scratch = nullptr;
+    src_cap = dst_cap = scratch_cap = 0;
+    for (int i = 0; i < kMaxChunks; ++i) {
+      if (in_done[i]) cudaEventDestroy(in_done[i]);
+      if (enc_done[i]) cudaEventDestroy(enc_done[i]);
+      in_done[i] = enc_done[i] = nullptr;
+    }
+    if (copy_in) cudaStreamDestroy(copy_in);
+    if (compute) cudaStreamDestroy(compute);
+    if (copy_out) cudaStreamDestroy(copy_out);
+    copy_in = compute = copy_out = nullptr;
+    device = -1;
+  }
+  // Deliberately no destructor work: at process exit the CUDA context may already be gone.
+};
+
+thread_local HostPipe t_pipe;
+
+}  // namespace
+
+// =============================================================================================================
+// extern "C"
+// =============================================================================================================
+
+extern "C" {
+
+int icb_abi_version(void) { return ICB_ABI_VERSION; }
+
+const char *icb_last_error(void) { return t_last_error.c_str(); }
+
+int icb_device_count(void) {
+  int n = 0;
+  ICB_CUDA(cudaGetDeviceCount(&n));
+  return n;
+}
+
+uint64_t icb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int icb_set_tma_mode(int mode) { return g_tma_mode.exchange(mode < 0 ? -1 : (mode ? 1 : 0)); }
+
+size_t icb_compressed_size(int codec, uint32_t coded_height, uint32_t coded_width) {
+  if (coded_height == 0 || coded_width == 0) return 0;
+  const size_t blocks = static_cast<size_t>((coded_height + 3) / 4) * ((coded_width + 3) / 4);
+  switch (codec) {
+    case ICB_CODEC_DXT1: return blocks * 8;
+    case ICB_CODEC_DXT5: return blocks * 16;
+    case ICB_CODEC_ETC1: return blocks * 8;
+    case ICB_CODEC_PVRTC2: return static_cast<size_t>(coded_width) * coded_height / 4;
+    default: return 0;
+  }
+}
+
+int icb_dxt1_encode_rgb8(const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t ch, uint32_t cw, int swap_rb,
+                         void *d_dst, void *stream) {
+  return encode4x4(ICB_CODEC_DXT1, 3, d_src, h, w, pitch, ch, cw, swap_rb, 0, 0, (ch + 3) / 4, d_dst, stream);
+}
+int icb_dxt1_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t ch, uint32_t cw,
+                          int swap_rb, void *d_dst, void *stream) {
+  return encode4x4(ICB_CODEC_DXT1, 4, d_src, h, w, pitch, ch, cw, swap_rb, 0, 0, (ch + 3) / 4, d_dst, stream);
+}
+int icb_dxt5_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t ch, uint32_t cw,
+                          int swap_rb, void *d_dst, void *stream) {
+  return encode4x4(ICB_CODEC_DXT5, 4, d_src, h, w, pitch, ch, cw, swap_rb, 0, 0, (ch + 3) / 4, d_dst, stream);
+}
+int icb_etc1_encode_rgb8(const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t ch, uint32_t cw,
+                         int strategy, void *d_dst, void *stream) {
+  return encode4x4(ICB_CODEC_ETC1, 3, d_src, h, w, pitch, ch, cw, 0, strategy, 0, (ch + 3) / 4, d_dst, stream);
+}
+
+int icb_encode4x4_stripe(int codec, int ncomp, const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t ch,
+                         uint32_t cw, int swap_rb, int strategy, uint32_t r0, uint32_t r1, void *d_dst, void *stream) {
+  return encode4x4(codec, ncomp, d_src, h, w, pitch, ch, cw, swap_rb, strategy, r0, r1, d_dst, stream);
+}
+
+size_t icb_pvrtc2_scratch_size(uint32_t h, uint32_t w) { return static_cast<size_t>(w / 8) * (h / 4) * 4 * 2; }
+
+int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_dst, void *d_scratch, void *stream) {
+  if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero image dimension");
+  if ((w & (w - 1)) || (h & (h - 1)) || w != h || w % 8 != 0 || h % 4 != 0)
+    return fail(ICB_ERR_UNSUPPORTED, "PVRTC needs a square power-of-two image of at least 8x8, got %ux%u", h, w);
+  if (reinterpret_cast<uintptr_t>(d_src) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+  DeviceInfo info;
+  if (int s = device_info(&info)) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void *scratch = d_scratch;
+  if (!scratch) ICB_CUDA(cudaMallocAsync(&scratch, icb_pvrtc2_scratch_size(h, w), st));
+  icb::PvrtcParams p;
+  const uint32_t nblocks = (w / 8) * (h / 4);
+  p.src = static_cast<const uint32_t *>(d_src);
+  p.low_a = static_cast<uint32_t *>(scratch);
+  p.low_b = p.low_a + nblocks;
+  p.dst = static_cast<uint2 *>(d_dst);
+  p.width = w;
+  p.height = h;
+  const uint32_t grid = (nblocks + 127) / 128;
+  icb::pvrtc_morph_kernel<<<grid, 128, 0, st>>>(p);
+  icb::pvrtc_modulate_kernel<<<grid, 128, 0, st>>>(p);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));
+  return ICB_OK;
+}
+
+int icb_fill_synthetic(void *d_dst, size_t bytes, uint64_t seed, uint64_t byte_offset, void *stream) {
+  if (bytes == 0) return ICB_OK;
+  if (!d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  const uint64_t words = (bytes + 15) / 8;
+  uint64_t grid = (words + 255) / 256;
+  if (grid > 148ull * 16) grid = 148ull * 16;
+  fill_synthetic_kernel<<<static_cast<uint32_t>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint8_t *>(d_dst), bytes, seed, byte_offset);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+void *icb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    fail(ICB_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void icb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t padded_h, uint32_t padded_w,
+                      uint32_t padding, int strategy, const void *src, void *dst, size_t dst_size) {
+  // Same rejections, in the same order of concern, as the reference entry points
+  // (dxtc_compressor.cc:739, etc_compressor.cc:751-754, pvrtc_compressor.cc:640-650).
+  if (!src || !dst || h == 0 || w == 0) return fail(ICB_ERR_INVALID, "null buffer or zero dimension");
+  if (format < ICB_RGB || format > ICB_BGRA) return fail(ICB_ERR_INVALID, "unknown format %d", format);
+  const int ncomp = (format == ICB_RGB || format == ICB_BGR) ? 3 : 4;
+  const int swap_rb = (format == ICB_BGR || format == ICB_BGRA);
+  if (codec == ICB_CODEC_DXT5 && ncomp != 4) return fail(ICB_ERR_INVALID, "DXT5 needs a 4-component format");
+  if (codec == ICB_CODEC_ETC1 && format != ICB_RGB) return fail(ICB_ERR_INVALID, "ETC1 supports kRGB only");
+  if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_PVRTC2) return fail(ICB_ERR_INVALID, "unknown codec %d", codec);
+
+  if (int s = t_pipe.prepare()) return s;
+  HostPipe &pipe = t_pipe;
+
+  if (codec == ICB_CODEC_PVRTC2) {
+    if ((w & (w - 1)) || (h & (h - 1)) || w != h) return fail(ICB_ERR_UNSUPPORTED, "PVRTC needs a square power-of-two image");
+    if (padding != 0) return fail(ICB_ERR_UNSUPPORTED, "PVRTC does not take padded rows");
+    if (w % 8 != 0 || h % 4 != 0) return fail(ICB_ERR_UNSUPPORTED, "PVRTC image smaller than one block");
+    const size_t need = static_cast<size_t>(w) * h / 4, src_bytes = static_cast<size_t>(w) * h * 4;
+    if (dst_size != need) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need);
+    if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, src_bytes)) return s;
+    if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need)) return s;
+    if (int s = HostPipe::grow(&pipe.d_scratch, &pipe.scratch_cap, icb_pvrtc2_scratch_size(h, w))) return s;
+    ICB_CUDA(cudaMemcpyAsync(pipe.d_src, src, src_bytes, cudaMemcpyHostToDevice, pipe.compute));
+    if (int s = icb_pvrtc2_encode_rgba8(pipe.d_src, h, w, pipe.d_dst, pipe.d_scratch, pipe.compute)) return s;
+    ICB_CUDA(cudaMemcpyAsync(dst, pipe.d_dst, need, cudaMemcpyDeviceToHost, pipe.compute));
+    ICB_CUDA(cudaStreamSynchronize(pipe.compute));
+    return ICB_OK;
+  }
+
+  const uint32_t coded_h = padded_h > h ? padded_h : h, coded_w = padded_w > w ? padded_w : w;
+  const size_t need = icb_compressed_size(codec, coded_h, coded_w);
+  if (dst_size != need) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need);
+  const size_t host_pitch = static_cast<size_t>(w) * ncomp + padding;
+  // Device copy keeps the caller's pitch when it is already 16-byte aligned (one contiguous copy per chunk, TMA
+  // eligible); otherwise rows are re-pitched to a multiple of 16 by cudaMemcpy2D.
+  const size_t row_bytes = static_cast<size_t>(w) * ncomp;
+  const bool keep_pitch = host_pitch % 16 == 0;
+  const size_t dev_pitch = keep_pitch ? host_pitch : (row_bytes + 15) / 16 * 16;
+  if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, dev_pitch * h)) return s;
+  if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need)) return s;
+
+  const uint32_t grid_rows = (coded_h + 3) / 4, grid_cols = (coded_w + 3) / 4;
+  const size_t block_bytes = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  // Chunks of whole block rows, about 16 MiB of source each, at most kMaxChunks.
+  uint32_t chunks = static_cast<uint32_t>((dev_pitch * h + (16u << 20) - 1) / (16u << 20));
+  if (chunks < 1) chunks = 1;
+  if (chunks > HostPipe::kMaxChunks) chunks = HostPipe::kMaxChunks;
+  if (chunks > grid_rows) chunks = grid_rows;
+  const uint32_t rows_per_chunk = (grid_rows + chunks - 1) / chunks;
+  const uint8_t *hsrc = static_cast<const uint8_t *>(src);
+  uint8_t *hdst = static_cast<uint8_t *>(dst);
+  uint32_t chunk = 0;
+  for (uint32_t r0 = 0; r0 < grid_rows; r0 += rows_per_chunk, ++chunk) {
+    const uint32_t r1 = r0 + rows_per_chunk < grid_rows ? r0 + rows_per_chunk : grid_rows;
+    // Source rows this chunk adds: pixel rows [4*r0, min(4*r1, h)).  Later chunks only ever clamp to row h-1,
+    // which the chunk containing it has already uploaded (chunks run in order on the compute stream).
+    const uint32_t y0 = 4 * r0 < h ? 4 * r0 : h, y1 = 4 * r1 < h ? 4 * r1 : h;
+    if (y1 > y0) {
+      if (keep_pitch) {
+        const size_t bytes = (y1 == h) ? (static_cast<size_t>(y1 - y0 - 1) * host_pitch + row_bytes)
+                                       : static_cast<size_t>(y1 - y0) * host_pitch;
+        ICB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pipe.d_src) + y0 * dev_pitch, hsrc + y0 * host_pitch, bytes,
+                                 cudaMemcpyHostToDevice, pipe.copy_in));
+      } else {
+        ICB_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t *>(pipe.d_src) + y0 * dev_pitch, dev_pitch, hsrc + y0 * host_pitch,
+                                   host_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, pipe.copy_in));
+      }
+    }
+    ICB_CUDA(cudaEventRecord(pipe.in_done[chunk], pipe.copy_in));
+    ICB_CUDA(cudaStreamWaitEvent(pipe.compute, pipe.in_done[chunk], 0));
+    uint8_t *d_out = static_cast<uint8_t *>(pipe.d_dst) + static_cast<size_t>(r0) * grid_cols * block_bytes;
+    if (int s = encode4x4(codec, ncomp, pipe.d_src, h, w, dev_pitch, coded_h, coded_w, swap_rb, strategy, r0, r1, d_out,
+                          pipe.compute))
+      return s;
+    ICB_CUDA(cudaEventRecord(pipe.enc_done[chunk], pipe.compute));
+    ICB_CUDA(cudaStreamWaitEvent(pipe.copy_out, pipe.enc_done[chunk], 0));
+    const size_t out_off = static_cast<size_t>(r0) * grid_cols * block_bytes;
+    ICB_CUDA(cudaMemcpyAsync(hdst + out_off, d_out, static_cast<size_t>(r1 - r0) * grid_cols * block_bytes,
+                             cudaMemcpyDeviceToHost, pipe.copy_out));
+  }
+  ICB_CUDA(cudaStreamSynchronize(pipe.copy_out));
+  ICB_CUDA(cudaStreamSynchronize(pipe.compute));
+  return ICB_OK;
+}
+
+}  // extern "C"

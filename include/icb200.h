@@ -1,0 +1,139 @@
+/*
+ * icb200.h -- C ABI of the B200 (sm_100a) texture-block encoder: the drop-in boundary for the compress path of
+ * google/image-compression.
+ *
+ * What each entry point replaces (paths relative to /root/reference/image_compression/):
+ *
+ *   icb_dxt1_encode_rgb8 / icb_dxt5_encode_rgba8
+ *       the block loop + encoders behind DxtcCompressor::Compress / CompressAndPad
+ *       (internal/dxtc_compressor.cc:735-750, 799-818 -> internal/compressor4x4_helper.h:175-216, 479-520)
+ *   icb_dxt1_encode_rgba8
+ *       same DXT1 encoder fed from a 4-byte-per-pixel source with alpha ignored -- an extension needed by the
+ *       headline metric ("DXT1 of RGBA8"); the reference can only reach it by stripping alpha first
+ *       
+ *   icb_etc1_encode_rgb8
+ *       EtcCompressor::Compress / CompressAndPad (internal/etc_compressor.cc:747-758, 787-800)
+ *   icb_pvrtc2_encode_rgba8
+ *       CompressPVRTC_RGBA_2BPP behind PvrtcCompressor::Compress (internal/pvrtc_compressor.cc:586-597, 636-667)
+ *   icb_compress_host
+ *       what XxxCompressor::Compress hands its buffer to: host pixels in, host blocks out
+ *   icb_compressed_size
+ *       ComputeCompressedDataSize (dxtc_compressor.cc:725-733, etc_compressor.cc:734-745, pvrtc_compressor.cc:631-634)
+ *
+ * Conventions: plain pointers and sizes only; every function returns ICB_OK (0) or a negative icb_status and
+ * never throws; (height, width) argument order as in the reference API; device pointers are ordinary CUDA device
+ * pointers on the current device; `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device
+ * entry points are asynchronous with respect to the host.  There is no CPU fallback: without a usable CUDA
+ * device every compute entry point fails with ICB_ERR_CUDA.
+ */
+#ifndef ICB200_H_
+#define ICB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ICB_API __attribute__((visibility("default")))
+#else
+#define ICB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICB_ABI_VERSION 1
+
+typedef enum icb_status {
+  ICB_OK = 0,
+  ICB_ERR_INVALID = -1,     /* null pointer, zero dimension, unsupported format for the codec ...          */
+  ICB_ERR_CUDA = -2,        /* a CUDA call failed; icb_last_error() has the text                            */
+  ICB_ERR_SIZE = -3,        /* destination buffer size does not match the required size                     */
+  ICB_ERR_UNSUPPORTED = -4  /* shape the codec rejects (PVRTC: non power-of-two / non-square / padded rows)  */
+} icb_status;
+
+typedef enum icb_codec { ICB_CODEC_DXT1 = 0, ICB_CODEC_DXT5 = 1, ICB_CODEC_ETC1 = 2, ICB_CODEC_PVRTC2 = 3 } icb_codec;
+
+/* Same numbering as CompressedImage::Format (public/compressed_image.h:35-40). */
+typedef enum icb_format { ICB_RGB = 0, ICB_BGR = 1, ICB_RGBA = 2, ICB_BGRA = 3 } icb_format;
+
+/* Same numbering as EtcCompressor::CompressionStrategy (public/etc_compressor.h:57-62). */
+typedef enum icb_etc_strategy {
+  ICB_ETC_SPLIT_HORIZONTALLY = 0,
+  ICB_ETC_SPLIT_VERTICALLY = 1,
+  ICB_ETC_SMALLER_ERROR = 2,
+  ICB_ETC_HEURISTIC = 3
+} icb_etc_strategy;
+
+ICB_API int icb_abi_version(void);
+/* Thread-local description of the last failure on the calling thread ("" if none). */
+ICB_API const char *icb_last_error(void);
+/* Number of visible CUDA devices, or a negative icb_status. */
+ICB_API int icb_device_count(void);
+
+/* Bytes of packed blocks for an image whose block grid covers coded_height x coded_width pixels. */
+ICB_API size_t icb_compressed_size(int codec, uint32_t coded_height, uint32_t coded_width);
+
+/*
+ * Device-resident encoders.  d_src: pixel (0,0) of a height x width image with src_pitch bytes per row.
+ * The block grid covers coded_height x coded_width pixels (>= height, width; equal for Compress, the padded size
+ * for CompressAndPad); windows beyond the image replicate its last row / column.  d_dst receives
+ * ceil(coded_height/4) * ceil(coded_width/4) blocks in raster order.  swap_rb selects kBGR / kBGRA.
+ */
+ICB_API int icb_dxt1_encode_rgb8(const void *d_src, uint32_t height, uint32_t width, size_t src_pitch, uint32_t coded_height,
+                         uint32_t coded_width, int swap_rb, void *d_dst, void *stream);
+ICB_API int icb_dxt1_encode_rgba8(const void *d_src, uint32_t height, uint32_t width, size_t src_pitch, uint32_t coded_height,
+                          uint32_t coded_width, int swap_rb, void *d_dst, void *stream);
+ICB_API int icb_dxt5_encode_rgba8(const void *d_src, uint32_t height, uint32_t width, size_t src_pitch, uint32_t coded_height,
+                          uint32_t coded_width, int swap_rb, void *d_dst, void *stream);
+ICB_API int icb_etc1_encode_rgb8(const void *d_src, uint32_t height, uint32_t width, size_t src_pitch, uint32_t coded_height,
+                         uint32_t coded_width, int strategy, void *d_dst, void *stream);
+
+/*
+ * Row-stripe form of the three encoders above, for sharding one image over several GPUs: encodes only block rows
+ * [block_row_begin, block_row_end) of the grid.  d_src still points at pixel (0,0) of the WHOLE image (rows the
+ * stripe does not touch need not be resident); d_dst points at the first block of the stripe.
+ */
+ICB_API int icb_encode4x4_stripe(int codec, int format_components, const void *d_src, uint32_t height, uint32_t width,
+                         size_t src_pitch, uint32_t coded_height, uint32_t coded_width, int swap_rb, int etc_strategy,
+                         uint32_t block_row_begin, uint32_t block_row_end, void *d_dst, void *stream);
+
+/*
+ * PVRTC1 2 bpp.  width == height, power of two, >= 8; rows contiguous.  d_dst receives width*height/4 bytes
+ * (blocks in Z-order).  d_scratch: icb_pvrtc2_scratch_size() bytes of device memory, or NULL to let the library
+ * allocate it stream-ordered.
+ */
+ICB_API size_t icb_pvrtc2_scratch_size(uint32_t height, uint32_t width);
+ICB_API int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t height, uint32_t width, void *d_dst, void *d_scratch,
+                            void *stream);
+
+/*
+ * Host-buffer path: validates like the reference's Compress / CompressAndPad, stages src to the device in
+ * chunks overlapped with the kernels, and copies the blocks back.  padded_height / padded_width: 0 for Compress.
+ * dst_size must equal the required size exactly (ICB_ERR_SIZE otherwise), mirroring SetUpCompressedImage
+ * (internal/compressor4x4_helper.cc:22-43).  Blocking.  Pinned src/dst (icb_host_alloc) avoids a staging copy.
+ */
+ICB_API int icb_compress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t padded_height,
+                      uint32_t padded_width, uint32_t padding_bytes_per_row, int etc_strategy, const void *src,
+                      void *dst, size_t dst_size);
+
+/* Page-locked host memory for icb_compress_host callers. */
+ICB_API void *icb_host_alloc(size_t bytes);
+ICB_API void icb_host_free(void *p);
+
+/*
+ * Synthetic input stream S(seed): fills d_dst[0..bytes) with bytes byte_offset.. of the
+ * stream, so any stripe can be generated in place on its GPU.
+ */
+ICB_API int icb_fill_synthetic(void *d_dst, size_t bytes, uint64_t seed, uint64_t byte_offset, void *stream);
+
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+ICB_API uint64_t icb_launch_count(void);
+
+/* Force (1) or forbid (0) the TMA fast path for testing; -1 restores automatic selection.  Returns previous. */
+ICB_API int icb_set_tma_mode(int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICB200_H_ */

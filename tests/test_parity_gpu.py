@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the reference-generated
+golden fixtures.  Bit-exact (integer/byte work): every comparison is array_equal."""
+import numpy as np
+import pytest
+import torch
+
+import checkers as ck
+import imagegen
+
+pytestmark = pytest.mark.gpu
+
+CODEC = {"dxt1": 0, "dxt5": 1, "etc1": 2, "pvrtc": 3}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_encode(icb, codec, fmt, buf, h, w, pitch=None, coded=None, strategy=2, tma=-1):
+    prev = icb.set_tma_mode(tma)
+    try:
+        ch, cw = coded if coded else (h, w)
+        out = icb.encode_device(codec, fmt, dev(buf), h, w, pitch=pitch, coded_h=max(h, ch), coded_w=max(w, cw), strategy=strategy)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+    finally:
+        icb.set_tma_mode(prev)
+
+
+def golden_codec(meta):
+    if meta["codec"] == "dxt":
+        return CODEC["dxt1"] if meta["ncomp"] == 3 else CODEC["dxt5"]
+    return CODEC["etc1"] if meta["codec"] == "etc" else CODEC["pvrtc"]
+
+
+def test_golden_device_path(icb, golden):
+    """Every reference-generated fixture through the device entry points (generic driver: tiny, odd shapes)."""
+    for meta, buf, want in golden:
+        h, w = meta["h"], meta["w"]
+        pitch = w * meta["ncomp"] + meta["padding"]
+        got = gpu_encode(icb, golden_codec(meta), meta["format"], buf, h, w, pitch=pitch, coded=meta["padded"], strategy=meta["strategy"])
+        assert np.array_equal(got, want), meta
+
+
+def test_golden_host_path(icb, golden):
+    """Same fixtures through icb_compress_host (host buffers, H2D/D2H inside the call)."""
+    for meta, buf, want in golden:
+        got = icb.compress_host(golden_codec(meta), meta["format"], np.ascontiguousarray(buf), meta["h"], meta["w"],
+                                padded=meta["padded"], padding=meta["padding"], strategy=meta["strategy"])
+        assert np.array_equal(got, want), meta
+
+
+@pytest.mark.parametrize("fmt", [ck.RGB, ck.BGR, ck.RGBA, ck.BGRA])
+@pytest.mark.parametrize("tma", [0, 1])
+def test_dxt_vs_oracle(icb, fmt, tma):
+    nc = ck.ncomp(fmt)
+    codec = CODEC["dxt1"] if nc == 3 else CODEC["dxt5"]
+    for kind in imagegen.KINDS:
+        # widths are multiples of 4 with 16-byte aligned pitch so that tma=1 is legal; heights are ragged
+        for (h, w) in ((64, 256), (37, 512), (130, 64), (16, 1028)):
+            if tma == 1 and (w * nc) % 16 != 0:
+                continue
+            img = imagegen.make(kind, h, w, nc, seed=11)
+            got = gpu_encode(icb, codec, fmt, img.ravel(), h, w, tma=tma)
+            assert np.array_equal(got, ck.oracle_dxt(fmt, img.ravel(), h, w)), (kind, h, w)
+
+
+@pytest.mark.parametrize("swap", [0, 1])
+@pytest.mark.parametrize("tma", [0, 1])
+def test_dxt1_from_rgba_extension(icb, swap, tma):
+    fmt = ck.BGRA if swap else ck.RGBA
+    for kind in imagegen.KINDS:
+        for (h, w) in ((64, 256), (37, 516), (5, 8)):
+            img = imagegen.make(kind, h, w, 4, seed=12)
+            got = gpu_encode(icb, CODEC["dxt1"], fmt, img.ravel(), h, w, tma=tma)
+            assert np.array_equal(got, ck.oracle_dxt1_rgba(img.ravel(), h, w, swap_rb=swap)), (kind, h, w)
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3])
+@pytest.mark.parametrize("tma", [0, 1])
+def test_etc1_vs_oracle(icb, strategy, tma):
+    for kind in imagegen.KINDS:
+        for (h, w) in ((32, 64), (21, 128), (64, 272)):
+            img = imagegen.make(kind, h, w, 3, seed=13)
+            got = gpu_encode(icb, CODEC["etc1"], ck.RGB, img.ravel(), h, w, strategy=strategy, tma=tma)
+            assert np.array_equal(got, ck.oracle_etc1(strategy, img.ravel(), h, w)), (kind, h, w)
+
+
+def test_ragged_sizes_and_padding(icb):
+    """Widths/heights that are not multiples of 4, odd row padding (unaligned pitch), CompressAndPad grids."""
+    for fmt in (ck.RGB, ck.BGRA):
+        nc = ck.ncomp(fmt)
+        codec = CODEC["dxt1"] if nc == 3 else CODEC["dxt5"]
+        for (h, w, padding, coded) in ((1, 1, 0, None), (3, 3, 1, None), (9, 13, 7, None), (70, 258, 0, None),
+                                       (70, 258, 0, (96, 300)), (8, 8, 0, (8, 40)), (8, 8, 0, (40, 8)), (33, 67, 5, (64, 128))):
+            img = imagegen.make("smooth_noise", h, w, nc, seed=14)
+            buf, pitch = imagegen.with_row_padding(img, padding)
+            got = gpu_encode(icb, codec, fmt, buf, h, w, pitch=pitch, coded=coded)
+            ch, cw = coded if coded else (None, None)
+            assert np.array_equal(got, ck.oracle_dxt(fmt, buf, h, w, ch, cw, padding)), (fmt, h, w, padding, coded)
+    img = imagegen.make("random", 33, 67, 3, seed=15)
+    buf, pitch = imagegen.with_row_padding(img, 3)
+    got = gpu_encode(icb, CODEC["etc1"], ck.RGB, buf, 33, 67, pitch=pitch, coded=(64, 128))
+    assert np.array_equal(got, ck.oracle_etc1(2, buf, 33, 67, 64, 128, 3))
+
+
+def test_tma_path_ragged_edges_aligned_pitch(icb):
+    """TMA path with image edges that cut through blocks (clamp inside the tile) and a padded, aligned pitch."""
+    for fmt, nc in ((ck.RGBA, 4), (ck.RGB, 3)):
+        codec = CODEC["dxt5"] if nc == 4 else CODEC["dxt1"]
+        for (h, w) in ((67, 1000), (258, 260), (19, 2052)):
+            if nc == 3 and w % 4:
+                continue
+            img = imagegen.make("gradient", h, w, nc, seed=16)
+            padding = (-w * nc) % 16 + 32
+            buf, pitch = imagegen.with_row_padding(img, padding)
+            got = gpu_encode(icb, codec, fmt, buf, h, w, pitch=pitch, tma=1)
+            assert np.array_equal(got, ck.oracle_dxt(fmt, buf, h, w, None, None, padding)), (fmt, h, w)
+    img = imagegen.make("random", 67, 1001, 4, seed=17)  # width not a multiple of 4, RGBA: TMA still legal
+    buf, pitch = imagegen.with_row_padding(img, 12)
+    got = gpu_encode(icb, CODEC["dxt5"], ck.RGBA, buf, 67, 1001, pitch=pitch, tma=1)
+    assert np.array_equal(got, ck.oracle_dxt(ck.RGBA, buf, 67, 1001, None, None, 12))
+
+
+def test_pvrtc_vs_oracle(icb):
+    for s in (8, 16, 64, 256):
+        for kind in imagegen.KINDS:
+            img = imagegen.make(kind, s, s, 4, seed=s + 1)
+            got = icb.pvrtc_encode_device(dev(img.ravel()), s, s).cpu().numpy()
+            assert np.array_equal(got, ck.oracle_pvrtc(img.ravel(), s, s)), (s, kind)
+
+
+def test_pvrtc_rejections(icb):
+    img = dev(np.zeros(16 * 16 * 4, np.uint8))
+    for (h, w) in ((8, 16), (4, 4), (12, 12)):
+        with pytest.raises(icb.IcbError) as e:
+            icb.pvrtc_encode_device(img, h, w)
+        assert e.value.status == -4
+    with pytest.raises(icb.IcbError) as e:
+        icb.compress_host(icb.CODEC_PVRTC2, icb.RGBA, np.zeros(8 * 12 * 4, np.uint8), 8, 8, padding=4)
+    assert e.value.status == -4
+
+
+def test_host_path_size_mismatch(icb):
+    src = np.zeros(16 * 16 * 4, np.uint8)
+    with pytest.raises(icb.IcbError) as e:
+        icb.compress_host(icb.CODEC_DXT5, icb.RGBA, src, 16, 16, out=np.zeros(100, np.uint8))
+    assert e.value.status == -3
+
+
+def test_synthetic_fill_matches_oracle_stream(icb):
+    for (n, seed, off) in ((4096, 1, 0), (1000, 2, 13), (77, 3, 5), (65536 + 3, 2, 8 * 1000 + 1)):
+        buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+        icb.fill_synthetic(buf, seed, off)
+        assert np.array_equal(buf.cpu().numpy(), ck.synthetic(n, seed, off)), (n, seed, off)
+
+
+def test_medium_synthetic_all_codecs(icb):
+    """512^2 synthetic input (the bench's generator) through every codec, TMA path, against the oracle."""
+    n = 512
+    rgb = torch.empty(n * n * 3, dtype=torch.uint8, device="cuda")
+    rgba = torch.empty(n * n * 4, dtype=torch.uint8, device="cuda")
+    icb.fill_synthetic(rgb, 1)
+    icb.fill_synthetic(rgba, 2)
+    h_rgb, h_rgba = rgb.cpu().numpy(), rgba.cpu().numpy()
+    assert np.array_equal(icb.encode_device(0, ck.RGB, rgb, n, n).cpu().numpy(), ck.oracle_dxt(ck.RGB, h_rgb, n, n))
+    assert np.array_equal(icb.encode_device(0, ck.RGBA, rgba, n, n).cpu().numpy(), ck.oracle_dxt1_rgba(h_rgba, n, n))
+    assert np.array_equal(icb.encode_device(1, ck.RGBA, rgba, n, n).cpu().numpy(), ck.oracle_dxt(ck.RGBA, h_rgba, n, n))
+    assert np.array_equal(icb.encode_device(2, ck.RGB, rgb, n, n).cpu().numpy(), ck.oracle_etc1(2, h_rgb, n, n))
+    assert np.array_equal(icb.pvrtc_encode_device(rgba, n, n).cpu().numpy(), ck.oracle_pvrtc(h_rgba, n, n))
+
+
+def test_stripes_equal_whole_image(icb):
+    """Row-stripe sharding: concatenated stripe outputs == single launch, for uneven splits."""
+    h, w = 200, 512
+    for codec, fmt in ((0, ck.RGBA), (1, ck.BGRA), (2, ck.RGB), (0, ck.RGB)):
+        nc = ck.ncomp(fmt)
+        img = dev(imagegen.make("smooth_noise", h, w, nc, seed=18).ravel())
+        whole = icb.encode_device(codec, fmt, img, h, w).cpu().numpy()
+        grid_rows = (h + 3) // 4
+        bb = 16 if codec == 1 else 8
+        for world in (2, 3, 8):
+            parts = []
+            for rank in range(world):
+                r0, r1 = icb.stripe_rows(grid_rows, rank, world)
+                out = torch.empty((r1 - r0) * (w // 4) * bb, dtype=torch.uint8, device="cuda")
+                icb.encode_stripe_device(codec, fmt, img.data_ptr(), h, w, w * nc, h, w, r0, r1, out)
+                parts.append(out.cpu().numpy())
+            assert np.array_equal(np.concatenate(parts), whole), (codec, fmt, world)
+
+
+def test_full_size_properties(icb):
+    """BASELINE.json full sizes, where the scalar oracle would take minutes: size-independent properties.
+    (a) TMA path == generic path byte for byte; (b) block-row translation invariance: encoding rows [k, k+256)
+    as its own image gives the same bytes as that slice of the full output; (c) a random sample of blocks agrees
+    with the oracle applied to just those 4x4 windows."""
+    n = 8192
+    rgba = torch.empty(n * n * 4, dtype=torch.uint8, device="cuda")
+    icb.fill_synthetic(rgba, 2)
+    for codec, bb in ((0, 8), (1, 16)):
+        icb.set_tma_mode(1)
+        fast = icb.encode_device(codec, ck.RGBA, rgba, n, n)
+        icb.set_tma_mode(0)
+        slow = icb.encode_device(codec, ck.RGBA, rgba, n, n)
+        icb.set_tma_mode(-1)
+        assert torch.equal(fast, slow)
+        # (b) rows 4096..5119 as a standalone 1024 x 8192 image
+        sub = rgba[4096 * n * 4:(4096 + 1024) * n * 4]
+        sub_out = icb.encode_device(codec, ck.RGBA, sub, 1024, n)
+        assert torch.equal(sub_out, fast[1024 * (n // 4) * bb:(1024 + 256) * (n // 4) * bb])
+        # (c) 4096 sampled blocks against the oracle
+        rng = np.random.default_rng(3)
+        brs, bcs = rng.integers(0, n // 4, 4096), rng.integers(0, n // 4, 4096)
+        img = rgba.view(n, n, 4)
+        idx_r = torch.from_numpy(brs).cuda()[:, None] * 4 + torch.arange(4, device="cuda")[None, :]
+        idx_c = torch.from_numpy(bcs).cuda()[:, None] * 4 + torch.arange(4, device="cuda")[None, :]
+        windows = img[idx_r[:, :, None], idx_c[:, None, :]].cpu().numpy()  # [4096, 4, 4, 4]
+        strip = np.ascontiguousarray(windows.transpose(1, 0, 2, 3).reshape(4, 4096 * 4, 4))  # one row of blocks
+        want = ck.oracle_dxt1_rgba(strip.ravel(), 4, 4096 * 4) if codec == 0 else ck.oracle_dxt(ck.RGBA, strip.ravel(), 4, 4096 * 4)
+        got = fast.view(n // 4, n // 4, bb)[torch.from_numpy(brs).cuda(), torch.from_numpy(bcs).cuda()].cpu().numpy()
+        assert np.array_equal(got.ravel(), want)
