@@ -1,0 +1,50 @@
+// Compressor: abstract interface of the block-based texture compressors.
+//
+// Interface-compatible with the reference's image_compression/public/compressor.h:46-138.  Source images are
+// 8 bits per component, interleaved RGB (3 bytes) or RGBA (4 bytes), row-major, top row first, with
+// padding_bytes_per_row extra bytes after each row.  Argument order is (height, width) everywhere.  Functions
+// returning a CompressedImage through an out-parameter allocate into a default-constructed instance or fill
+// caller storage of exactly ComputeCompressedDataSize() bytes.  Errors are reported as `false`.
+//
+// In this build Compress() and CompressAndPad() run on the GPU (CUDA, sm_100a) through the C ABI in
+// include/icb200.h; see INTEGRATION.md.
+#ifndef IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_
+#define IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_
+
+#include <stddef.h>
+
+#include <vector>
+
+#include "base/integral_types.h"
+#include "image_compression/public/compressed_image.h"
+
+namespace image_codec_compression {
+
+class Compressor {
+ public:
+  virtual ~Compressor() {}
+
+  virtual bool SupportsFormat(CompressedImage::Format format) const = 0;
+  virtual bool IsValidCompressedImage(const CompressedImage &image) = 0;
+  virtual size_t ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) = 0;
+
+  // The hot path (GPU).
+  virtual bool Compress(CompressedImage::Format format, uint32 height, uint32 width, uint32 padding_bytes_per_row,
+                        const uint8 *buffer, CompressedImage *image) = 0;
+  virtual bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,
+                              uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,
+                              CompressedImage *padded_image) = 0;
+
+  virtual bool Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) = 0;
+  virtual bool Downsample(const CompressedImage &image, CompressedImage *downsampled_image) = 0;
+  virtual bool Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width,
+                   CompressedImage *padded_image) = 0;
+  virtual bool CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,
+                                CompressedImage *image) = 0;
+  virtual bool CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height,
+                            uint32 width, CompressedImage *subimage) = 0;
+};
+
+}  // namespace image_codec_compression
+
+#endif  // IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_

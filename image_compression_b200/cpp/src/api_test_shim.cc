@@ -1,0 +1,62 @@
+// api_test_shim.cc -- extern "C" doorway used by tests/ to drive the C++ Compressor classes of this build exactly
+// the way oracle/ref_shim.cc drives the reference's, so the two can be compared call for call.
+#include <cstring>
+
+#include "image_compression/public/dxtc_compressor.h"
+#include "image_compression/public/etc_compressor.h"
+#include "image_compression/public/pvrtc_compressor.h"
+
+using namespace image_codec_compression;  // NOLINT
+
+namespace {
+long Run(Compressor *c, int format, unsigned h, unsigned w, int pad_mode, unsigned ph, unsigned pw, unsigned padding,
+         const unsigned char *src, unsigned char *dst, size_t dst_cap, unsigned *meta, int external) {
+  const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);
+  CompressedImage owned;
+  CompressedImage outside(dst_cap, dst);
+  CompressedImage *image = external ? &outside : &owned;
+  const bool ok = pad_mode ? c->CompressAndPad(f, h, w, ph, pw, padding, src, image)
+                           : c->Compress(f, h, w, padding, src, image);
+  if (!ok) return 0;
+  if (!external) {
+    if (image->GetDataSize() > dst_cap) return -1;
+    std::memcpy(dst, image->GetData(), image->GetDataSize());
+  }
+  if (meta) {
+    const CompressedImage::Metadata &m = image->GetMetadata();
+    meta[0] = m.format; meta[1] = m.uncompressed_height; meta[2] = m.uncompressed_width;
+    meta[3] = m.compressed_height; meta[4] = m.compressed_width; meta[5] = m.padding_bytes_per_row;
+    meta[6] = static_cast<unsigned>(m.compressor_name.size());
+  }
+  return static_cast<long>(image->GetDataSize());
+}
+}  // namespace
+
+extern "C" {
+__attribute__((visibility("default"))) long icapi_dxt(int format, unsigned h, unsigned w, int pad_mode, unsigned ph,
+                                                      unsigned pw, unsigned padding, const unsigned char *src,
+                                                      unsigned char *dst, size_t dst_cap, unsigned *meta, int external) {
+  DxtcCompressor c;
+  return Run(&c, format, h, w, pad_mode, ph, pw, padding, src, dst, dst_cap, meta, external);
+}
+__attribute__((visibility("default"))) long icapi_etc(int strategy, int format, unsigned h, unsigned w, int pad_mode,
+                                                      unsigned ph, unsigned pw, unsigned padding,
+                                                      const unsigned char *src, unsigned char *dst, size_t dst_cap,
+                                                      unsigned *meta, int external) {
+  EtcCompressor c;
+  c.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  return Run(&c, format, h, w, pad_mode, ph, pw, padding, src, dst, dst_cap, meta, external);
+}
+__attribute__((visibility("default"))) long icapi_pvrtc(int format, unsigned h, unsigned w, unsigned padding,
+                                                        const unsigned char *src, unsigned char *dst, size_t dst_cap,
+                                                        unsigned *meta, int external) {
+  PvrtcCompressor c;
+  return Run(&c, format, h, w, 0, 0, 0, padding, src, dst, dst_cap, meta, external);
+}
+__attribute__((visibility("default"))) size_t icapi_size(int codec, int format, unsigned h, unsigned w) {
+  const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);
+  if (codec == 0) return DxtcCompressor().ComputeCompressedDataSize(f, h, w);
+  if (codec == 1) return EtcCompressor().ComputeCompressedDataSize(f, h, w);
+  return PvrtcCompressor().ComputeCompressedDataSize(f, h, w);
+}
+}

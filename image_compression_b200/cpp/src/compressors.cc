@@ -1,0 +1,210 @@
+// compressors.cc -- the image_codec_compression::{Dxtc,Etc,Pvrtc}Compressor classes of the B200 build.
+//
+// Host-side mirror of the reference's public methods: identical argument checks, metadata and ownership rules
+//   DxtcCompressor::Compress / CompressAndPad   reference internal/dxtc_compressor.cc:735-750, 799-818
+//   EtcCompressor::Compress / CompressAndPad    reference internal/etc_compressor.cc:747-758, 787-800
+//   PvrtcCompressor::Compress                   reference internal/pvrtc_compressor.cc:636-667
+//   SetUpCompressedImage                        reference internal/compressor4x4_helper.cc:22-43
+// ...and then one call through the C ABI (include/icb200.h, icb_compress_host) where the reference ran its
+// per-block CPU loop.  No CPU encoder exists in this library: if the CUDA call fails, Compress returns false.
+#include <algorithm>
+#include <string>
+
+#include "icb200.h"
+#include "image_compression/public/dxtc_compressor.h"
+#include "image_compression/public/dxtc_to_etc_transcoder.h"
+#include "image_compression/public/etc_compressor.h"
+#include "image_compression/public/pvrtc_compressor.h"
+
+namespace image_codec_compression {
+
+namespace {
+
+inline uint32 NumBlocks(uint32 pixels) { return (pixels + 3) / 4; }
+
+// Gives `image` storage for a grid covering coded_height x coded_width and fills its metadata; mirrors
+// SetUpCompressedImage, including the exact-size check for caller-owned storage.
+bool PrepareOutput(const char *name, size_t block_size, CompressedImage::Format format, uint32 coded_height,
+                   uint32 coded_width, uint32 padding_bytes_per_row, CompressedImage *image) {
+  const uint32 rows = NumBlocks(coded_height), cols = NumBlocks(coded_width);
+  const size_t size = static_cast<size_t>(rows) * cols * block_size;
+  const CompressedImage::Metadata meta(format, name, coded_height, coded_width, 4 * rows, 4 * cols,
+                                       padding_bytes_per_row);
+  if (image->OwnsData()) {
+    image->CreateOwnedData(meta, size);
+  } else {
+    if (image->GetDataSize() != size) return false;
+    image->SetMetadata(meta);
+  }
+  return true;
+}
+
+bool Encode4x4(int codec, const char *name, size_t block_size, CompressedImage::Format format, uint32 height,
+               uint32 width, uint32 padded_height, uint32 padded_width, uint32 padding, int strategy,
+               const uint8 *buffer, CompressedImage *image) {
+  // CompressAndPad reports the padded size as the "uncompressed" size (compressor4x4_helper.h:486-492).
+  const uint32 coded_h = std::max(height, padded_height), coded_w = std::max(width, padded_width);
+  if (!PrepareOutput(name, block_size, format, coded_h, coded_w, padding, image)) return false;
+  return icb_compress_host(codec, static_cast<int>(format), height, width, padded_height, padded_width, padding,
+                           strategy, buffer, image->GetMutableData(), image->GetDataSize()) == ICB_OK;
+}
+
+bool IsPowerOfTwo(uint32 x) { return x != 0 && (x & (x - 1)) == 0; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// DXT1 / DXT5
+// ---------------------------------------------------------------------------------------------------------
+
+DxtcCompressor::DxtcCompressor() {}
+DxtcCompressor::~DxtcCompressor() {}
+
+bool DxtcCompressor::SupportsFormat(CompressedImage::Format) const { return true; }
+
+size_t DxtcCompressor::ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) {
+  if (height == 0 || width == 0) return 0;
+  const size_t block = GetNumFormatComponents(format) == 3 ? 8 : 16;
+  return static_cast<size_t>(std::max(1u, NumBlocks(height))) * std::max(1u, NumBlocks(width)) * block;
+}
+
+bool DxtcCompressor::IsValidCompressedImage(const CompressedImage &image) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  return m.compressor_name == "dxtc" && m.uncompressed_height > 0 && m.uncompressed_width > 0 &&
+         m.compressed_height >= m.uncompressed_height && m.compressed_width >= m.uncompressed_width &&
+         image.GetDataSize() == ComputeCompressedDataSize(m.format, m.compressed_height, m.compressed_width);
+}
+
+bool DxtcCompressor::Compress(CompressedImage::Format format, uint32 height, uint32 width,
+                              uint32 padding_bytes_per_row, const uint8 *buffer, CompressedImage *image) {
+  if (!buffer || !image || height == 0 || width == 0) return false;
+  const bool dxt1 = GetNumFormatComponents(format) == 3;
+  return Encode4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, "dxtc", dxt1 ? 8 : 16, format, height, width, 0, 0,
+                   padding_bytes_per_row, 0, buffer, image);
+}
+
+bool DxtcCompressor::CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width,
+                                    uint32 padded_height, uint32 padded_width, uint32 padding_bytes_per_row,
+                                    const uint8 *buffer, CompressedImage *padded_image) {
+  if (!buffer || !padded_image || height == 0 || width == 0) return false;
+  const bool dxt1 = GetNumFormatComponents(format) == 3;
+  return Encode4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, "dxtc", dxt1 ? 8 : 16, format, height, width,
+                   padded_height, padded_width, padding_bytes_per_row, 0, buffer, padded_image);
+}
+
+// Outside the GPU compress path; see DESIGN.md ("next" rows of SURVEY.md section 8f).
+bool DxtcCompressor::Decompress(const CompressedImage &, std::vector<uint8> *) { return false; }
+bool DxtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
+bool DxtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
+bool DxtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
+  return false;
+}
+bool DxtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint32, uint32, CompressedImage *) {
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ETC1
+// ---------------------------------------------------------------------------------------------------------
+
+EtcCompressor::EtcCompressor() : compression_strategy_(kSmallerError) {}
+EtcCompressor::~EtcCompressor() {}
+
+bool EtcCompressor::SupportsFormat(CompressedImage::Format format) const { return format == CompressedImage::kRGB; }
+
+size_t EtcCompressor::ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) {
+  if (height == 0 || width == 0 || format != CompressedImage::kRGB) return 0;
+  return static_cast<size_t>(std::max(1u, NumBlocks(height))) * std::max(1u, NumBlocks(width)) * 8;
+}
+
+bool EtcCompressor::IsValidCompressedImage(const CompressedImage &image) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  return m.format == CompressedImage::kRGB && m.compressor_name == "etc" && m.uncompressed_height > 0 &&
+         m.uncompressed_width > 0 && m.compressed_height >= m.uncompressed_height &&
+         m.compressed_width >= m.uncompressed_width &&
+         image.GetDataSize() == static_cast<size_t>(NumBlocks(m.compressed_height)) * NumBlocks(m.compressed_width) * 8;
+}
+
+bool EtcCompressor::Compress(CompressedImage::Format format, uint32 height, uint32 width,
+                             uint32 padding_bytes_per_row, const uint8 *buffer, CompressedImage *image) {
+  if (!buffer || !image || height == 0 || width == 0 || format != CompressedImage::kRGB) return false;
+  return Encode4x4(ICB_CODEC_ETC1, "etc", 8, format, height, width, 0, 0, padding_bytes_per_row,
+                   static_cast<int>(compression_strategy_), buffer, image);
+}
+
+bool EtcCompressor::CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,
+                                   uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,
+                                   CompressedImage *padded_image) {
+  if (!buffer || !padded_image || height == 0 || width == 0 || format != CompressedImage::kRGB) return false;
+  return Encode4x4(ICB_CODEC_ETC1, "etc", 8, format, height, width, padded_height, padded_width,
+                   padding_bytes_per_row, static_cast<int>(compression_strategy_), buffer, padded_image);
+}
+
+bool EtcCompressor::Decompress(const CompressedImage &, std::vector<uint8> *) { return false; }
+bool EtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
+bool EtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
+bool EtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
+  return false;
+}
+bool EtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint32, uint32, CompressedImage *) {
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PVRTC1 2bpp
+// ---------------------------------------------------------------------------------------------------------
+
+PvrtcCompressor::PvrtcCompressor() {}
+PvrtcCompressor::~PvrtcCompressor() {}
+
+bool PvrtcCompressor::SupportsFormat(CompressedImage::Format format) const { return format == CompressedImage::kRGBA; }
+
+size_t PvrtcCompressor::ComputeCompressedDataSize(CompressedImage::Format, uint32 height, uint32 width) {
+  return static_cast<size_t>(width * height / 4);  // 32-bit product, as in the reference
+}
+
+bool PvrtcCompressor::IsValidCompressedImage(const CompressedImage &image) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  return m.format == CompressedImage::kRGBA && m.compressor_name == "pvrtc" && m.uncompressed_height >= 4 &&
+         m.uncompressed_width >= 8 && m.compressed_width == m.compressed_height &&
+         IsPowerOfTwo(m.uncompressed_height) && IsPowerOfTwo(m.uncompressed_width) &&
+         m.compressed_height == m.uncompressed_height && m.compressed_width == m.uncompressed_width &&
+         image.GetDataSize() == ComputeCompressedDataSize(m.format, m.uncompressed_height, m.uncompressed_width);
+}
+
+bool PvrtcCompressor::Compress(CompressedImage::Format format, uint32 height, uint32 width,
+                               uint32 padding_bytes_per_row, const uint8 *buffer, CompressedImage *image) {
+  if (!buffer || !image || height == 0 || width == 0) return false;
+  if (!IsPowerOfTwo(width) || !IsPowerOfTwo(height) || width != height) return false;
+  if (padding_bytes_per_row != 0) return false;
+  if (width % 8 != 0 || height % 4 != 0) return false;
+  // `format` is recorded but not checked: the pixels are always read as RGBA8888 (pvrtc_compressor.cc:664).
+  const size_t size = ComputeCompressedDataSize(format, height, width);
+  const CompressedImage::Metadata meta(format, "pvrtc", height, width, height, width, 0);
+  if (image->OwnsData()) {
+    image->CreateOwnedData(meta, size);
+  } else {
+    if (image->GetDataSize() != size) return false;
+    image->SetMetadata(meta);
+  }
+  return icb_compress_host(ICB_CODEC_PVRTC2, ICB_RGBA, height, width, 0, 0, 0, 0, buffer, image->GetMutableData(),
+                           size) == ICB_OK;
+}
+
+bool PvrtcCompressor::CompressAndPad(CompressedImage::Format, uint32, uint32, uint32, uint32, uint32, const uint8 *,
+                                     CompressedImage *) {
+  return false;
+}
+bool PvrtcCompressor::Decompress(const CompressedImage &, std::vector<uint8> *) { return false; }
+bool PvrtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
+bool PvrtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
+bool PvrtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
+  return false;
+}
+bool PvrtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint32, uint32, CompressedImage *) {
+  return false;
+}
+
+bool TranscodeDxt1ToEtc1(CompressedImage *) { return false; }
+
+}  // namespace image_codec_compression

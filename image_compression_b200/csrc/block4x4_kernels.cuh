@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + kTmaStages * Shape::kBytes);
   uint64_t *empty_bar = full_bar + kTmaStages;
   constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
+  const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTmaStages; ++s) {
@@ -185,16 +186,22 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     if ((threadIdx.x & 31) == 0) {
       const uint64_t policy = l2_evict_first_policy();
       uint32_t stage = 0, phase = 0;
+      uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&full_bar[stage], Shape::kBytes);
-        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
         tma_load_2d(tiles + stage * Shape::kBytes, &src_map, &full_bar[stage],
                     static_cast<int32_t>((p.col0 + tx * Shape::kBlocksX) * kNcomp),
                     static_cast<int32_t>((p.row0 + ty * Shape::kBlocksY) * 4u), policy);
         if (++stage == kTmaStages) {
           stage = 0;
           phase ^= 1u;
+        }
+        tx += step_x;  // next tile of this CTA: tile + gridDim.x, kept as (tx, ty) without dividing
+        ty += step_y;
+        if (tx >= tiles_x) {
+          tx -= tiles_x;
+          ++ty;
         }
       }
     }
@@ -204,8 +211,8 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
   // ---- consumer warps: thread t owns block (t / kBlocksX, t % kBlocksX) of every tile
   const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
   uint32_t stage = 0, phase = 0;
+  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
   for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const uint32_t br = p.row0 + ty * Shape::kBlocksY + lby, bc = p.col0 + tx * Shape::kBlocksX + lbx;
     const uint32_t *tile_words = reinterpret_cast<const uint32_t *>(tiles + stage * Shape::kBytes);
     mbar_wait(&full_bar[stage], phase);
@@ -254,6 +261,12 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     if (++stage == kTmaStages) {
       stage = 0;
       phase ^= 1u;
+    }
+    tx += step_x;
+    ty += step_y;
+    if (tx >= tiles_x) {
+      tx -= tiles_x;
+      ++ty;
     }
   }
 }

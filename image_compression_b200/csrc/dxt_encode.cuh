@@ -97,54 +97,99 @@ __device__ __noinline__ uint32_t dxt_const_colour(uint32_t t, bool always4, uint
 // Weights for IDP.4A: 16*(4,8,1) on the logical (r,g,b); the alpha byte always gets weight 0.
 __device__ __forceinline__ uint32_t dxt_lum_weights(bool swap_rb) { return swap_rb ? 0x00408010u : 0x00108040u; }
 
+// 565 quantisation straight from a packed pixel.  round(v*31/255) == (v*249 + 1024) >> 11 and
+// round(v*63/255) == (v*253 + 512) >> 10 for every 8-bit v (checked exhaustively in tests/test_host_math.py), so
+// one IDP.4A per channel -- weight in the byte that holds the channel, rounding term in the accumulator --
+// replaces byte extraction, multiply and the two-step Blinn rounding.
+__device__ __forceinline__ uint32_t dxt_to_565(uint32_t p, uint32_t w_red, uint32_t w_blue) {
+  const uint32_t xr = __dp4a(p, w_red, 1024u), xg = __dp4a(p, 0x0000fd00u, 512u), xb = __dp4a(p, w_blue, 1024u);
+  return (xr & 0xf800u) | ((xg >> 5) & 0x07e0u) | (xb >> 11);
+}
+
+__device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
 // Encodes the colour half.  px[i] = pixel i (raster order) as bytes (c0,c1,c2,x) in MEMORY order; the top byte
 // is ignored.  fetch(i) must return px[i] (kept as a functor so callers can re-read shared memory instead of
 // forcing a register-indexed array into local memory).  Returns {c0 | c1<<16, index bits}.
+//
+// Index search.  The reference scores pixel luminance l against the four candidate luminances L_c with
+// (L_c - l)^2 and keeps the first strict minimum (dxtc_compressor.cc:334-345).  On a line that is a nearest-
+// neighbour search, so the answer only changes where l crosses the midpoint of two neighbouring candidates:
+//   * sort the candidates by (L_c, c) once per block (five min/max pairs);
+//   * walking upwards, candidate b replaces the current one a iff 2l > L_a + L_b, or 2l == L_a + L_b and b has the
+//     smaller index (that is what "first strict minimum" does with a tie); candidates with equal luminance are
+//     represented by their smallest index;
+//   * per pixel, each of the three crossings is one saturating float add (1.0 if crossed, else 0.0) and one
+//     float multiply-add that accumulates the index change -- exact, since every value is an integer below 2^24,
+//     and it runs on the FMA pipes while the integer pipe, which bounds this kernel, only does the final bit
+//     insert.  The pixel value 2^23 + 16*l + i is produced directly in float format by the IDP.4A that computes
+//     the luminance (accumulator 0x4B000000 + i), so no int->float conversion is needed.
 template <typename Fetch>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
-  uint32_t key[16];
+  uint32_t kf[16];  // 0x4B000000 + 16*lum + i: as an integer a (lum, index) key, as a float 2^23 + 16*lum + i
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) key[i] = __dp4a(px[i], w16, static_cast<uint32_t>(i));
-
-  uint32_t kmin = key[0], kmax = key[0] ^ 15u;
-#pragma unroll
-  for (int i = 1; i < 16; ++i) {
-    kmin = min(kmin, key[i]);
-    kmax = max(kmax, key[i] ^ 15u);
+  for (int i = 0; i < 16; ++i) {
+    kf[i] = __dp4a(px[i], w16, 0x4b000000u + static_cast<uint32_t>(i));
+    kmin = min(kmin, kf[i]);                                                // first minimum in raster order
+    kmax = max(kmax, __dp4a(px[i], w16, 15u - static_cast<uint32_t>(i)));   // first maximum in raster order
   }
-  // Base colours = first pixel of minimum / maximum luminance; brought into logical (r,g,b) byte order.
-  uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);
-  if (swap_rb) {
-    p0 = __byte_perm(p0, 0u, 0x3012);
-    p1 = __byte_perm(p1, 0u, 0x3012);
-  }
-  uint32_t lum0 = kmin & ~15u, lum1 = kmax & ~15u;  // 16 * luminance of p0 / p1
-  uint32_t c0 = to_565(p0 & 255u, (p0 >> 8) & 255u, (p0 >> 16) & 255u);
-  uint32_t c1 = to_565(p1 & 255u, (p1 >> 8) & 255u, (p1 >> 16) & 255u);
+  uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
+  uint32_t lum0 = kmin & 0x000ffff0u, lum1 = kmax & 0x000ffff0u;   // 16 * luminance of p0 / p1
+  const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
+  uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
   uint32_t bits;
   if (c0 == c1) {
-    // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. looks up the
+    // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
     // memory-order colour.
-    const uint32_t target = swap_rb ? __byte_perm(p0, 0u, 0x3012) : p0;
-    bits = dxt_const_colour(target, always4, &c0, &c1) * 0x55555555u;
+    bits = dxt_const_colour(p0, always4, &c0, &c1) * 0x55555555u;
   } else {
     if (c0 < c1) {
       uint32_t t = p0; p0 = p1; p1 = t;
       t = c0; c0 = c1; c1 = t;
       t = lum0; lum0 = lum1; lum1 = t;
     }
-    // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation.
-    const uint32_t r0 = p0 & 255u, g0 = (p0 >> 8) & 255u, b0 = (p0 >> 16) & 255u;
-    const uint32_t r1 = p1 & 255u, g1 = (p1 >> 8) & 255u, b1 = (p1 >> 16) & 255u;
-    const uint32_t lum2 = 64u * div3_small(2u * r0 + r1) + 128u * div3_small(2u * g0 + g1) + 16u * div3_small(2u * b0 + b1);
-    const uint32_t lum3 = 64u * div3_small(r0 + 2u * r1) + 128u * div3_small(g0 + 2u * g1) + 16u * div3_small(b0 + 2u * b1);
+    // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
+    // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
+    const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
+    const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
+    const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
+    constexpr uint32_t kThird = 683u << 21;
+    const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
+                          16u * __umulhi(2u * b0 + b1, kThird);
+    const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
+                          16u * __umulhi(b0 + 2u * b1, kThird);
+    // Candidates as keys 16*L_c + c, sorted ascending.
+    uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
+    sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
+    const uint32_t sorted[4] = {s0, s1, s2, s3};
+    uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
+    float acc0 = __uint_as_float(0x4b000000u + (s0 & 3u));  // 2^23 + index of the lowest candidate
+    float cross[3], step[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t b = sorted[j + 1];
+      const bool same_lum = (b - rep) < 4u;             // keys differ only in the index bits
+      const uint32_t cb = b & 3u, cr = rep & 3u;
+      // pixel key v = 16*l + i crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
+      const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
+      cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : 0x4b000000u + h - 1u);
+      step[j] = same_lum ? 0.0f : static_cast<float>((cb - cr) & 3u);
+      rep = same_lum ? rep : b;
+    }
     bits = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const uint32_t l = key[i] & ~15u;
-      const uint32_t k = min(min(__usad(lum0, l, 0u), __usad(lum1, l, 1u)), min(__usad(lum2, l, 2u), __usad(lum3, l, 3u)));
-      bits = __funnelshift_r(bits, k, 2);  // low two bits of k = chosen index
+      const float v = __uint_as_float(kf[i]);
+      float acc = fmaf(__saturatef(v - cross[0]), step[0], acc0);
+      acc = fmaf(__saturatef(v - cross[1]), step[1], acc);
+      acc = fmaf(__saturatef(v - cross[2]), step[2], acc);
+      bits = __funnelshift_r(bits, __float_as_uint(acc), 2);  // low two mantissa bits = chosen index (mod 4)
     }
   }
   return make_uint2(c0 | (c1 << 16), bits);
