@@ -107,35 +107,38 @@ __global__ void __launch_bounds__(128) encode4x4_generic_kernel(const Encode4x4P
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// mbarrier / TMA primitives; every address is a 32-bit shared-window address computed once per kernel.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Blocks until the barrier's phase with the given parity has completed.  The suspend-time hint lets the hardware
+// park the warp instead of spinning through the issue slots the encoder warps need.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(0x989680)
       : "memory");
 }
 // 2-D tiled bulk tensor load, global -> shared, completion on an mbarrier; streaming (evict-first) L2 policy.
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t x, int32_t y,
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, uint32_t bar, int32_t x, int32_t y,
                                             uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(policy)
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -157,40 +160,40 @@ struct TileShape {
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
 };
 
-constexpr int kTmaStages = 4;
-
-template <int kCodec, int kNcomp>
+template <int kCodec, int kNcomp, int kTmaStages>
 __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                          uint32_t num_tiles) {
   using Shape = TileShape<kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t *tiles = smem_raw;  // kTmaStages * Shape::kBytes
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + kTmaStages * Shape::kBytes);
-  uint64_t *empty_bar = full_bar + kTmaStages;
+  // layout: kTmaStages tiles, then kTmaStages "full" barriers, then kTmaStages "empty" barriers
+  // (kTmaStages trades bytes in flight per CTA against resident CTAs per SM; the launcher picks)
+  const uint32_t tiles_s = smem_u32(smem_raw);
+  const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, empty_s = full_s + kTmaStages * 8;
   constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
+  constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTmaStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
+      mbar_init(full_s + 8 * s, 1);
+      mbar_init(empty_s + 8 * s, kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
+  uint32_t stage = 0, phase = 0;
+  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
   const uint32_t warp = threadIdx.x >> 5;
   if (warp == kConsumerWarps) {
     // ---- producer warp: one lane streams this CTA's tiles through the ring
     if ((threadIdx.x & 31) == 0) {
       const uint64_t policy = l2_evict_first_policy();
-      uint32_t stage = 0, phase = 0;
-      uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], Shape::kBytes);
-        tma_load_2d(tiles + stage * Shape::kBytes, &src_map, &full_bar[stage],
+        mbar_wait(empty_s + 8 * stage, phase ^ 1u);
+        mbar_arrive_expect_tx(full_s + 8 * stage, Shape::kBytes);
+        tma_load_2d(tiles_s + stage * Shape::kBytes, &src_map, full_s + 8 * stage,
                     static_cast<int32_t>((p.col0 + tx * Shape::kBlocksX) * kNcomp),
                     static_cast<int32_t>((p.row0 + ty * Shape::kBlocksY) * 4u), policy);
         if (++stage == kTmaStages) {
@@ -210,54 +213,59 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
 
   // ---- consumer warps: thread t owns block (t / kBlocksX, t % kBlocksX) of every tile
   const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
-  uint32_t stage = 0, phase = 0;
-  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const uint32_t own_off = (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;  // byte offset of the window in a tile
   for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint32_t br = p.row0 + ty * Shape::kBlocksY + lby, bc = p.col0 + tx * Shape::kBlocksX + lbx;
-    const uint32_t *tile_words = reinterpret_cast<const uint32_t *>(tiles + stage * Shape::kBytes);
-    mbar_wait(&full_bar[stage], phase);
+    const uint32_t tile_br = p.row0 + ty * Shape::kBlocksY, tile_bc = p.col0 + tx * Shape::kBlocksX;
+    const uint8_t *tile_bytes = smem_raw + stage * Shape::kBytes;
+    // Whole tile inside the image and inside this launch's block range: no clamping, no bounds checks.
+    const bool tile_inside = (tile_br + Shape::kBlocksY) * 4u <= p.height && (tile_bc + Shape::kBlocksX) * 4u <= p.width &&
+                             tile_br + Shape::kBlocksY <= p.row1 && tile_bc + Shape::kBlocksX <= p.col1;
+    // Last valid row / column, tile-relative, for clamp-to-edge replication.  The clamped coordinate never
+    // leaves the tile because every encoded window starts inside the image.
+    const uint32_t ymax = min(p.height - 1u - tile_br * 4u, static_cast<uint32_t>(Shape::kRows - 1));
+    const uint32_t xmax = min(p.width - 1u - tile_bc * 4u, static_cast<uint32_t>(Shape::kBlocksX * 4 - 1));
+    auto fetch = [&](uint32_t i) {
+      const uint32_t y = min(lby * 4u + (i >> 2), ymax), x = min(lbx * 4u + (i & 3u), xmax);
+      if constexpr (kNcomp == 4) {
+        return *reinterpret_cast<const uint32_t *>(tile_bytes + (y * Shape::kRowWords + x) * 4u);
+      } else {
+        const uint8_t *q = tile_bytes + y * (Shape::kRowWords * 4) + x * 3u;
+        return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
+      }
+    };
+    mbar_wait(full_s + 8 * stage, phase);
 
-    if (br < p.row1 && bc < p.col1) {
-      uint32_t px[16];
-      const bool interior = 4u * br + 4u <= p.height && 4u * bc + 4u <= p.width;
-      if (interior) {
+    uint32_t px[16];
+    bool active = true;
+    if (tile_inside) {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          const uint32_t *row = tile_words + (lby * 4 + y) * Shape::kRowWords + lbx * kNcomp;
-          if constexpr (kNcomp == 4) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(row);
-            px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
-          } else {
-            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];  // 12 bytes = four packed RGB pixels
-            px[4 * y + 0] = w0 & 0x00ffffffu;
-            px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
-            px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
-            px[4 * y + 3] = w2 >> 8;
-          }
+      for (int y = 0; y < 4; ++y) {
+        const uint8_t *row = tile_bytes + own_off + y * (Shape::kRowWords * 4);
+        if constexpr (kNcomp == 4) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(row);
+          px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
+        } else {
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(row);  // 12 bytes = four packed RGB pixels
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          px[4 * y + 0] = w0 & 0x00ffffffu;
+          px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+          px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
+          px[4 * y + 3] = w2 >> 8;
         }
       }
-      // Pixel i of this thread's window, read back from the tile with clamp-to-edge replication.  The clamped
-      // coordinate never leaves the tile because the window's origin is inside the image.
-      const uint32_t ymax = p.height - 1u - (p.row0 + ty * Shape::kBlocksY) * 4u;  // last valid row, tile-relative
-      const uint32_t xmax = p.width - 1u - (p.col0 + tx * Shape::kBlocksX) * 4u;
-      auto fetch = [&](uint32_t i) {
-        const uint32_t y = min(lby * 4u + (i >> 2), ymax), x = min(lbx * 4u + (i & 3u), xmax);
-        if constexpr (kNcomp == 4) {
-          return tile_words[y * Shape::kRowWords + x];
-        } else {
-          const uint8_t *q = reinterpret_cast<const uint8_t *>(tile_words) + y * (Shape::kRowWords * 4) + x * 3u;
-          return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
-        }
-      };
-      if (!interior) {
+    } else {
+      active = tile_br + lby < p.row1 && tile_bc + lbx < p.col1;
+      if (active) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) px[i] = fetch(i);
       }
-      uint8_t *out = p.dst + (static_cast<size_t>(br) * p.grid_cols + bc) * CodecTraits<kCodec>::kBlockBytes;
+    }
+    if (active) {
+      uint8_t *out = p.dst + (static_cast<size_t>(tile_br + lby) * p.grid_cols + tile_bc + lbx) * kBlockBytes;
       encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, out);
     }
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[stage]);
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
     if (++stage == kTmaStages) {
       stage = 0;
       phase ^= 1u;

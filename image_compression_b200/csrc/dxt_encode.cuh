@@ -50,8 +50,10 @@ __device__ __forceinline__ uint32_t lum_of_diff_sq(uint32_t tr, uint32_t tg, uin
 }
 
 // Constant-colour block (rare path, divergent by design).  `t` is the target colour as (r,g,b) bytes.
-// Returns the 2-bit index to replicate; writes the two 565 endpoints.
-__device__ __noinline__ uint32_t dxt_const_colour(uint32_t t, bool always4, uint32_t *c0_out, uint32_t *c1_out) {
+// Returns c0 | c1 << 16 | index << 32: the two 565 endpoints and the 2-bit index to replicate.  (Packed return
+// value: pointer out-parameters of a non-inlined function would force the caller's registers through local
+// memory on every block, not just on constant ones.)
+__device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
   const uint32_t tr = t & 255u, tg = (t >> 8) & 255u, tb = (t >> 16) & 255u;
   const uint32_t qr = quant_round(tr, 31u), qg = quant_round(tg, 63u), qb = quant_round(tb, 31u);
   uint32_t c0 = (qr << 11) | (qg << 5) | qb, c1 = c0, which = 0;
@@ -89,9 +91,7 @@ __device__ __noinline__ uint32_t dxt_const_colour(uint32_t t, bool always4, uint
       }
     }
   }
-  *c0_out = c0;
-  *c1_out = c1;
-  return which;
+  return c0 | (c1 << 16) | (static_cast<uint64_t>(which) << 32);
 }
 
 // Weights for IDP.4A: 16*(4,8,1) on the logical (r,g,b); the alpha byte always gets weight 0.
@@ -137,17 +137,20 @@ __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], boo
   for (int i = 0; i < 16; ++i) {
     kf[i] = __dp4a(px[i], w16, 0x4b000000u + static_cast<uint32_t>(i));
     kmin = min(kmin, kf[i]);                                                // first minimum in raster order
-    kmax = max(kmax, __dp4a(px[i], w16, 15u - static_cast<uint32_t>(i)));   // first maximum in raster order
+    kmax = max(kmax, kf[i] ^ 15u);  // index field reversed: first maximum in raster order
   }
   uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
-  uint32_t lum0 = kmin & 0x000ffff0u, lum1 = kmax & 0x000ffff0u;   // 16 * luminance of p0 / p1
+  uint32_t lum0 = kmin & 0x000ffff0u, lum1 = kmax & 0x000ffff0u;  // 16 * luminance of p0 / p1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
   uint32_t bits;
   if (c0 == c1) {
     // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
     // memory-order colour.
-    bits = dxt_const_colour(p0, always4, &c0, &c1) * 0x55555555u;
+    const uint64_t packed = dxt_const_colour(p0, always4);
+    c0 = static_cast<uint32_t>(packed) & 0xffffu;
+    c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
+    bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
   } else {
     if (c0 < c1) {
       uint32_t t = p0; p0 = p1; p1 = t;
@@ -179,7 +182,7 @@ __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], boo
       // pixel key v = 16*l + i crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
       const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
       cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : 0x4b000000u + h - 1u);
-      step[j] = same_lum ? 0.0f : static_cast<float>((cb - cr) & 3u);
+      step[j] = static_cast<float>((cb - cr) & 3u);  // irrelevant when same_lum: that crossing never fires
       rep = same_lum ? rep : b;
     }
     bits = 0;

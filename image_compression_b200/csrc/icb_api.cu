@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -112,27 +113,41 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
 
-  auto kernel = icb::encode4x4_tma_kernel<kCodec, kNcomp>;
+  // Ring depth: 3 or 4 stages.  Fewer stages leave shared memory for one more resident CTA per SM; pick the
+  // depth that gives the most resident warps (ties -> deeper ring).  ICB_TMA_STAGES=3|4 overrides for experiments.
   constexpr int kThreads = Shape::kConsumerThreads + 32;
-  constexpr size_t kSmem = static_cast<size_t>(icb::kTmaStages) * Shape::kBytes + 2 * icb::kTmaStages * sizeof(uint64_t);
-  static thread_local int ctas_per_sm[64] = {0};
+  struct Config {
+    void (*kernel)(const CUtensorMap, const Encode4x4Params, uint32_t, uint32_t);
+    size_t smem;
+    int ctas_per_sm;
+  };
+  static thread_local Config chosen[64] = {};
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
-  if (ctas_per_sm[dev] == 0) {
-    ICB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
-    int occ = 0;
-    ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, kSmem));
-    ctas_per_sm[dev] = occ > 0 ? occ : 1;
+  if (chosen[dev].kernel == nullptr) {
+    Config cand[2] = {{icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * (Shape::kBytes + 16), 0},
+                      {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * (Shape::kBytes + 16), 0}};
+    const char *force = getenv("ICB_TMA_STAGES");
+    int best = -1;
+    for (int c = 0; c < 2; ++c) {
+      ICB_CUDA(cudaFuncSetAttribute(cand[c].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cand[c].smem)));
+      ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cand[c].ctas_per_sm, cand[c].kernel, kThreads, cand[c].smem));
+      if (cand[c].ctas_per_sm < 1) cand[c].ctas_per_sm = 1;
+      if (force && atoi(force) == (c == 0 ? 4 : 3)) best = c;
+    }
+    if (best < 0) best = cand[1].ctas_per_sm > cand[0].ctas_per_sm ? 1 : 0;
+    chosen[dev] = cand[best];
   }
+  const Config cfg = chosen[dev];
   const uint32_t tiles_x = (p.col1 - p.col0 + Shape::kBlocksX - 1) / Shape::kBlocksX;
   const uint32_t tiles_y = (p.row1 - p.row0 + Shape::kBlocksY - 1) / Shape::kBlocksY;
   const uint64_t num_tiles64 = static_cast<uint64_t>(tiles_x) * tiles_y;
   if (num_tiles64 == 0) return ICB_OK;
   if (num_tiles64 > 0xffffffffull) return fail(ICB_ERR_INVALID, "image too large");
   const uint32_t num_tiles = static_cast<uint32_t>(num_tiles64);
-  const uint32_t max_ctas = static_cast<uint32_t>(sm_count * ctas_per_sm[dev]);
+  const uint32_t max_ctas = static_cast<uint32_t>(sm_count * cfg.ctas_per_sm);
   const uint32_t grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  kernel<<<grid, kThreads, kSmem, stream>>>(map, p, tiles_x, num_tiles);
+  cfg.kernel<<<grid, kThreads, cfg.smem, stream>>>(map, p, tiles_x, num_tiles);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   ICB_CUDA(cudaGetLastError());
   return ICB_OK;
