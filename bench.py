@@ -236,6 +236,8 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]
     n, nc, codec, fmt = wl["n"], wl["nc"], wl["codec"], wl["fmt"]

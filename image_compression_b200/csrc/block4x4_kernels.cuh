@@ -55,12 +55,12 @@ struct CodecTraits<kCodecEtc1> {
 // sources c3 is zero.
 template <int kCodec, typename Fetch>
 __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch fetch, bool one_pixel, int swap_rb,
-                                                 int etc_strategy, uint8_t *out) {
+                                                 int etc_strategy, const uint4 *alpha_table, uint8_t *out) {
   if constexpr (kCodec == kCodecDxt1) {
     const uint2 c = dxt1_encode_block(px, swap_rb != 0, false, fetch);
     *reinterpret_cast<uint2 *>(out) = c;
   } else if constexpr (kCodec == kCodecDxt5) {
-    const uint2 a = dxt5_encode_alpha(px, one_pixel);
+    const uint2 a = dxt5_encode_alpha(px, one_pixel, alpha_table);
     const uint2 c = dxt1_encode_block(px, swap_rb != 0, true, fetch);
     *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
   } else {
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(128) encode4x4_generic_kernel(const Encode4x4P
     auto fetch = [&](uint32_t i) { return load_pixel_clamped<kNcomp>(p, 4u * br + (i >> 2), 4u * bc + (i & 3u)); };
     const bool one_pixel = 4u * br >= p.height && 4u * bc >= p.width;  // pixel4x4.cc:58
     uint8_t *out = p.dst + (static_cast<size_t>(br) * p.grid_cols + bc) * CodecTraits<kCodec>::kBlockBytes;
-    encode_and_store<kCodec>(px, fetch, one_pixel, p.swap_rb, p.etc_strategy, out);
+    encode_and_store<kCodec>(px, fetch, one_pixel, p.swap_rb, p.etc_strategy,
+                             reinterpret_cast<const uint4 *>(g_dxt5_alpha_table), out);
   }
 }
 
@@ -173,6 +174,13 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
   constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
+  // DXT5 keeps its 8 KB crossing-point table behind the ring
+  const uint4 *alpha_table = reinterpret_cast<const uint4 *>(smem_raw + kTmaStages * (Shape::kBytes + 16));
+  if constexpr (kCodec == kCodecDxt5) {
+    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + kTmaStages * (Shape::kBytes + 16));
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
+    for (uint32_t i = threadIdx.x; i < kDxt5AlphaTableBytes / 16; i += blockDim.x) dst[i] = src[i];
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTmaStages; ++s) {
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     }
     if (active) {
       uint8_t *out = p.dst + (static_cast<size_t>(tile_br + lby) * p.grid_cols + tile_bc + lbx) * kBlockBytes;
-      encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, out);
+      encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);

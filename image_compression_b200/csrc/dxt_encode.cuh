@@ -8,13 +8,16 @@
 //                              internal/dxtc_const_color_table.cc:322-392
 //   ComputeBaseAlphas/AlphaBits internal/dxtc_compressor.cc:374-479
 //
-// How the scalar loops map to sm_100a instructions (checked with cuobjdump -sass):
+// How the scalar loops map to sm_100a instructions (checked with cuobjdump -sass, rates measured with
+// tools/microbench/pipe_rates.cu):
 //   * luminance and its raster index are produced together by one IDP.4A: key = 16*(4R+8G+B) + i.  The first
 //     minimum in raster order is min(key); the first maximum is max(key ^ 15).  VIMNMX3 reduces three keys per
 //     instruction.
-//   * per-pixel index search: |16*L_c - 16*l| + c is one VABSDIFF.U32 with accumulate; the smallest such value
-//     over c carries the reference's "first strict minimum" tie-break in its low bits.  A funnel shift
-//     (SHF.R.W) moves those bits into the output word without masking.
+//   * both index searches (colour: 4 candidates on the luminance line; alpha: 8 candidates) are nearest-neighbour
+//     searches on a line, evaluated as "how many crossing points has this pixel passed" with saturating
+//     floating-point adds and multiply-adds on exactly representable integers -- fp32 for luminance (values
+//     < 2^24), packed fp16 for alpha (values <= 256, two pixels per instruction) -- because the integer pipe
+//     (LOP3/SHF/VIMNMX/VABSDIFF, one warp-instruction per two cycles per scheduler) is what bounds these kernels.
 #pragma once
 #include <cstdint>
 
@@ -198,66 +201,139 @@ __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], boo
   return make_uint2(c0 | (c1 << 16), bits);
 }
 
-// Encodes the DXT5 alpha half from the top byte of each pixel.  Returns the 8 output bytes as two words.
-__device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], bool one_pixel) {
+// ---------------------------------------------------------------------------------------------------------
+// DXT5 alpha block
+// ---------------------------------------------------------------------------------------------------------
+
+// Crossing-point table, 512 entries x 16 bytes; layout and derivation in tools/gen_dxt5_alpha_table.py, which also
+// verifies the table-driven search against the reference's direct search for every (a0, a1, alpha).
+__device__ __align__(16) const uint8_t g_dxt5_alpha_table[512 * 16] = {
+#include "dxt5_alpha_table.inc"
+};
+constexpr int kDxt5AlphaTableBytes = 512 * 16;
+
+// Packed fp16 helpers on raw 32-bit registers (two lanes per instruction; HFMA2 / HADD2 in SASS).
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_fma_sat(uint32_t a, uint32_t b, uint32_t c) {  // clamps each lane to [0, 1]
+  uint32_t d;
+  asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_add_sat(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.sat.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+// Encodes the DXT5 alpha half from the top byte of each pixel (ComputeBaseAlphas, dxtc_compressor.cc:374-424;
+// ComputeAlphaBits :427-479; bit layout Dxt5AlphaBits :103-158).  Returns the 8 output bytes as two words.
+// `table` points at the crossing-point table (shared memory in the TMA kernel, global memory otherwise).
+//
+// Alphas and every threshold are integers <= 256, exact in fp16, so the block is processed two pixels per
+// instruction: pixel pair (i, i+8) lives in one register as half2(1280 + a_i, 1280 + a_{i+8}) -- the bit pattern
+// 0x6500 | a, so building it costs a byte permute and a mask, no conversion.
+//   statistics  [a >= 1] and [a == 255] are saturating adds; "min over alphas that are not 0" and "max over
+//               alphas that are not 255" become min/max over x - 255*[..] on the raw bit patterns (VIMNMX.U16x2);
+//               the counts accumulate as 1024 + n so they can be read back from the mantissa.
+//   indices     nearest-candidate search as seven crossings: t = sat(+-x + K_p) is 1 once the pixel has crossed,
+//               acc += t * step_p accumulates the candidate index modulo 8 in the mantissa of 1024 + index.
+__device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], bool one_pixel, const uint4 *table) {
   if (one_pixel) {  // window entirely outside the image: both endpoints = that alpha, all indices 0
     const uint32_t a = px[0] >> 24;
     return make_uint2(a | (a << 8), 0u);
   }
-  uint32_t n0 = 0, n255 = 0, lo = 255, hi = 0;
+  uint32_t x[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t a = px[i] >> 24;
-    n0 += (a == 0u);
-    n255 += (a == 255u);
-    lo = min(lo, a == 0u ? 255u : a);   // 0 and 255 never tighten the interior range
-    hi = max(hi, a == 255u ? 0u : a);
+  for (int i = 0; i < 8; ++i) x[i] = (__byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu) | 0x65006500u;
+
+  // ---- statistics
+  uint32_t fmin = 0xffffffffu, gmax = 0u, nz = 0x64006400u, n255 = 0x64006400u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t z = h2_add_sat(x[i], 0xe500e500u);        // [a >= 1]      (x - 1280, clamped to [0,1])
+    const uint32_t y = h2_add_sat(x[i], 0xe5fee5feu);        // [a == 255]    (x - 1534)
+    fmin = __vminu2(fmin, h2_fma(z, 0xdbf8dbf8u, x[i]));     // 1025 + (a == 0 ? 255 : a)
+    gmax = __vmaxu2(gmax, h2_fma(y, 0xdbf8dbf8u, x[i]));     // 1280 + (a == 255 ? 0 : a)
+    nz = h2_add(nz, z);
+    n255 = h2_add(n255, y);
   }
+  int lo = static_cast<int>(min(fmin & 0xffffu, fmin >> 16) & 0x3ffu) - 1;
+  int hi = static_cast<int>(max(gmax & 0xffffu, gmax >> 16) & 0x3ffu) - 256;
+  const uint32_t num_nonzero = (nz & 0x3ffu) + ((nz >> 16) & 0x3ffu);
+  const uint32_t num_opaque = (n255 & 0x3ffu) + ((n255 >> 16) & 0x3ffu);
   if (lo > hi) {  // every alpha is 0 or 255
     lo = 0;
     hi = 255;
   }
   uint32_t a0, a1;
-  if (n0 > 1 || n255 > 1) {
+  if (num_nonzero < 15u || num_opaque > 1u) {  // more than one fully transparent or fully opaque pixel
     a0 = lo;
     a1 = hi;
   } else {
-    if (n0 > 0) lo = 0;
-    if (n255 > 0) hi = 255;
+    if (num_nonzero < 16u) lo = 0;
+    if (num_opaque > 0u) hi = 255;
     a0 = hi;
     a1 = lo;
   }
-  uint32_t t[8];  // candidate alphas scaled by 8 so the index fits below them
-  t[0] = 8u * a0;
-  t[1] = 8u * a1;
-  if (a0 <= a1) {
-    t[2] = 8u * ((4u * a0 + a1) / 5u);
-    t[3] = 8u * ((3u * a0 + 2u * a1) / 5u);
-    t[4] = 8u * ((2u * a0 + 3u * a1) / 5u);
-    t[5] = 8u * ((a0 + 4u * a1) / 5u);
-    t[6] = 0u;
-    t[7] = 8u * 255u;
-  } else {
-    t[2] = 8u * ((6u * a0 + a1) / 7u);
-    t[3] = 8u * ((5u * a0 + 2u * a1) / 7u);
-    t[4] = 8u * ((4u * a0 + 3u * a1) / 7u);
-    t[5] = 8u * ((3u * a0 + 4u * a1) / 7u);
-    t[6] = 8u * ((2u * a0 + 5u * a1) / 7u);
-    t[7] = 8u * ((a0 + 6u * a1) / 7u);
+
+  // ---- crossings for this (mode, |a0 - a1|)
+  const bool six = a0 <= a1;  // 6-alpha mode: candidates 0 and 255 are explicit
+  const uint32_t dist = __usad(a0, a1, 0u);
+  const uint4 e = table[(six ? 0u : 256u) + dist];
+  const uint32_t base = (six ? 0xe4ffu : 0x6402u) + a0;
+  uint32_t K[7], S[7];
+  K[0] = __dp4a(e.x, 0x00000001u, base); K[1] = __dp4a(e.x, 0x00000100u, base);
+  K[2] = __dp4a(e.x, 0x00010000u, base); K[3] = __dp4a(e.x, 0x01000000u, base);
+  K[4] = __dp4a(e.y, 0x00000001u, base); K[5] = __dp4a(e.y, 0x00000100u, base);
+  K[6] = __dp4a(e.y, 0x00010000u, base);
+  S[0] = __byte_perm(e.z, 0u, 0x0404); S[1] = __byte_perm(e.z, 0u, 0x1414);
+  S[2] = __byte_perm(e.z, 0u, 0x2424); S[3] = __byte_perm(e.z, 0u, 0x3434);
+  S[4] = __byte_perm(e.w, 0u, 0x0404); S[5] = __byte_perm(e.w, 0u, 0x1414);
+  S[6] = __byte_perm(e.w, 0u, 0x2424);
+  uint32_t start = 0x6400u;
+  if (six) {
+    // crossings against the explicit candidates: 0 (index 6, or 0 when a0 is itself 0) below the line and
+    // 255 (index 7, or the line's last index when a1 is itself 255) above it
+    const uint32_t a0_zero = a0 == 0u ? 1u : 0u, last = e.y >> 24;
+    K[0] = 0xe4ffu + ((a0 + a0_zero + 1u) >> 1);
+    S[0] = a0_zero ? 0u : 0x4000u;                               // 6 -> 0 is +2 (mod 8)
+    K[6] = 0xe4ffu + ((a1 + 257u) >> 1);
+    S[6] = a1 == 255u ? 0u : 0x4700u - (last << 8);              // last -> 7
+    start += a0_zero ? 0u : 6u;
   }
-  uint32_t acc_lo = 0, acc_hi = 0;  // 64-bit shift register; 3 bits enter at the top per pixel
+  const uint32_t sign = six ? 0x3c003c00u : 0xbc00bc00u;         // +1 / -1 in both lanes
+  start *= 0x10001u;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t a8 = (px[i] >> 21) & 0x7f8u;
-    uint32_t k = min(__usad(t[0], a8, 0u), __usad(t[1], a8, 1u));
-    k = min(k, min(__usad(t[2], a8, 2u), __usad(t[3], a8, 3u)));
-    k = min(k, min(__usad(t[4], a8, 4u), __usad(t[5], a8, 5u)));
-    k = min(k, min(__usad(t[6], a8, 6u), __usad(t[7], a8, 7u)));
-    acc_lo = __funnelshift_r(acc_lo, acc_hi, 3);
-    acc_hi = __funnelshift_r(acc_hi, k, 3);
+  for (int p = 0; p < 7; ++p) K[p] *= 0x10001u;
+  S[0] *= six ? 0x10001u : 1u;  // table steps are already in both lanes; the on-the-fly ones are not
+  S[6] *= six ? 0x10001u : 1u;
+
+  // ---- indices: words 0..3 and 4..7 accumulate 3-bit codes at bit 3*(w & 3) of each lane
+  uint32_t acc_a = 0, acc_b = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    uint32_t acc = start;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) acc = h2_fma(h2_fma_sat(x[w], sign, K[p]), S[p], acc);
+    const uint32_t code = acc & 0x00070007u;
+    if (w < 4)
+      acc_a += code << (3 * w);
+    else
+      acc_b += code << (3 * (w - 4));
   }
-  // 48 code bits now sit in bits 16..63 of (acc_hi:acc_lo); bytes 0,1 are the endpoints.
-  return make_uint2((acc_lo & 0xffff0000u) | a0 | (a1 << 8), acc_hi);
+  // lanes: low = pixels 0..7, high = pixels 8..15; pixel n's code goes to bit 16 + 3n of the 64-bit block half
+  const uint32_t word0 = a0 | (a1 << 8) | ((acc_a & 0xfffu) << 16) | (acc_b << 28);
+  const uint32_t word1 = ((acc_b & 0xfffu) >> 4) | ((acc_a >> 16) << 8) | ((acc_b >> 16) << 20);
+  return make_uint2(word0, word1);
 }
 
 }  // namespace icb

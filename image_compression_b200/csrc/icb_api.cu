@@ -125,8 +125,9 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
   if (chosen[dev].kernel == nullptr) {
-    Config cand[2] = {{icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * (Shape::kBytes + 16), 0},
-                      {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * (Shape::kBytes + 16), 0}};
+    constexpr size_t kExtra = kCodec == icb::kCodecDxt5 ? icb::kDxt5AlphaTableBytes : 0;  // DXT5 crossing table
+    Config cand[2] = {{icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * (Shape::kBytes + 16) + kExtra, 0},
+                      {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * (Shape::kBytes + 16) + kExtra, 0}};
     const char *force = getenv("ICB_TMA_STAGES");
     int best = -1;
     for (int c = 0; c < 2; ++c) {
