@@ -10,6 +10,8 @@
 // sm_100a mapping: a candidate colour is one VIADDMNMX.RELU per channel (add, min 255, clamp at 0); the squared
 // distance of a pixel to a candidate is VABSDIFF4.U8 followed by IDP.4A of the difference with itself; the
 // "first strict minimum" rules are carried by keys (error*4 + index) and (cumulative*8 + codeword).
+// The exhaustive search only accumulates errors; pixel indices are computed once, for the winning orientation
+// and codewords (the reference recomputes them inside every ComputeCodewordError call).
 #pragma once
 #include <cstdint>
 
@@ -35,99 +37,112 @@ __device__ __forceinline__ uint32_t etc_ssd(uint32_t px, uint32_t cand) {
   return __dp4a(d, d, 0u);
 }
 
-// Error of encoding the 8 pixels selected by `mask` (bit i = raster pixel i) with codeword cw around base
-// (r,g,b).  Returns the cumulative error; *indices gets the 2-bit choices in wire positions.
-__device__ __forceinline__ uint32_t etc_codeword_error(const uint32_t (&px)[16], uint32_t mask, int cw, int r, int g,
-                                                       int b, uint32_t *indices) {
-  const int ms = etc_small(cw), ml = etc_large(cw);
-  const uint32_t c0 = etc_candidate(r, g, b, ms);
-  const uint32_t c1 = etc_candidate(r, g, b, ml);
-  const uint32_t c2 = etc_candidate(r, g, b, -ms);
-  const uint32_t c3 = etc_candidate(r, g, b, -ml);
-  uint32_t total = 0, idx = 0;
+struct EtcCandidates {
+  uint32_t c[4];  // base + {small, large, -small, -large}, clamped, packed (r,g,b,0)
+};
+
+__device__ __forceinline__ EtcCandidates etc_candidates(uint32_t base_rgb, int ms, int ml) {
+  const int r = base_rgb & 255u, g = (base_rgb >> 8) & 255u, b = (base_rgb >> 16) & 255u;
+  EtcCandidates k;
+  k.c[0] = etc_candidate(r, g, b, ms);
+  k.c[1] = etc_candidate(r, g, b, ml);
+  k.c[2] = etc_candidate(r, g, b, -ms);
+  k.c[3] = etc_candidate(r, g, b, -ml);
+  return k;
+}
+
+// Sum over the pixels selected by kMask of the distance to the nearest of the four candidates
+// (ComputeCodewordError without the index bookkeeping, which only the winning codeword needs).
+template <uint32_t kMask>
+__device__ __forceinline__ uint32_t etc_codeword_error(const uint32_t (&px)[16], const EtcCandidates &k) {
+  uint32_t total = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    if (mask & (1u << i)) {  // mask is a compile-time constant at every call site after unrolling
-      const uint32_t k = min(min(etc_ssd(px[i], c0) * 4u, etc_ssd(px[i], c1) * 4u + 1u),
-                             min(etc_ssd(px[i], c2) * 4u + 2u, etc_ssd(px[i], c3) * 4u + 3u));
-      total += k >> 2;
-      const int p = 4 * (i & 3) + (i >> 2);  // column-major position: pixel (y,x) -> 4x + y
-      idx |= (k & 1u) << p;
-      idx |= ((k >> 1) & 1u) << (p + 16);
-    }
+    if (kMask & (1u << i))
+      total += min(min(etc_ssd(px[i], k.c[0]), etc_ssd(px[i], k.c[1])), min(etc_ssd(px[i], k.c[2]), etc_ssd(px[i], k.c[3])));
   }
-  *indices = idx;
   return total;
 }
 
+// Best codeword for one sub-block as a key: cumulative_error * 8 + codeword; min over keys = FindBestCodeword's
+// first strict minimum (errors are < 2^21, so the key fits 32 bits).
 template <uint32_t kMask>
-__device__ __forceinline__ uint32_t etc_pick_codeword(const uint32_t (&px)[16], int r, int g, int b, bool heuristic,
-                                                 uint32_t *indices, uint32_t *error) {
-  if (heuristic) {
-    const uint32_t base = static_cast<uint32_t>(r | (g << 8) | (b << 16));
-    uint32_t dev_rb = 0, dev_g = 0;  // per-channel sums of |base - pixel| over the 8 pixels (each <= 2040)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (kMask & (1u << i)) {
-        const uint32_t d = __vabsdiffu4(px[i], base);
-        dev_rb += d & 0x00ff00ffu;
-        dev_g += (d >> 8) & 0xffu;
-      }
-    }
-    const uint32_t dev = max(max((dev_rb & 0xffffu) >> 3, dev_rb >> 19), dev_g >> 3);
-    const uint32_t cw = dev > 144 ? 7 : dev > 93 ? 6 : dev > 70 ? 5 : dev > 51 ? 4 : dev > 35 ? 3 : dev > 23 ? 2 : dev > 12 ? 1 : 0;
-    *error = etc_codeword_error(px, kMask, cw, r, g, b, indices);
-    return cw;
-  }
-  uint32_t best = 0xffffffffu, best_idx = 0;
-  uint32_t best_cw = 0;
+__device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[16], uint32_t base_rgb) {
+  uint32_t best = 0xffffffffu;
 #pragma unroll
   for (int cw = 0; cw < 8; ++cw) {
-    uint32_t idx;
-    const uint32_t e = etc_codeword_error(px, kMask, cw, r, g, b, &idx);
-    if (e < best) {
-      best = e;
-      best_idx = idx;
-      best_cw = cw;
-    }
+    const EtcCandidates k = etc_candidates(base_rgb, etc_small(cw), etc_large(cw));
+    best = min(best, etc_codeword_error<kMask>(px, k) * 8u + static_cast<uint32_t>(cw));
   }
-  *indices = best_idx;
-  *error = best;
-  return best_cw;
+  return best;
 }
 
-// One orientation: kFlip=false -> left/right 2x4 halves, kFlip=true -> top/bottom 4x2 halves.
-// sum1/sum2: per-channel sums of the two halves, (r | b<<16) and g.  Returns hi word, *lo, *error.
-template <bool kFlip>
-__device__ __forceinline__ uint32_t etc_encode_split(const uint32_t (&px)[16], uint32_t sum1_rb, uint32_t sum1_g,
-                                                     uint32_t sum2_rb, uint32_t sum2_g, bool heuristic, uint32_t *lo,
-                                                     uint32_t *error) {
-  constexpr uint32_t kMask1 = kFlip ? 0x00ffu : 0x3333u;
-  constexpr uint32_t kMask2 = kFlip ? 0xff00u : 0xccccu;
+// FindCodewordHeuristic: codeword from the largest per-channel mean absolute deviation; key as above.
+template <uint32_t kMask>
+__device__ __forceinline__ uint32_t etc_heuristic_codeword_key(const uint32_t (&px)[16], uint32_t base_rgb) {
+  uint32_t dev_rb = 0, dev_g = 0;  // per-channel sums of |base - pixel| over the 8 pixels (each <= 2040)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (kMask & (1u << i)) {
+      const uint32_t d = __vabsdiffu4(px[i], base_rgb);
+      dev_rb += d & 0x00ff00ffu;
+      dev_g += (d >> 8) & 0xffu;
+    }
+  }
+  const uint32_t dev = max(max((dev_rb & 0xffffu) >> 3, dev_rb >> 19), dev_g >> 3);
+  const uint32_t cw = dev > 144 ? 7 : dev > 93 ? 6 : dev > 70 ? 5 : dev > 51 ? 4 : dev > 35 ? 3 : dev > 23 ? 2 : dev > 12 ? 1 : 0;
+  const EtcCandidates k = etc_candidates(base_rgb, etc_small(cw), etc_large(cw));
+  return etc_codeword_error<kMask>(px, k) * 8u + cw;
+}
+
+// Base colours of one orientation.  sum1/sum2: per-channel sums of the two halves, (r | b<<16) and g.
+// Returns the colour part of the hi word (flip and diff bits included) and the two decoded base colours.
+struct EtcBases {
+  uint32_t hi, base1, base2;
+};
+__device__ __forceinline__ EtcBases etc_bases(bool flip, uint32_t sum1_rb, uint32_t sum1_g, uint32_t sum2_rb,
+                                              uint32_t sum2_g) {
   const uint32_t a1r = (sum1_rb & 0xffffu) >> 3, a1g = sum1_g >> 3, a1b = sum1_rb >> 19;  // truncating means
   const uint32_t a2r = (sum2_rb & 0xffffu) >> 3, a2g = sum2_g >> 3, a2b = sum2_rb >> 19;
   const uint32_t q1r = a1r >> 3, q1g = a1g >> 3, q1b = a1b >> 3, q2r = a2r >> 3, q2g = a2g >> 3, q2b = a2b >> 3;
   const int dr = static_cast<int>(q2r - q1r), dg = static_cast<int>(q2g - q1g), db = static_cast<int>(q2b - q1b);
   const bool diff_mode = dr >= -4 && dr <= 3 && dg >= -4 && dg <= 3 && db >= -4 && db <= 3;
-  uint32_t hi = kFlip ? 1u : 0u;
-  uint32_t b1r, b1g, b1b, b2r, b2g, b2b;  // base colours as a decoder will see them
-  if (diff_mode) {
-    hi |= 2u | (q1r << 27) | (q1g << 19) | (q1b << 11) | ((dr & 7u) << 24) | ((dg & 7u) << 16) | ((db & 7u) << 8);
-    b1r = (q1r << 3) | (q1r >> 2); b1g = (q1g << 3) | (q1g >> 2); b1b = (q1b << 3) | (q1b >> 2);
-    b2r = (q2r << 3) | (q2r >> 2); b2g = (q2g << 3) | (q2g >> 2); b2b = (q2b << 3) | (q2b >> 2);
-  } else {
+  EtcBases out;
+  out.hi = flip ? 1u : 0u;
+  if (diff_mode) {  // 5-bit base + 3-bit two's-complement delta; decoder replicates the top three bits
+    out.hi |= 2u | (q1r << 27) | (q1g << 19) | (q1b << 11) | ((dr & 7u) << 24) | ((dg & 7u) << 16) | ((db & 7u) << 8);
+    out.base1 = ((q1r << 3) | (q1r >> 2)) | (((q1g << 3) | (q1g >> 2)) << 8) | (((q1b << 3) | (q1b >> 2)) << 16);
+    out.base2 = ((q2r << 3) | (q2r >> 2)) | (((q2g << 3) | (q2g >> 2)) << 8) | (((q2b << 3) | (q2b >> 2)) << 16);
+  } else {  // two 4-bit colours; decoder multiplies by 17
     const uint32_t n1r = a1r >> 4, n1g = a1g >> 4, n1b = a1b >> 4, n2r = a2r >> 4, n2g = a2g >> 4, n2b = a2b >> 4;
-    hi |= (n1r << 28) | (n1g << 20) | (n1b << 12) | (n2r << 24) | (n2g << 16) | (n2b << 8);
-    b1r = n1r * 17; b1g = n1g * 17; b1b = n1b * 17;
-    b2r = n2r * 17; b2g = n2g * 17; b2b = n2b * 17;
+    out.hi |= (n1r << 28) | (n1g << 20) | (n1b << 12) | (n2r << 24) | (n2g << 16) | (n2b << 8);
+    out.base1 = (n1r | (n1g << 8) | (n1b << 16)) * 17u;
+    out.base2 = (n2r | (n2g << 8) | (n2b << 16)) * 17u;
   }
-  uint32_t idx1, idx2, e1, e2;
-  const uint32_t cw1 = etc_pick_codeword<kMask1>(px, b1r, b1g, b1b, heuristic, &idx1, &e1);
-  const uint32_t cw2 = etc_pick_codeword<kMask2>(px, b2r, b2g, b2b, heuristic, &idx2, &e2);
-  hi |= (cw1 << 5) | (cw2 << 2);
-  *lo = idx1 | idx2;
-  *error = e1 + e2;
-  return hi;
+  return out;
+}
+
+// Pixel indices (the lo word) for the chosen orientation and codewords.  Pixels whose sub-block is the same in
+// both orientations use a fixed candidate set; the top-right and bottom-left quadrants pick theirs by `flip`.
+__device__ __forceinline__ uint32_t etc_pixel_indices(const uint32_t (&px)[16], bool flip, const EtcCandidates &k1,
+                                                      const EtcCandidates &k2) {
+  EtcCandidates top_right, bottom_left;  // flip: top-right belongs to sub-block 1 (top), bottom-left to 2
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    top_right.c[j] = flip ? k1.c[j] : k2.c[j];
+    bottom_left.c[j] = flip ? k2.c[j] : k1.c[j];
+  }
+  uint32_t lo = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int quadrant = ((i >> 3) << 1) | ((i >> 1) & 1);
+    const EtcCandidates &k = quadrant == 0 ? k1 : quadrant == 3 ? k2 : quadrant == 1 ? top_right : bottom_left;
+    const uint32_t key = min(min(etc_ssd(px[i], k.c[0]) * 4u, etc_ssd(px[i], k.c[1]) * 4u + 1u),
+                             min(etc_ssd(px[i], k.c[2]) * 4u + 2u, etc_ssd(px[i], k.c[3]) * 4u + 3u));
+    const int p = 4 * (i & 3) + (i >> 2);  // column-major position: pixel (y,x) -> 4x + y
+    lo |= ((key & 1u) << p) | ((key & 2u) << (p + 15));
+  }
+  return lo;
 }
 
 // px[i]: bytes (r,g,b,0) -- the top byte MUST be zero.  Returns the 8 wire bytes as two little-endian words
@@ -141,39 +156,53 @@ __device__ __forceinline__ uint2 etc1_encode_block(const uint32_t (&px)[16], int
     q_rb[q] += px[i] & 0x00ff00ffu;
     q_g[q] += (px[i] >> 8) & 0xffu;
   }
-  const uint32_t left_rb = q_rb[0] + q_rb[2], left_g = q_g[0] + q_g[2];
-  const uint32_t right_rb = q_rb[1] + q_rb[3], right_g = q_g[1] + q_g[3];
-  const uint32_t top_rb = q_rb[0] + q_rb[1], top_g = q_g[0] + q_g[1];
-  const uint32_t bottom_rb = q_rb[2] + q_rb[3], bottom_g = q_g[2] + q_g[3];
-  uint32_t hi, lo, err;
-  if (strategy == kEtcSplitHorizontally) {
-    hi = etc_encode_split<true>(px, top_rb, top_g, bottom_rb, bottom_g, false, &lo, &err);
-  } else if (strategy == kEtcSplitVertically) {
-    hi = etc_encode_split<false>(px, left_rb, left_g, right_rb, right_g, false, &lo, &err);
-  } else if (strategy == kEtcHeuristic) {
-    // The reference's bottom-right quadrant sum adds pixel (2,2) twice and never (3,3) (etc_compressor.cc:563-564).
+  const EtcBases lr = etc_bases(false, q_rb[0] + q_rb[2], q_g[0] + q_g[2], q_rb[1] + q_rb[3], q_g[1] + q_g[3]);
+  const EtcBases tb = etc_bases(true, q_rb[0] + q_rb[1], q_g[0] + q_g[1], q_rb[2] + q_rb[3], q_g[2] + q_g[3]);
+  constexpr uint32_t kLeft = 0x3333u, kRight = 0xccccu, kTop = 0x00ffu, kBottom = 0xff00u;
+
+  bool flip;
+  uint32_t key1, key2;  // cumulative_error * 8 + codeword of sub-blocks 1 and 2 of the chosen orientation
+  if (strategy == kEtcHeuristic) {
+    // Orientation from the colour difference of the halves.  The reference's bottom-right quadrant sum adds
+    // pixel (2,2) twice and never (3,3) (etc_compressor.cc:563-564); the sub-block means below use the true sums.
     const uint32_t q3_rb = q_rb[3] - (px[15] & 0x00ff00ffu) + (px[10] & 0x00ff00ffu);
     const uint32_t q3_g = q_g[3] - ((px[15] >> 8) & 0xffu) + ((px[10] >> 8) & 0xffu);
     const uint32_t l_rb = q_rb[0] + q_rb[2], r_rb = q_rb[1] + q3_rb, t_rb = q_rb[0] + q_rb[1], b_rb = q_rb[2] + q3_rb;
-    const int lr = (l_rb & 0xffffu) >> 3, lg = (q_g[0] + q_g[2]) >> 3, lb = l_rb >> 19;
+    const int lr_ = (l_rb & 0xffffu) >> 3, lg = (q_g[0] + q_g[2]) >> 3, lb = l_rb >> 19;
     const int rr = (r_rb & 0xffffu) >> 3, rg = (q_g[1] + q3_g) >> 3, rb = r_rb >> 19;
-    const int tr = (t_rb & 0xffffu) >> 3, tg = (q_g[0] + q_g[1]) >> 3, tb = t_rb >> 19;
+    const int tr = (t_rb & 0xffffu) >> 3, tg = (q_g[0] + q_g[1]) >> 3, tb_ = t_rb >> 19;
     const int br = (b_rb & 0xffffu) >> 3, bg = (q_g[2] + q3_g) >> 3, bb = b_rb >> 19;
-    const uint32_t e_lr = (rr - lr) * (rr - lr) + (rg - lg) * (rg - lg) + (rb - lb) * (rb - lb);
-    const uint32_t e_tb = (br - tr) * (br - tr) + (bg - tg) * (bg - tg) + (bb - tb) * (bb - tb);
-    if (e_lr > e_tb)
-      hi = etc_encode_split<false>(px, left_rb, left_g, right_rb, right_g, true, &lo, &err);
-    else
-      hi = etc_encode_split<true>(px, top_rb, top_g, bottom_rb, bottom_g, true, &lo, &err);
-  } else {
-    uint32_t lo2, err2;
-    hi = etc_encode_split<false>(px, left_rb, left_g, right_rb, right_g, false, &lo, &err);
-    const uint32_t hi2 = etc_encode_split<true>(px, top_rb, top_g, bottom_rb, bottom_g, false, &lo2, &err2);
-    if (err2 < err) {
-      hi = hi2;
-      lo = lo2;
+    const uint32_t e_lr = (rr - lr_) * (rr - lr_) + (rg - lg) * (rg - lg) + (rb - lb) * (rb - lb);
+    const uint32_t e_tb = (br - tr) * (br - tr) + (bg - tg) * (bg - tg) + (bb - tb_) * (bb - tb_);
+    flip = !(e_lr > e_tb);
+    if (flip) {
+      key1 = etc_heuristic_codeword_key<kTop>(px, tb.base1);
+      key2 = etc_heuristic_codeword_key<kBottom>(px, tb.base2);
+    } else {
+      key1 = etc_heuristic_codeword_key<kLeft>(px, lr.base1);
+      key2 = etc_heuristic_codeword_key<kRight>(px, lr.base2);
     }
+  } else {
+    uint32_t lr1 = 0, lr2 = 0, tb1 = 0, tb2 = 0;
+    if (strategy != kEtcSplitHorizontally) {
+      lr1 = etc_best_codeword_key<kLeft>(px, lr.base1);
+      lr2 = etc_best_codeword_key<kRight>(px, lr.base2);
+    }
+    if (strategy != kEtcSplitVertically) {
+      tb1 = etc_best_codeword_key<kTop>(px, tb.base1);
+      tb2 = etc_best_codeword_key<kBottom>(px, tb.base2);
+    }
+    // kSmallerError keeps the unflipped block unless the flipped one is strictly better (etc_compressor.cc:583)
+    flip = strategy == kEtcSplitHorizontally ||
+           (strategy == kEtcSmallerError && (tb1 >> 3) + (tb2 >> 3) < (lr1 >> 3) + (lr2 >> 3));
+    key1 = flip ? tb1 : lr1;
+    key2 = flip ? tb2 : lr2;
   }
+  const uint32_t cw1 = key1 & 7u, cw2 = key2 & 7u;
+  const uint32_t base1 = flip ? tb.base1 : lr.base1, base2 = flip ? tb.base2 : lr.base2;
+  const uint32_t hi = (flip ? tb.hi : lr.hi) | (cw1 << 5) | (cw2 << 2);
+  const uint32_t lo = etc_pixel_indices(px, flip, etc_candidates(base1, etc_small(cw1), etc_large(cw1)),
+                                        etc_candidates(base2, etc_small(cw2), etc_large(cw2)));
   return make_uint2(__byte_perm(hi, 0u, 0x0123), __byte_perm(lo, 0u, 0x0123));
 }
 

@@ -352,7 +352,10 @@ int icb_encode4x4_stripe(int codec, int ncomp, const void *d_src, uint32_t h, ui
   return encode4x4(codec, ncomp, d_src, h, w, pitch, ch, cw, swap_rb, strategy, r0, r1, d_dst, stream);
 }
 
-size_t icb_pvrtc2_scratch_size(uint32_t h, uint32_t w) { return static_cast<size_t>(w / 8) * (h / 4) * 4 * 2; }
+// two low-resolution colour images (4 B per block each) + 2-bit modulation per pixel (2 B per 8 pixels)
+size_t icb_pvrtc2_scratch_size(uint32_t h, uint32_t w) {
+  return static_cast<size_t>(w / 8) * (h / 4) * 4 * 2 + static_cast<size_t>(w / 8) * h * 2;
+}
 
 int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_dst, void *d_scratch, void *stream) {
   if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
@@ -370,13 +373,15 @@ int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_d
   p.src = static_cast<const uint32_t *>(d_src);
   p.low_a = static_cast<uint32_t *>(scratch);
   p.low_b = p.low_a + nblocks;
+  p.mod = reinterpret_cast<uint16_t *>(p.low_b + nblocks);
   p.dst = static_cast<uint2 *>(d_dst);
   p.width = w;
   p.height = h;
   const uint32_t grid = (nblocks + 127) / 128;
   icb::pvrtc_morph_kernel<<<grid, 128, 0, st>>>(p);
-  icb::pvrtc_modulate_kernel<<<grid, 128, 0, st>>>(p);
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  icb::pvrtc_modulate_kernel<<<(nblocks * 4 + 255) / 256, 256, 0, st>>>(p);
+  icb::pvrtc_pack_kernel<<<grid, 128, 0, st>>>(p);
+  g_launches.fetch_add(3, std::memory_order_relaxed);
   ICB_CUDA(cudaGetLastError());
   if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));
   return ICB_OK;

@@ -17,6 +17,14 @@ namespace icb {
 
 __device__ __forceinline__ uint32_t pv_l1(uint32_t p, uint32_t q) { return __vsadu4(p, q); }
 
+// a*32 + c as ONE multiply-add on the FMA pipe.  Written in PTX because the compiler otherwise rewrites
+// (x & mask)*32 + c into shift/and/or -- three instructions on the integer pipe that bounds these kernels.
+__device__ __forceinline__ uint32_t pv_mad32(uint32_t a, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 32, %2;" : "=r"(d) : "r"(a), "r"(c));
+  return d;
+}
+
 // Keep the top n bits of an 8-bit value and replicate them downwards (ApplyBitDepthReduction).
 __device__ __forceinline__ uint32_t pv_keep_bits(uint32_t v, uint32_t n) {
   const uint32_t kept = v & ((0xffu << (8u - n)) & 0xffu);
@@ -41,53 +49,48 @@ __device__ __forceinline__ uint32_t pv_reduce_colour(uint32_t c, bool is_b) {
   return r | (g << 8) | (b << 16) | (a << 24);
 }
 
-// The block's two extreme colours.  px[j], j = 8*y + x, are the block's 32 pixels; first_pixel is the image's
-// pixel (0,0), which the reference uses whenever an axis is all zero in the block (its "max" slot never moves
-// off index 0).  Outputs are the already bit-reduced A and B colours.
-__device__ __forceinline__ void pv_block_extremes(const uint32_t (&px)[32], uint32_t first_pixel, uint32_t *colour_a,
-                                                  uint32_t *colour_b) {
-  uint32_t kmin[5], kmax[5];
+// The block's two extreme colours (GetExtremesFast + ApplyColorChannelReduction).  px[j], j = 8*y + x, are the
+// block's 32 pixels; fetch(j) must return px[j] (callers re-read memory by index: a register-indexed lookup would
+// be a 31-deep select chain per colour); first_pixel is the image's pixel (0,0), which the reference uses whenever
+// an axis is all zero in the block (its "max" slot never moves off index 0).
+// Keys: value*32 + j for "first minimum", the same with the index field reversed (^31) for "first maximum".
+// A key needs 13 bits, so the four channel axes ride two to a register -- (r,b) and (g,a) in 16-bit lanes: one
+// mask or byte permute plus one IMAD builds two keys, VIMNMX3.U16x2 folds two pixels of two axes per instruction.
+template <typename Fetch>
+__device__ __forceinline__ void pv_block_extremes(const uint32_t (&px)[32], uint32_t first_pixel, Fetch fetch,
+                                                  uint32_t *colour_a, uint32_t *colour_b) {
+  uint32_t min_l = 0xffffffffu, max_l = 0u;              // lightness axis, scalar keys
+  uint32_t min_rb = 0xffffffffu, max_rb = 0u, min_ga = 0xffffffffu, max_ga = 0u;  // packed channel keys
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    kmin[k] = 0xffffffffu;
-    kmax[k] = 0u;
-  }
+  for (int j = 0; j < 32; j += 2) {
+    uint32_t kl[2], krb[2], kga[2];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    uint32_t v[5];
-    v[0] = __dp4a(px[j], 0x001c964du, 0u) >> 8;  // (77r + 150g + 28b) / 256
-    v[1] = px[j] & 255u;
-    v[2] = (px[j] >> 8) & 255u;
-    v[3] = (px[j] >> 16) & 255u;
-    v[4] = px[j] >> 24;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      kmin[k] = min(kmin[k], v[k] * 32u + j);
-      kmax[k] = max(kmax[k], v[k] * 32u + (31u - j));
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t p = px[j + t], idx = static_cast<uint32_t>(j + t);
+      kl[t] = pv_mad32(__dp4a(p, 0x001c964du, 0u) >> 8, idx);  // lightness (77r + 150g + 28b) / 256
+      krb[t] = pv_mad32(p & 0x00ff00ffu, idx * 0x10001u);
+      kga[t] = pv_mad32(__byte_perm(p, 0u, 0x4341), idx * 0x10001u);
     }
+    min_l = __vimin3_u32(min_l, kl[0], kl[1]);
+    max_l = __vimax3_u32(max_l, kl[0] ^ 31u, kl[1] ^ 31u);
+    min_rb = __vimin3_u16x2(min_rb, krb[0], krb[1]);
+    max_rb = __vimax3_u16x2(max_rb, krb[0] ^ 0x001f001fu, krb[1] ^ 0x001f001fu);
+    min_ga = __vimin3_u16x2(min_ga, kga[0], kga[1]);
+    max_ga = __vimax3_u16x2(max_ga, kga[0] ^ 0x001f001fu, kga[1] ^ 0x001f001fu);
   }
-  // Turn keys into colours.  Register-indexed lookup, written as a select chain over the 32 pixels.
-  uint32_t cmin[5], cmax[5];
+  // axis order of the reference: lightness, r, g, b, a
+  const uint32_t kmin[5] = {min_l, min_rb & 0xffffu, min_ga & 0xffffu, min_rb >> 16, min_ga >> 16};
+  const uint32_t kmax[5] = {max_l, max_rb & 0xffffu, max_ga & 0xffffu, max_rb >> 16, max_ga >> 16};
+  uint32_t best = 0, c0 = 0, c1 = 0;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const uint32_t jmin = kmin[k] & 31u, jmax = 31u - (kmax[k] & 31u);
-    uint32_t a = px[0], b = px[0];
-#pragma unroll
-    for (int j = 1; j < 32; ++j) {
-      a = (jmin == j) ? px[j] : a;
-      b = (jmax == j) ? px[j] : b;
-    }
-    cmin[k] = a;
-    cmax[k] = (kmax[k] >> 5) == 0u ? first_pixel : b;  // all-zero axis: stays at the image's first pixel
-  }
-  uint32_t best = 0, c0 = cmin[0], c1 = cmax[0];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const uint32_t d = pv_l1(cmin[k], cmax[k]);
-    if (d > best) {
-      best = d;
-      c0 = cmin[k];
-      c1 = cmax[k];
+    const uint32_t cmin = fetch(kmin[k] & 31u);
+    const uint32_t cmax = (kmax[k] >> 5) == 0u ? first_pixel : fetch(31u - (kmax[k] & 31u));  // all-zero axis
+    const uint32_t d = pv_l1(cmin, cmax);
+    if (k == 0 || d > best) {  // strict '>' from 0: pair 0 unless a later one is strictly farther apart
+      best = k == 0 ? d : max(best, d);
+      c0 = cmin;
+      c1 = cmax;
     }
   }
   if (__dp4a(c1, 0x01010101u, 0u) < __dp4a(c0, 0x01010101u, 0u)) {  // darker colour first
@@ -103,26 +106,25 @@ struct PvLanes {
   uint32_t rb, ga;  // (r | b<<16), (g | a<<16)
 };
 
-__device__ __forceinline__ PvLanes pv_split(uint32_t c) { return PvLanes{c & 0x00ff00ffu, (c >> 8) & 0x00ff00ffu}; }
-__device__ __forceinline__ uint32_t pv_join(PvLanes v) { return v.rb | (v.ga << 8); }
-
-// (wa*a + wb*b) >> shift on both lanes; the per-lane sums never carry into the neighbouring lane.
-__device__ __forceinline__ PvLanes pv_mix(PvLanes a, uint32_t wa, PvLanes b, uint32_t wb, uint32_t shift) {
-  PvLanes out;
-  out.rb = ((a.rb * wa + b.rb * wb) >> shift) & 0x00ff00ffu;
-  out.ga = ((a.ga * wa + b.ga * wb) >> shift) & 0x00ff00ffu;
-  return out;
+__device__ __forceinline__ PvLanes pv_split(uint32_t c) { return PvLanes{c & 0x00ff00ffu, __byte_perm(c, 0u, 0x4341)}; }
+// Blend of two colours given as lane pairs, with the weights pre-scaled so that the divisor becomes 256:
+// (wa*a + wb*b) / 256 per channel, wa + wb == 256.  Each 16-bit lane then holds at most 255*256 and the quotient
+// is simply the lane's high byte, so ONE byte permute both divides and re-interleaves (r,g,b,a) -- no shifts or
+// masks on the integer pipe, which is what bounds this kernel.
+__device__ __forceinline__ uint32_t pv_blend256(PvLanes a, uint32_t wa, PvLanes b, uint32_t wb) {
+  return __byte_perm(a.rb * wa + b.rb * wb, a.ga * wa + b.ga * wb, 0x7351);
 }
 
 // BestModulation: 0 = A, 1 = (5A+3B)/8, 2 = (3A+5B)/8, 3 = B; stops at the first step that does not improve.
-__device__ __forceinline__ uint32_t pv_pick_modulation(uint32_t pixel, PvLanes a, PvLanes b) {
-  const uint32_t d0 = pv_l1(pixel, pv_join(a));
-  const uint32_t d1 = pv_l1(pixel, pv_join(pv_mix(a, 5u, b, 3u, 3u)));
-  const uint32_t d2 = pv_l1(pixel, pv_join(pv_mix(a, 3u, b, 5u, 3u)));
-  const uint32_t d3 = pv_l1(pixel, pv_join(b));
-  uint32_t m = 0;
-  if (d1 < d0) m = (d2 < d1) ? ((d3 < d2) ? 3u : 2u) : 1u;
-  return m;
+// a, b: the interpolated A and B colours of this pixel as packed bytes.
+__device__ __forceinline__ uint32_t pv_pick_modulation(uint32_t pixel, uint32_t a, uint32_t b) {
+  const PvLanes la = pv_split(a), lb = pv_split(b);
+  const uint32_t d0 = pv_l1(pixel, a);
+  const uint32_t d1 = pv_l1(pixel, pv_blend256(la, 160u, lb, 96u));
+  const uint32_t d2 = pv_l1(pixel, pv_blend256(la, 96u, lb, 160u));
+  const uint32_t d3 = pv_l1(pixel, b);
+  const bool s1 = d1 < d0, s2 = s1 && d2 < d1, s3 = s2 && d3 < d2;
+  return (s1 ? 1u : 0u) + (s2 ? 1u : 0u) + (s3 ? 1u : 0u);
 }
 
 // EncodeColors: bit 0 = mode flag, A in bits 1..15, B in bits 16..31.
@@ -141,19 +143,47 @@ __device__ __forceinline__ uint32_t pv_pack_colours(uint32_t ca, uint32_t cb, bo
   return v;
 }
 
-// Modulation mode + data word for one block.  m[y][x]: the block's own 4x8 values in rows 0..3 / columns 0..7,
-// the wrapped right-hand neighbour column in x = 8 and the wrapped row below in y = 4.
+// Eight 2-bit fields of a row word -> eight bytes (two registers of four).
+__device__ __forceinline__ uint32_t pv_fields_to_bytes(uint32_t four_fields) {  // input: bits 0..7
+  uint32_t x = (four_fields | (four_fields << 12)) & 0x000f000fu;
+  return (x | (x << 6)) & 0x03030303u;
+}
+// Fields 0,2,4,6 of a row word packed into 8 contiguous bits.
+__device__ __forceinline__ uint32_t pv_even_fields(uint32_t row) {
+  uint32_t x = row & 0x3333u;
+  x = (x | (x >> 2)) & 0x0f0fu;
+  return (x | (x >> 4)) & 0xffu;
+}
+// The high bit of each of the eight fields packed into 8 contiguous bits.
+__device__ __forceinline__ uint32_t pv_high_bits(uint32_t row) {
+  uint32_t x = (row >> 1) & 0x5555u;
+  x = (x | (x >> 1)) & 0x3333u;
+  x = (x | (x >> 2)) & 0x0f0fu;
+  return (x | (x >> 4)) & 0xffu;
+}
+
+// Modulation mode + data word for one block (CalculateBlockModulationMode / Data).  row[y], y = 0..3: the block's
+// rows, eight 2-bit values each (pixel x in bits 2x..2x+1); row[4]: the wrapped row below; right[y]: the 2-bit value
+// of the wrapped pixel to the right of row y.  Works on whole rows: value differences are summed four at a time
+// with VABSDIFF4.ACC on byte-expanded rows, counts come from population counts.
 // Returns the 32 modulation bits; *one_bpp tells the colour packer which mode flag to write.
-__device__ __forceinline__ uint32_t pv_pack_modulation(const uint32_t (&m)[5][9], bool *one_bpp) {
+__device__ __forceinline__ uint32_t pv_pack_modulation(const uint32_t (&row)[5], const uint32_t (&right)[4], bool *one_bpp) {
   uint32_t inter = 0, horizontal = 0, vertical = 0;
+  uint32_t lo_bytes[5], hi_bytes[5];
 #pragma unroll
-  for (int y = 0; y < 4; ++y)
+  for (int y = 0; y < 5; ++y) {
+    lo_bytes[y] = pv_fields_to_bytes(row[y] & 0xffu);
+    hi_bytes[y] = pv_fields_to_bytes(row[y] >> 8);
+  }
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      inter += (m[y][x] == 1u || m[y][x] == 2u);
-      horizontal += __usad(m[y][x], m[y + 1][x], 0u);  // (sic) "horizontal" looks at the row below
-      vertical += __usad(m[y][x], m[y][x + 1], 0u);    // (sic) "vertical" looks at the column to the right
-    }
+  for (int y = 0; y < 4; ++y) {
+    inter += __popc((row[y] ^ (row[y] >> 1)) & 0x5555u);  // values 1 and 2 have unequal bits
+    // (sic) the reference's "horizontal" count compares with the row BELOW, "vertical" with the pixel to the RIGHT
+    horizontal = __vsadu4(lo_bytes[y], lo_bytes[y + 1]) + __vsadu4(hi_bytes[y], hi_bytes[y + 1]) + horizontal;
+    const uint32_t shifted = (row[y] >> 2) | (right[y] << 14);  // pixel x+1 in the place of pixel x
+    vertical = __vsadu4(lo_bytes[y], pv_fields_to_bytes(shifted & 0xffu)) +
+               __vsadu4(hi_bytes[y], pv_fields_to_bytes(shifted >> 8)) + vertical;
+  }
   enum { k1Bpp, kAverage4, kVertical, kHorizontal } mode;
   if (inter <= 4u)
     mode = k1Bpp;
@@ -164,25 +194,16 @@ __device__ __forceinline__ uint32_t pv_pack_modulation(const uint32_t (&m)[5][9]
   else
     mode = kAverage4;
 
-  uint32_t bits = 0;
-  if (mode == k1Bpp) {
-#pragma unroll
-    for (int y = 0; y < 4; ++y)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) bits |= (m[y][x] >> 1) << (8 * y + x);
+  uint32_t bits;
+  if (mode == k1Bpp) {  // one bit per pixel: value / 2, raster order
+    bits = pv_high_bits(row[0]) | (pv_high_bits(row[1]) << 8) | (pv_high_bits(row[2]) << 16) | (pv_high_bits(row[3]) << 24);
   } else {
-    int pos = 0;
-#pragma unroll
-    for (int y = 0; y < 4; ++y)
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        if ((x ^ y) & 1) continue;  // checkerboard
-        uint32_t v = m[y][x];
-        if (pos == 0) v = (mode == kAverage4) ? (v & 2u) : (v | 1u);
-        if (pos == 20) v = (mode == kVertical) ? (v | 1u) : (v & 2u);
-        bits |= v << pos;
-        pos += 2;
-      }
+    // checkerboard (x ^ y even), two bits each in raster order: even rows keep fields 0,2,4,6, odd rows 1,3,5,7
+    bits = pv_even_fields(row[0]) | (pv_even_fields(row[1] >> 2) << 8) | (pv_even_fields(row[2]) << 16) |
+           (pv_even_fields(row[3] >> 2) << 24);
+    // the low bit of the entries at bit positions 0 and 20 carries the sub-mode instead of data
+    bits = (mode == kAverage4) ? (bits & ~1u) : (bits | 1u);
+    bits = (mode == kVertical) ? (bits | (1u << 20)) : (bits & ~(1u << 20));
   }
   *one_bpp = (mode == k1Bpp);
   return bits;

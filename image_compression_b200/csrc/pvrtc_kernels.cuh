@@ -2,12 +2,13 @@
 // /root/reference/image_compression/internal/pvrtc_compressor.cc:586-597 = Morph :506-521, Modulate :527-540,
 // Encode :551-580).
 //
-// Two kernels instead of the reference's three passes:
-//   pvrtc_morph_kernel       one thread per 8x4 block -> bit-reduced A and B colours (two w/8 x h/4 images)
-//   pvrtc_modulate_kernel    one thread per block: bilinear upscale of A and B over the block plus the wrapped
-//                            pixel column to its right and row below (all the mode decision needs), modulation
-//                            choice per pixel, mode + bit packing, store at the block's Z-order slot.  The
-//                            per-pixel modulation image of the reference is never written to memory.
+// Three kernels, all coalesced and small enough to stay in the instruction cache:
+//   pvrtc_morph_kernel     one thread per 8x4 block -> bit-reduced A and B colours (two w/8 x h/4 images, scratch)
+//   pvrtc_modulate_kernel  one thread per 8-pixel row segment: bilinear upscale of A and B (toroidal), modulation
+//                          choice per pixel, eight 2-bit values packed into one uint16 of scratch.  The
+//                          reference's byte-per-pixel modulation image becomes 2 bits per pixel and stays in L2.
+//   pvrtc_pack_kernel      one thread per block: its 4 row words plus the wrapped column to the right and row
+//                          below (all the mode decision needs), mode + bit packing, store at the Z-order slot.
 #pragma once
 #include <cstdint>
 
@@ -19,6 +20,7 @@ struct PvrtcParams {
   const uint32_t *src;  // RGBA8 pixels, row-major, no padding
   uint32_t *low_a;      // (w/8) x (h/4) A colours
   uint32_t *low_b;      // (w/8) x (h/4) B colours
+  uint16_t *mod;        // h x (w/8) words: 2-bit modulation of pixels 8*bx .. 8*bx+7 of row y
   uint2 *dst;           // w*h/32 blocks in Z-order
   uint32_t width, height;
 };
@@ -28,71 +30,73 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * lh) return;
   const uint32_t bx = t % lw, by = t / lw;
+  const uint32_t *origin = p.src + static_cast<size_t>(by * 4) * p.width + bx * 8;
   uint32_t px[32];
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
-    const uint4 *row = reinterpret_cast<const uint4 *>(p.src + static_cast<size_t>(by * 4 + y) * p.width + bx * 8);
+    const uint4 *row = reinterpret_cast<const uint4 *>(origin + static_cast<size_t>(y) * p.width);
     const uint4 u = __ldg(row), v = __ldg(row + 1);
     px[8 * y + 0] = u.x; px[8 * y + 1] = u.y; px[8 * y + 2] = u.z; px[8 * y + 3] = u.w;
     px[8 * y + 4] = v.x; px[8 * y + 5] = v.y; px[8 * y + 6] = v.z; px[8 * y + 7] = v.w;
   }
+  auto fetch = [&](uint32_t j) { return __ldg(origin + static_cast<size_t>(j >> 3) * p.width + (j & 7u)); };
   uint32_t ca, cb;
-  pv_block_extremes(px, __ldg(p.src), &ca, &cb);
+  pv_block_extremes(px, __ldg(p.src), fetch, &ca, &cb);
   p.low_a[t] = ca;
   p.low_b[t] = cb;
 }
 
-__global__ void __launch_bounds__(128) pvrtc_modulate_kernel(const PvrtcParams p) {
+__global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p) {
+  const uint32_t lw = p.width >> 3, lh = p.height >> 2;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lw * p.height) return;
+  const uint32_t bx = t % lw, y = t / lw;
+  // Low-resolution rows/columns this pixel row interpolates between, wrapped (pvrtc_compressor.cc:216-223).
+  const uint32_t top = ((y - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
+  const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
+  const uint32_t fy = (y + 2u) & 3u;
+  PvLanes va[3], vb[3];  // vertical blend, shared by the whole row: (4-fy)*top + fy*bottom, not yet divided
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const PvLanes at = pv_split(__ldg(p.low_a + top * lw + col[i])), ab = pv_split(__ldg(p.low_a + bottom * lw + col[i]));
+    const PvLanes bt = pv_split(__ldg(p.low_b + top * lw + col[i])), bb = pv_split(__ldg(p.low_b + bottom * lw + col[i]));
+    va[i].rb = at.rb * (4u - fy) + ab.rb * fy;
+    va[i].ga = at.ga * (4u - fy) + ab.ga * fy;
+    vb[i].rb = bt.rb * (4u - fy) + bb.rb * fy;
+    vb[i].ga = bt.ga * (4u - fy) + bb.ga * fy;
+  }
+  const uint4 *row = reinterpret_cast<const uint4 *>(p.src + static_cast<size_t>(y) * p.width + bx * 8);
+  const uint4 u = __ldg(row), v = __ldg(row + 1);
+  const uint32_t px[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    const int left = x < 4 ? 0 : 1;       // pixels 0..3 sit between columns (bx-1, bx), 4..7 between (bx, bx+1)
+    const uint32_t fx = (x + 4) & 7;
+    // ((8-fx)*V_left + fx*V_right) / 32, V <= 4*255: weights scaled by 8 so the divisor is 256 (lanes < 2^16)
+    const uint32_t ca = pv_blend256(va[left], 64u - 8u * fx, va[left + 1], 8u * fx);
+    const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
+    bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
+  }
+  p.mod[t] = static_cast<uint16_t>(bits);
+}
+
+__global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * lh) return;
   const uint32_t bx = t % lw, by = t / lw;
-
-  // 3x3 neighbourhood of low-resolution colours, wrapped (pvrtc_compressor.cc:216-223).
-  PvLanes na[3][3], nb[3][3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const uint32_t sx = (bx + lw + i - 1) & (lw - 1), sy = (by + lh + j - 1) & (lh - 1);
-      na[j][i] = pv_split(__ldg(p.low_a + sy * lw + sx));
-      nb[j][i] = pv_split(__ldg(p.low_b + sy * lw + sx));
-    }
-
-  uint32_t m[5][9];
+  const uint32_t right_bx = (bx + 1u) & (lw - 1u);
+  uint32_t row[5], right[4];
 #pragma unroll
   for (int y = 0; y < 5; ++y) {
-    // Source row (wrapped below the image) and the vertical blend shared by the whole row.
-    const uint32_t sy = (by * 4 + y) & (p.height - 1);
-    const uint32_t *row = p.src + static_cast<size_t>(sy) * p.width;
-    const int top = (y & 3) < 2 ? (y >> 2) : (y >> 2) + 1;  // rows y=0,1 use (by-1,by); 2,3 (by,by+1); 4 like 0 of next
-    const uint32_t fy = (y + 2) & 3;
-    // For y == 4 the pixel belongs to block by+1, whose neighbourhood is shifted one low-res row down; its
-    // rows (by, by+1) are still inside our 3x3 window.
-    PvLanes va[3], vb[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      va[i].rb = na[top][i].rb * (4u - fy) + na[top + 1][i].rb * fy;
-      va[i].ga = na[top][i].ga * (4u - fy) + na[top + 1][i].ga * fy;
-      vb[i].rb = nb[top][i].rb * (4u - fy) + nb[top + 1][i].rb * fy;
-      vb[i].ga = nb[top][i].ga * (4u - fy) + nb[top + 1][i].ga * fy;
-    }
-#pragma unroll
-    for (int x = 0; x < 9; ++x) {
-      if (y == 4 && x == 8) continue;  // corner is never read
-      const int left = (x & 7) < 4 ? (x >> 3) : (x >> 3) + 1;
-      const uint32_t fx = (x + 4) & 7;
-      const uint32_t sx = (bx * 8 + x) & (p.width - 1);
-      const uint32_t pixel = __ldg(row + sx);
-      const PvLanes ca = pv_mix(va[left], 8u - fx, va[left + 1], fx, 5u);
-      const PvLanes cb = pv_mix(vb[left], 8u - fx, vb[left + 1], fx, 5u);
-      m[y][x] = pv_pick_modulation(pixel, ca, cb);
-    }
+    const uint32_t sy = (by * 4u + y) & (p.height - 1u);  // y == 4: the wrapped row below
+    row[y] = p.mod[sy * lw + bx];
+    if (y < 4) right[y] = p.mod[sy * lw + right_bx] & 3u;  // wrapped pixel to the right of the row
   }
-  m[4][8] = 0;
   bool one_bpp;
-  const uint32_t mod_bits = pv_pack_modulation(m, &one_bpp);
-  const uint32_t colours = pv_pack_colours(pv_join(na[1][1]), pv_join(nb[1][1]), one_bpp);
+  const uint32_t mod_bits = pv_pack_modulation(row, right, &one_bpp);
+  const uint32_t colours = pv_pack_colours(__ldg(p.low_a + t), __ldg(p.low_b + t), one_bpp);
   p.dst[pv_z_index(bx, by)] = make_uint2(mod_bits, colours);
 }
 

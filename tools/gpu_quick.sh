@@ -15,5 +15,14 @@ except Exception as e:
 PY
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"encode4x4_tma|pvrtc" -s 4 -c 1 -o $OUT/prof_$wl \
       python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_$wl.log 2>&1; echo "ncu exit $?"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/launches_$wl.csv \
+      python bench.py --workload $wl --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_$wl.log 2>&1
+  python - <<PY
+import csv, collections
+rows = [r for r in csv.reader(open("$OUT/launches_$wl.csv")) if len(r) > 10 and r[0].isdigit()]
+agg = collections.defaultdict(list)
+for r in rows: agg[r[4][:70]].append(float(r[-1]))
+for k, v in agg.items(): print("   %-70s n=%2d avg %.1f us" % (k, len(v), sum(v)/len(v)/ (1000.0 if max(v) > 5000 else 1.0)))
+PY
 done
 if [ -x tools/microbench/pipe_rates ] && [ ! -f gpurun_out/pipe_rates.txt ]; then tools/microbench/pipe_rates > gpurun_out/pipe_rates.txt 2>&1; cat gpurun_out/pipe_rates.txt; fi
