@@ -129,21 +129,32 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 //   * per pixel, each of the three crossings is one saturating float add (1.0 if crossed, else 0.0) and one
 //     float multiply-add that accumulates the index change -- exact, since every value is an integer below 2^24,
 //     and it runs on the FMA pipes while the integer pipe, which bounds this kernel, only does the final bit
-//     insert.  The pixel value 2^23 + 16*l + i is produced directly in float format by the IDP.4A that computes
-//     the luminance (accumulator 0x4B000000 + i), so no int->float conversion is needed.
+//     insert.  The pixel value 2^23 + 16*l is produced directly in float format by the IDP.4A that computes the
+//     luminance (accumulator 0x4B000000), so no int->float conversion is needed.
 template <typename Fetch>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
-  uint32_t kf[16];  // 0x4B000000 + 16*lum + i: as an integer a (lum, index) key, as a float 2^23 + 16*lum + i
-  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  // kf[i] = 0x4B000000 + 16*lum: read as a float it is 2^23 + 16*lum, which the index search below consumes as is.
+  uint32_t kf[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    kf[i] = __dp4a(px[i], w16, 0x4b000000u + static_cast<uint32_t>(i));
-    kmin = min(kmin, kf[i]);                                                // first minimum in raster order
-    kmax = max(kmax, kf[i] ^ 15u);  // index field reversed: first maximum in raster order
-  }
+  for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, 0x4b000000u);
+  // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
+  // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
+  // folds two more registers (four pixels) per instruction.
+  uint32_t pk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) pk[k] = __byte_perm(kf[2 * k], kf[2 * k + 1], 0x5410) + ((2u * k) | ((2u * k + 1u) << 16));
+  uint32_t mn = __vimin3_u16x2(pk[0], pk[1], pk[2]);
+  mn = __vimin3_u16x2(mn, pk[3], pk[4]);
+  mn = __vimin3_u16x2(mn, pk[5], pk[6]);
+  mn = __vminu2(mn, pk[7]);
+  uint32_t mx = __vimax3_u16x2(pk[0] ^ 0x000f000fu, pk[1] ^ 0x000f000fu, pk[2] ^ 0x000f000fu);
+  mx = __vimax3_u16x2(mx, pk[3] ^ 0x000f000fu, pk[4] ^ 0x000f000fu);
+  mx = __vimax3_u16x2(mx, pk[5] ^ 0x000f000fu, pk[6] ^ 0x000f000fu);
+  mx = __vmaxu2(mx, pk[7] ^ 0x000f000fu);
+  const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
   uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
-  uint32_t lum0 = kmin & 0x000ffff0u, lum1 = kmax & 0x000ffff0u;  // 16 * luminance of p0 / p1
+  uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
   uint32_t bits;
