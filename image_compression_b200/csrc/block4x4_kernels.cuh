@@ -243,33 +243,40 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     };
     mbar_wait(full_s + 8 * stage, phase);
 
-    uint32_t px[16];
-    bool active = true;
+    uint8_t *out = p.dst + (static_cast<size_t>(tile_br + lby) * p.grid_cols + tile_bc + lbx) * kBlockBytes;
     if (tile_inside) {
+      if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
+        // RGB888 -> DXT1 never needs the unpacked pixels: luminance keys come straight from the row words
+        uint32_t rows[4][3];
 #pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const uint8_t *row = tile_bytes + own_off + y * (Shape::kRowWords * 4);
-        if constexpr (kNcomp == 4) {
-          const uint4 v = *reinterpret_cast<const uint4 *>(row);
-          px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
-        } else {
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(row);  // 12 bytes = four packed RGB pixels
-          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-          px[4 * y + 0] = w0 & 0x00ffffffu;
-          px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
-          px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
-          px[4 * y + 3] = w2 >> 8;
+        for (int y = 0; y < 4; ++y) {
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(tile_bytes + own_off + y * (Shape::kRowWords * 4));
+          rows[y][0] = w[0]; rows[y][1] = w[1]; rows[y][2] = w[2];
         }
-      }
-    } else {
-      active = tile_br + lby < p.row1 && tile_bc + lbx < p.col1;
-      if (active) {
+        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows(rows, p.swap_rb != 0, false, fetch);
+      } else {
+        uint32_t px[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) px[i] = fetch(i);
+        for (int y = 0; y < 4; ++y) {
+          const uint8_t *row = tile_bytes + own_off + y * (Shape::kRowWords * 4);
+          if constexpr (kNcomp == 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(row);
+            px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
+          } else {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(row);  // 12 bytes = four packed RGB pixels
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            px[4 * y + 0] = w0 & 0x00ffffffu;
+            px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+            px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
+            px[4 * y + 3] = w2 >> 8;
+          }
+        }
+        encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
       }
-    }
-    if (active) {
-      uint8_t *out = p.dst + (static_cast<size_t>(tile_br + lby) * p.grid_cols + tile_bc + lbx) * kBlockBytes;
+    } else if (tile_br + lby < p.row1 && tile_bc + lbx < p.col1) {
+      uint32_t px[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) px[i] = fetch(i);
       encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
     }
     __syncwarp();

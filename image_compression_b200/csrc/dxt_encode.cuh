@@ -131,13 +131,11 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 //     and it runs on the FMA pipes while the integer pipe, which bounds this kernel, only does the final bit
 //     insert.  The pixel value 2^23 + 16*l is produced directly in float format by the IDP.4A that computes the
 //     luminance (accumulator 0x4B000000), so no int->float conversion is needed.
+// kf[i] = 0x4B000000 + 16*lum(pixel i): read as a float it is 2^23 + 16*lum, which the index search consumes as is.
+constexpr uint32_t kDxtLumBias = 0x4b000000u;
+
 template <typename Fetch>
-__device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
-  const uint32_t w16 = dxt_lum_weights(swap_rb);
-  // kf[i] = 0x4B000000 + 16*lum: read as a float it is 2^23 + 16*lum, which the index search below consumes as is.
-  uint32_t kf[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, 0x4b000000u);
+__device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch) {
   // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
   // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
   // folds two more registers (four pixels) per instruction.
@@ -210,6 +208,37 @@ __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], boo
     }
   }
   return make_uint2(c0 | (c1 << 16), bits);
+}
+
+// Keys from 16 packed pixels (bytes c0,c1,c2,x in memory order; x ignored).
+template <typename Fetch>
+__device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
+  const uint32_t w16 = dxt_lum_weights(swap_rb);
+  uint32_t kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
+  return dxt1_encode_from_keys(kf, swap_rb, always4, fetch);
+}
+
+// Keys straight from four rows of packed RGB888 (three 32-bit words = four pixels per row): the byte weights of
+// IDP.4A do the unpacking, a pixel that straddles two words is two chained IDPs.  rows[y][0..2] = the 12 bytes.
+template <typename Fetch>
+__device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[4][3], bool swap_rb, bool always4, Fetch fetch) {
+  const uint32_t w = dxt_lum_weights(swap_rb);  // bytes (w0, w1, w2, 0) for memory-order channels 0,1,2
+  const uint32_t w0 = w & 0xffu, w1 = (w >> 8) & 0xffu, w2 = (w >> 16) & 0xffu;
+  const uint32_t wa = w;                                   // pixel 0: word 0 bytes 0,1,2
+  const uint32_t wb_lo = w0 << 24, wb_hi = w1 | (w2 << 8);  // pixel 1: word 0 byte 3, word 1 bytes 0,1
+  const uint32_t wc_lo = (w0 << 16) | (w1 << 24), wc_hi = w2;  // pixel 2: word 1 bytes 2,3, word 2 byte 0
+  const uint32_t wd = w << 8;                              // pixel 3: word 2 bytes 1,2,3
+  uint32_t kf[16];
+#pragma unroll
+  for (int y = 0; y < 4; ++y) {
+    kf[4 * y + 0] = __dp4a(rows[y][0], wa, kDxtLumBias);
+    kf[4 * y + 1] = __dp4a(rows[y][1], wb_hi, __dp4a(rows[y][0], wb_lo, kDxtLumBias));
+    kf[4 * y + 2] = __dp4a(rows[y][2], wc_hi, __dp4a(rows[y][1], wc_lo, kDxtLumBias));
+    kf[4 * y + 3] = __dp4a(rows[y][2], wd, kDxtLumBias);
+  }
+  return dxt1_encode_from_keys(kf, swap_rb, always4, fetch);
 }
 
 // ---------------------------------------------------------------------------------------------------------
