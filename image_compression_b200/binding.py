@@ -126,12 +126,7 @@ def encode_device(codec, fmt, src, h, w, pitch=None, coded_h=None, coded_w=None,
     return out
 
 
-def stripe_rows(grid_rows, rank, world):
-    """Block-row range [r0, r1) of rank `rank` when a grid of `grid_rows` block rows is split over `world` ranks
-    (contiguous stripes, the first grid_rows % world ranks take one extra row)."""
-    base, extra = divmod(grid_rows, world)
-    r0 = rank * base + min(rank, extra)
-    return r0, r0 + base + (1 if rank < extra else 0)
+from .sharding import stripe_rows  # noqa: E402,F401  (re-exported)
 
 
 def encode_stripe_device(codec, fmt, src_base_ptr, h, w, pitch, coded_h, coded_w, r0, r1, out, strategy=ETC_SMALLER_ERROR,
