@@ -228,11 +228,20 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     // Whole tile inside the image and inside this launch's block range: no clamping, no bounds checks.
     const bool tile_inside = (tile_br + Shape::kBlocksY) * 4u <= p.height && (tile_bc + Shape::kBlocksX) * 4u <= p.width &&
                              tile_br + Shape::kBlocksY <= p.row1 && tile_bc + Shape::kBlocksX <= p.col1;
-    // Last valid row / column, tile-relative, for clamp-to-edge replication.  The clamped coordinate never
-    // leaves the tile because every encoded window starts inside the image.
-    const uint32_t ymax = min(p.height - 1u - tile_br * 4u, static_cast<uint32_t>(Shape::kRows - 1));
-    const uint32_t xmax = min(p.width - 1u - tile_bc * 4u, static_cast<uint32_t>(Shape::kBlocksX * 4 - 1));
-    auto fetch = [&](uint32_t i) {
+    // Pixel i of this thread's window, re-read from the tile (the encoders look two pixels up by index).
+    auto fetch_inside = [&](uint32_t i) {
+      if constexpr (kNcomp == 4) {
+        return *reinterpret_cast<const uint32_t *>(tile_bytes + own_off + (i >> 2) * (Shape::kRowWords * 4) + (i & 3u) * 4u);
+      } else {
+        const uint8_t *q = tile_bytes + own_off + (i >> 2) * (Shape::kRowWords * 4) + (i & 3u) * 3u;
+        return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
+      }
+    };
+    // Same with clamp-to-edge replication for tiles that the image edge cuts through.  The clamped coordinate
+    // never leaves the tile because every encoded window starts inside the image.
+    auto fetch_edge = [&](uint32_t i) {
+      const uint32_t ymax = min(p.height - 1u - tile_br * 4u, static_cast<uint32_t>(Shape::kRows - 1));
+      const uint32_t xmax = min(p.width - 1u - tile_bc * 4u, static_cast<uint32_t>(Shape::kBlocksX * 4 - 1));
       const uint32_t y = min(lby * 4u + (i >> 2), ymax), x = min(lbx * 4u + (i & 3u), xmax);
       if constexpr (kNcomp == 4) {
         return *reinterpret_cast<const uint32_t *>(tile_bytes + (y * Shape::kRowWords + x) * 4u);
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
           const uint32_t *w = reinterpret_cast<const uint32_t *>(tile_bytes + own_off + y * (Shape::kRowWords * 4));
           rows[y][0] = w[0]; rows[y][1] = w[1]; rows[y][2] = w[2];
         }
-        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows(rows, p.swap_rb != 0, false, fetch);
+        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows(rows, p.swap_rb != 0, false, fetch_inside);
       } else {
         uint32_t px[16];
 #pragma unroll
@@ -271,13 +280,13 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
             px[4 * y + 3] = w2 >> 8;
           }
         }
-        encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
+        encode_and_store<kCodec>(px, fetch_inside, false, p.swap_rb, p.etc_strategy, alpha_table, out);
       }
     } else if (tile_br + lby < p.row1 && tile_bc + lbx < p.col1) {
       uint32_t px[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) px[i] = fetch(i);
-      encode_and_store<kCodec>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
+      for (int i = 0; i < 16; ++i) px[i] = fetch_edge(i);
+      encode_and_store<kCodec>(px, fetch_edge, false, p.swap_rb, p.etc_strategy, alpha_table, out);
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);

@@ -179,23 +179,44 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
                           16u * __umulhi(2u * b0 + b1, kThird);
     const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
                           16u * __umulhi(b0 + 2u * b1, kThird);
-    // Candidates as keys 16*L_c + c, sorted ascending.
-    uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
-    sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
-    const uint32_t sorted[4] = {s0, s1, s2, s3};
-    uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
-    float acc0 = __uint_as_float(0x4b000000u + (s0 & 3u));  // 2^23 + index of the lowest candidate
-    float cross[3], step[3];
+    float acc0, cross[3], step[3];
+    // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
+    // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
+    // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
+    // midpoints have to be computed.
+    const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
+    const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
+    if (__all_sync(__activemask(), rising || falling)) {
+      // ascending sequence: rising 0,2,3,1  falling 1,3,2,0 ; a tie goes to the smaller index
+      const uint32_t a0 = rising ? lum0 : lum1, a1 = rising ? lum2 : lum3, a2 = rising ? lum3 : lum2, a3 = rising ? lum1 : lum0;
+      const uint32_t h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
+      const uint32_t h2 = ((a1 + a2 + (rising ? 32u : 16u)) >> 1) & ~15u;    // 2->3 stays on tie, 3->2 moves
+      const uint32_t h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
+      cross[0] = __uint_as_float(kDxtLumBias + h1 - 1u);
+      cross[1] = __uint_as_float(kDxtLumBias + h2 - 1u);
+      cross[2] = __uint_as_float(kDxtLumBias + h3 - 1u);
+      step[0] = 2.0f;
+      step[1] = rising ? 1.0f : 3.0f;  // 2->3 is +1, 3->2 is -1 = +3 (mod 4)
+      step[2] = 2.0f;                  // 3->1 and 2->0 are both -2 = +2 (mod 4)
+      acc0 = __uint_as_float(kDxtLumBias + (rising ? 0u : 1u));
+    } else {
+      // General case (flat blocks, crossed or equal candidates): sort the candidates as keys 16*L_c + c.
+      uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
+      sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
+      const uint32_t sorted[4] = {s0, s1, s2, s3};
+      uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
+      acc0 = __uint_as_float(kDxtLumBias + (s0 & 3u));    // 2^23 + index of the lowest candidate
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const uint32_t b = sorted[j + 1];
-      const bool same_lum = (b - rep) < 4u;             // keys differ only in the index bits
-      const uint32_t cb = b & 3u, cr = rep & 3u;
-      // pixel key v = 16*l + i crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
-      const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
-      cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : 0x4b000000u + h - 1u);
-      step[j] = static_cast<float>((cb - cr) & 3u);  // irrelevant when same_lum: that crossing never fires
-      rep = same_lum ? rep : b;
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t b = sorted[j + 1];
+        const bool same_lum = (b - rep) < 4u;             // keys differ only in the index bits
+        const uint32_t cb = b & 3u, cr = rep & 3u;
+        // pixel key v = 16*l crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
+        const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
+        cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : kDxtLumBias + h - 1u);
+        step[j] = static_cast<float>((cb - cr) & 3u);  // irrelevant when same_lum: that crossing never fires
+        rep = same_lum ? rep : b;
+      }
     }
     bits = 0;
 #pragma unroll
