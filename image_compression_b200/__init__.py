@@ -8,6 +8,6 @@ the CUDA library has not been built, and every compute call fails if no CUDA dev
 from .binding import (  # noqa: F401
     BGR, BGRA, RGB, RGBA, CODEC_DXT1, CODEC_DXT5, CODEC_ETC1, CODEC_PVRTC2,
     ETC_HEURISTIC, ETC_SMALLER_ERROR, ETC_SPLIT_HORIZONTALLY, ETC_SPLIT_VERTICALLY,
-    IcbError, compress_host, compressed_size, encode_device, encode_stripe_device, fill_synthetic, launch_count,
+    IcbError, compress_host, compressed_size, decode_device, decompress_host, encode_device, encode_stripe_device, fill_synthetic, launch_count,
     lib, lib_path, pvrtc_encode_device, set_tma_mode, stripe_rows,
 )

@@ -37,6 +37,8 @@ PROTOTYPES = {
     "icb_pvrtc2_scratch_size": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "icb_pvrtc2_encode_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "icb_compress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "icb_decode4x4": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "icb_decompress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "icb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "icb_host_free": (None, [C.c_void_p]),
     "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -146,6 +148,26 @@ def pvrtc_encode_device(src, h, w, out=None, scratch=None, stream=None):
     with torch.cuda.device(src.device):
         _check(lib().icb_pvrtc2_encode_rgba8(src.data_ptr(), h, w, out.data_ptr(),
                                              scratch.data_ptr() if scratch is not None else None, _stream_ptr(stream)))
+    return out
+
+
+def decode_device(codec, blocks, h, w, swap_rb=0, block_cols=None, out=None, stream=None):
+    """Device-resident decode of a uint8 CUDA tensor of blocks -> uint8 CUDA tensor of h*w*(3|4) pixel bytes."""
+    import torch
+    nc = 4 if codec == CODEC_DXT5 else 3
+    block_cols = (w + 3) // 4 if block_cols is None else block_cols
+    if out is None:
+        out = torch.empty(h * w * nc, dtype=torch.uint8, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        _check(lib().icb_decode4x4(codec, blocks.data_ptr(), h, w, block_cols, swap_rb, out.data_ptr(), w * nc, _stream_ptr(stream)))
+    return out
+
+
+def decompress_host(codec, fmt, blocks, h, w, block_cols=None):
+    nc = 4 if codec == CODEC_DXT5 else 3
+    block_cols = (w + 3) // 4 if block_cols is None else block_cols
+    out = np.empty(h * w * nc, np.uint8)
+    _check(lib().icb_decompress_host(codec, fmt, h, w, block_cols, blocks.ctypes.data, blocks.size, out.ctypes.data, out.size))
     return out
 
 

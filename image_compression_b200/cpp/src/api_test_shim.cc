@@ -1,6 +1,7 @@
 // api_test_shim.cc -- extern "C" doorway used by tests/ to drive the C++ Compressor classes of this build exactly
 // the way oracle/ref_shim.cc drives the reference's, so the two can be compared call for call.
 #include <cstring>
+#include <vector>
 
 #include "image_compression/public/dxtc_compressor.h"
 #include "image_compression/public/etc_compressor.h"
@@ -52,6 +53,21 @@ __attribute__((visibility("default"))) long icapi_pvrtc(int format, unsigned h, 
                                                         unsigned *meta, int external) {
   PvrtcCompressor c;
   return Run(&c, format, h, w, 0, 0, 0, padding, src, dst, dst_cap, meta, external);
+}
+// Compress then Decompress through the classes; returns decompressed bytes (0 on failure).
+__attribute__((visibility("default"))) long icapi_roundtrip(int codec, int strategy, int format, unsigned h, unsigned w,
+                                                            const unsigned char *src, unsigned char *dst, size_t dst_cap) {
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  etc.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  Compressor *c = codec == 2 ? static_cast<Compressor *>(&etc) : static_cast<Compressor *>(&dxt);
+  CompressedImage image;
+  if (!c->Compress(static_cast<CompressedImage::Format>(format), h, w, 0, src, &image)) return 0;
+  std::vector<uint8> out;
+  if (!c->Decompress(image, &out)) return 0;
+  if (out.size() > dst_cap) return -1;
+  std::memcpy(dst, out.data(), out.size());
+  return static_cast<long>(out.size());
 }
 __attribute__((visibility("default"))) size_t icapi_size(int codec, int format, unsigned h, unsigned w) {
   const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);

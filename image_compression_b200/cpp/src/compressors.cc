@@ -51,6 +51,20 @@ bool Encode4x4(int codec, const char *name, size_t block_size, CompressedImage::
 
 bool IsPowerOfTwo(uint32 x) { return x != 0 && (x & (x - 1)) == 0; }
 
+// Compressor4x4Helper::Decompress (internal/compressor4x4_helper.h:218-262) on the GPU: the buffer is resized to
+// uncompressed_height * uncompressed_width pixels and blocks are walked ceil(uncompressed_width / 4) per row, as
+// the reference does.  The reference writes rows padding_bytes_per_row apart into a buffer that has no room for the
+// padding (undefined behaviour when padding != 0); this build refuses that case instead.
+bool Decode4x4(int codec, const CompressedImage &image, std::vector<uint8> *out) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  if (m.padding_bytes_per_row != 0) return false;
+  const size_t ncomp = codec == ICB_CODEC_DXT5 ? 4 : 3;
+  out->resize(static_cast<size_t>(m.uncompressed_height) * m.uncompressed_width * ncomp);
+  return icb_decompress_host(codec, static_cast<int>(m.format), m.uncompressed_height, m.uncompressed_width,
+                             NumBlocks(m.uncompressed_width), image.GetData(), image.GetDataSize(), &out->at(0),
+                             out->size()) == ICB_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -92,8 +106,13 @@ bool DxtcCompressor::CompressAndPad(CompressedImage::Format format, uint32 heigh
                    padded_height, padded_width, padding_bytes_per_row, 0, buffer, padded_image);
 }
 
-// Outside the GPU compress path; see DESIGN.md ("next" rows of SURVEY.md section 8f).
-bool DxtcCompressor::Decompress(const CompressedImage &, std::vector<uint8> *) { return false; }
+bool DxtcCompressor::Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) {
+  if (!IsValidCompressedImage(image) || !decompressed_buffer) return false;
+  const bool dxt1 = GetNumFormatComponents(image.GetMetadata().format) == 3;
+  return Decode4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, image, decompressed_buffer);
+}
+
+// Outside the GPU paths built so far; see DESIGN.md ("next" rows of SURVEY.md section 8f).
 bool DxtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
 bool DxtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
 bool DxtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
@@ -140,7 +159,10 @@ bool EtcCompressor::CompressAndPad(CompressedImage::Format format, uint32 height
                    padding_bytes_per_row, static_cast<int>(compression_strategy_), buffer, padded_image);
 }
 
-bool EtcCompressor::Decompress(const CompressedImage &, std::vector<uint8> *) { return false; }
+bool EtcCompressor::Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) {
+  if (!IsValidCompressedImage(image) || !decompressed_buffer) return false;
+  return Decode4x4(ICB_CODEC_ETC1, image, decompressed_buffer);
+}
 bool EtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
 bool EtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
 bool EtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {

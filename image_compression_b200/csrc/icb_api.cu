@@ -14,6 +14,7 @@
 
 #include "../../include/icb200.h"
 #include "block4x4_kernels.cuh"
+#include "decode4x4_kernels.cuh"
 #include "pvrtc_kernels.cuh"
 
 namespace {
@@ -384,6 +385,57 @@ int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_d
   g_launches.fetch_add(3, std::memory_order_relaxed);
   ICB_CUDA(cudaGetLastError());
   if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));
+  return ICB_OK;
+}
+
+int icb_decode4x4(int codec, const void *d_blocks, uint32_t h, uint32_t w, uint32_t block_cols, int swap_rb, void *d_dst,
+                  size_t dst_pitch, void *stream) {
+  if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (h == 0 || w == 0 || block_cols == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+  if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_INVALID, "codec %d has no decoder", codec);
+  const size_t ncomp = codec == ICB_CODEC_DXT5 ? 4 : 3;
+  if (dst_pitch < w * ncomp || dst_pitch > 0xffffffffull) return fail(ICB_ERR_INVALID, "bad destination pitch %zu", dst_pitch);
+  DeviceInfo info;
+  if (int s = device_info(&info)) return s;
+  icb::Decode4x4Params p;
+  p.blocks = static_cast<const uint8_t *>(d_blocks);
+  p.dst = static_cast<uint8_t *>(d_dst);
+  p.height = h;
+  p.width = w;
+  p.pitch = static_cast<uint32_t>(dst_pitch);
+  p.block_cols = block_cols;
+  p.block_rows = (h + 3) / 4;
+  p.swap_rb = swap_rb ? 1 : 0;
+  const uint64_t total = static_cast<uint64_t>(p.block_rows) * block_cols;
+  const uint64_t want = (total + 127) / 128;
+  const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(info.sm_count) * 32 ? want : info.sm_count * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (codec == ICB_CODEC_DXT1) icb::decode4x4_kernel<0><<<grid, 128, 0, st>>>(p);
+  if (codec == ICB_CODEC_DXT5) icb::decode4x4_kernel<1><<<grid, 128, 0, st>>>(p);
+  if (codec == ICB_CODEC_ETC1) icb::decode4x4_kernel<2><<<grid, 128, 0, st>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+int icb_decompress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t block_cols, const void *blocks,
+                        size_t blocks_size, void *dst, size_t dst_size) {
+  if (!blocks || !dst || h == 0 || w == 0 || block_cols == 0) return fail(ICB_ERR_INVALID, "null buffer or zero dimension");
+  if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_INVALID, "codec %d has no decoder", codec);
+  if (format < ICB_RGB || format > ICB_BGRA) return fail(ICB_ERR_INVALID, "unknown format %d", format);
+  const size_t ncomp = codec == ICB_CODEC_DXT5 ? 4 : 3, block_bytes = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  const size_t need_in = static_cast<size_t>((h + 3) / 4) * block_cols * block_bytes, need_out = static_cast<size_t>(h) * w * ncomp;
+  if (blocks_size < need_in) return fail(ICB_ERR_SIZE, "block stream is %zu bytes, need %zu", blocks_size, need_in);
+  if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
+  if (int s = t_pipe.prepare()) return s;
+  HostPipe &pipe = t_pipe;
+  if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_in)) return s;     // blocks live in the "dst" buffer
+  if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_out)) return s;    // pixels in the "src" buffer
+  ICB_CUDA(cudaMemcpyAsync(pipe.d_dst, blocks, need_in, cudaMemcpyHostToDevice, pipe.compute));
+  const int swap_rb = (format == ICB_BGR || format == ICB_BGRA);
+  if (int s = icb_decode4x4(codec, pipe.d_dst, h, w, block_cols, swap_rb, pipe.d_src, w * ncomp, pipe.compute)) return s;
+  ICB_CUDA(cudaMemcpyAsync(dst, pipe.d_src, need_out, cudaMemcpyDeviceToHost, pipe.compute));
+  ICB_CUDA(cudaStreamSynchronize(pipe.compute));
   return ICB_OK;
 }
 

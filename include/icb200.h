@@ -117,6 +117,18 @@ ICB_API int icb_compress_host(int codec, int format, uint32_t height, uint32_t w
                       uint32_t padded_width, uint32_t padding_bytes_per_row, int etc_strategy, const void *src,
                       void *dst, size_t dst_size);
 
+/*
+ * Block decoders (DXT1 -> RGB888, DXT5 -> RGBA8888, ETC1 -> RGB888), the step after the compress path:
+ * Compressor4x4Helper::Decompress (internal/compressor4x4_helper.h:218-262).  d_blocks holds
+ * ceil(height/4) * block_cols blocks in raster order (the reference walks ceil(uncompressed_width/4) blocks per
+ * row; pass that); pixels outside height x width are dropped.  d_dst rows are dst_pitch bytes apart.
+ */
+ICB_API int icb_decode4x4(int codec, const void *d_blocks, uint32_t height, uint32_t width, uint32_t block_cols,
+                          int swap_rb, void *d_dst, size_t dst_pitch, void *stream);
+/* Host-buffer form: blocks in, height*width*(3|4) bytes of pixels out (rows contiguous).  Blocking. */
+ICB_API int icb_decompress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t block_cols,
+                                const void *blocks, size_t blocks_size, void *dst, size_t dst_size);
+
 /* Page-locked host memory for icb_compress_host callers. */
 ICB_API void *icb_host_alloc(size_t bytes);
 ICB_API void icb_host_free(void *p);

@@ -84,6 +84,26 @@ int icref_etc_external(int strategy, unsigned h, unsigned w, unsigned padding, c
   return c.Compress(CompressedImage::kRGB, h, w, padding, src, &image) ? 1 : 0;
 }
 
+// Decompress a block stream through the reference's Decompress().  The CompressedImage is produced by compressing
+// a dummy image of the right shape into external storage (which sets the metadata) and then overwriting the
+// storage with `blocks`.  Returns bytes written to dst, 0 on failure.
+long icref_decompress(int codec, int strategy, int format, unsigned h, unsigned w, const unsigned char *blocks,
+                      size_t nbytes, unsigned char *dst, size_t dst_cap) {
+  std::vector<unsigned char> storage(nbytes), dummy(static_cast<size_t>(h) * w * 4, 0);
+  CompressedImage image(nbytes, storage.data());
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  etc.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  Compressor *c = codec == 2 ? static_cast<Compressor *>(&etc) : static_cast<Compressor *>(&dxt);
+  if (!c->Compress(static_cast<CompressedImage::Format>(format), h, w, 0, dummy.data(), &image)) return 0;
+  std::memcpy(storage.data(), blocks, nbytes);
+  std::vector<uint8> out;
+  if (!c->Decompress(image, &out)) return 0;
+  if (out.size() > dst_cap) return -1;
+  std::memcpy(dst, out.data(), out.size());
+  return static_cast<long>(out.size());
+}
+
 size_t icref_size(int codec, int format, unsigned h, unsigned w) {
   if (codec == 0) return DxtcCompressor().ComputeCompressedDataSize(static_cast<CompressedImage::Format>(format), h, w);
   if (codec == 1) return EtcCompressor().ComputeCompressedDataSize(static_cast<CompressedImage::Format>(format), h, w);

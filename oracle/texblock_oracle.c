@@ -787,6 +787,110 @@ size_t orc_pvrtc2_compress(uint32_t h, uint32_t w, const uint8_t *src, uint8_t *
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Decoders                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* DecodeColors (dxtc_compressor.cc:167-193): the four palette entries, channel by channel with truncation. */
+static void dxt_palette(const uint8_t *b, int swap, int always4, uint8_t pal[4][3]) {
+  int c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+  int e[2][3] = {{expand5(c0 >> 11), expand6((c0 >> 5) & 63), expand5(c0 & 31)},
+                 {expand5(c1 >> 11), expand6((c1 >> 5) & 63), expand5(c1 & 31)}};
+  for (int k = 0; k < 2; ++k) {
+    pal[k][0] = (uint8_t)(swap ? e[k][2] : e[k][0]);
+    pal[k][1] = (uint8_t)e[k][1];
+    pal[k][2] = (uint8_t)(swap ? e[k][0] : e[k][2]);
+  }
+  for (int ch = 0; ch < 3; ++ch) {
+    if (c0 == c1) {
+      pal[2][ch] = pal[3][ch] = pal[1][ch];
+    } else if (always4 || c0 > c1) {
+      pal[2][ch] = (uint8_t)((2 * pal[0][ch] + pal[1][ch]) / 3);
+      pal[3][ch] = (uint8_t)((pal[0][ch] + 2 * pal[1][ch]) / 3);
+    } else {
+      pal[2][ch] = (uint8_t)((pal[0][ch] + pal[1][ch]) / 2);
+      pal[3][ch] = 0;
+    }
+  }
+}
+
+static void decode_dxt_block(const uint8_t *blk, int dxt5, int swap, uint8_t out[16][4]) {
+  const uint8_t *colour = dxt5 ? blk + 8 : blk;
+  uint8_t pal[4][3], alpha[8];
+  dxt_palette(colour, swap, dxt5, pal);
+  uint64_t abits = 0;
+  if (dxt5) { /* DecodeAlphaValues (dxtc_compressor.cc:196-219) */
+    int a0 = blk[0], a1 = blk[1];
+    alpha[0] = (uint8_t)a0;
+    alpha[1] = (uint8_t)a1;
+    if (a0 > a1) {
+      for (int k = 1; k <= 6; ++k) alpha[1 + k] = (uint8_t)(((7 - k) * a0 + k * a1) / 7);
+    } else {
+      for (int k = 1; k <= 4; ++k) alpha[1 + k] = (uint8_t)(((5 - k) * a0 + k * a1) / 5);
+      alpha[6] = 0;
+      alpha[7] = 255;
+    }
+    for (int k = 0; k < 6; ++k) abits |= (uint64_t)blk[2 + k] << (8 * k);
+  }
+  for (int i = 0; i < 16; ++i) {
+    int code = (colour[4 + (i >> 2)] >> (2 * (i & 3))) & 3;
+    out[i][0] = pal[code][0];
+    out[i][1] = pal[code][1];
+    out[i][2] = pal[code][2];
+    out[i][3] = dxt5 ? alpha[(abits >> (3 * i)) & 7] : 255;
+  }
+}
+
+/* Etc1BlockDecoder (etc_compressor.cc:226-273) */
+static void decode_etc1_block(const uint8_t *blk, uint8_t out[16][4]) {
+  uint32_t hi = ((uint32_t)blk[0] << 24) | ((uint32_t)blk[1] << 16) | ((uint32_t)blk[2] << 8) | blk[3];
+  uint32_t lo = ((uint32_t)blk[4] << 24) | ((uint32_t)blk[5] << 16) | ((uint32_t)blk[6] << 8) | blk[7];
+  int flip = hi & 1, diff = (hi >> 1) & 1;
+  int cw[2] = {(int)((hi >> 5) & 7), (int)((hi >> 2) & 7)};
+  int base[2][3];
+  static const int shift5[3] = {27, 19, 11}, shift3[3] = {24, 16, 8}, shift4a[3] = {28, 20, 12}, shift4b[3] = {24, 16, 8};
+  for (int k = 0; k < 3; ++k) {
+    if (diff) {
+      int b5 = (int)((hi >> shift5[k]) & 31);
+      int d3 = (int)((hi >> shift3[k]) & 7);
+      if (d3 & 4) d3 -= 8; /* ExtendSignBit */
+      int second = b5 + d3; /* may leave 0..31 for blocks no encoder produces; arithmetic as in the reference */
+      base[0][k] = (b5 << 3) | ((b5 >> 2) & 7);
+      base[1][k] = (second * 8) | ((second >> 2) & 7); /* Extend5Bit on a plain int, arithmetic shift */
+    } else {
+      int a = (int)((hi >> shift4a[k]) & 15), b = (int)((hi >> shift4b[k]) & 15);
+      base[0][k] = a * 17;
+      base[1][k] = b * 17;
+    }
+  }
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) {
+      int p = 4 * x + y;
+      int idx = (int)((lo >> p) & 1) | (int)(((lo >> (p + 16)) & 1) << 1);
+      int second = flip ? (y >= 2) : (x >= 2);
+      int m = k_etc_codebook[cw[second]][idx];
+      for (int k = 0; k < 3; ++k) out[4 * y + x][k] = (uint8_t)clamp255(base[second][k] + m);
+      out[4 * y + x][3] = 255;
+    }
+}
+
+void orc_decode4x4(int codec, int swap_rb, uint32_t h, uint32_t w, uint32_t block_cols, const uint8_t *blocks,
+                   uint8_t *dst) {
+  uint32_t nbr = orc_num_blocks(h), bb = codec == 1 ? 16u : 8u, nc = codec == 1 ? 4u : 3u;
+  const uint8_t *blk = blocks;
+  uint8_t px[16][4];
+  for (uint32_t br = 0; br < nbr; ++br)
+    for (uint32_t bc = 0; bc < block_cols; ++bc, blk += bb) {
+      if (codec == 2)
+        decode_etc1_block(blk, px);
+      else
+        decode_dxt_block(blk, codec == 1, swap_rb, px);
+      for (uint32_t y = 0; y < 4 && 4 * br + y < h; ++y)
+        for (uint32_t x = 0; x < 4 && 4 * bc + x < w; ++x)
+          memcpy(dst + ((size_t)(4 * br + y) * w + 4 * bc + x) * nc, px[4 * y + x], nc);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Synthetic input + hash                                                     */
 /* ------------------------------------------------------------------------------------------------ */
 

@@ -42,6 +42,8 @@ def oracle():
             getattr(lib, name).argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
         lib.orc_pvrtc2_compress.restype = C.c_size_t
         lib.orc_pvrtc2_compress.argtypes = [C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_decode4x4.restype = None
+        lib.orc_decode4x4.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
         lib.orc_fill_synthetic.restype = None
         lib.orc_fill_synthetic.argtypes = [_u8p, C.c_size_t, C.c_uint64, C.c_uint64]
         lib.orc_fnv1a64.restype = C.c_uint64
@@ -69,6 +71,8 @@ def ref():
         lib.icref_dxt_external.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
         lib.icref_etc_external.restype = C.c_int
         lib.icref_etc_external.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
+        lib.icref_decompress.restype = C.c_long
+        lib.icref_decompress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, _u8p, C.c_size_t, _u8p, C.c_size_t]
         lib.icref_size.restype = C.c_size_t
         lib.icref_size.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint]
         _ref = lib
@@ -117,6 +121,21 @@ def oracle_pvrtc(img, h, w):
     n = oracle().orc_pvrtc2_compress(h, w, _ptr(img), _ptr(out))
     assert n == out.size
     return out
+
+
+def oracle_decode(codec, blocks, h, w, swap_rb=0, block_cols=None):
+    """codec: 0 DXT1 -> RGB888, 1 DXT5 -> RGBA8888, 2 ETC1 -> RGB888."""
+    block_cols = nblocks(w) if block_cols is None else block_cols
+    out = np.zeros(h * w * (4 if codec == 1 else 3), np.uint8)
+    oracle().orc_decode4x4(codec, swap_rb, h, w, block_cols, _ptr(blocks), _ptr(out))
+    return out
+
+
+def ref_decompress(codec, fmt, blocks, h, w):
+    """The reference's Decompress() on a block stream of an h x w image (codec 0/1 = DxtcCompressor, 2 = ETC)."""
+    out = np.zeros(h * w * 4 + 16, np.uint8)
+    n = ref().icref_decompress(codec, 2, fmt, h, w, _ptr(blocks), blocks.size, _ptr(out), out.size)
+    return out[:n].copy() if n > 0 else None
 
 
 def synthetic(nbytes, seed, offset=0):

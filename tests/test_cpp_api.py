@@ -93,3 +93,22 @@ def test_compress_matches_oracle_and_metadata(api):
         got, meta = call(api.icapi_pvrtc, (fmt, 32, 32, 0, img.ctypes.data_as(_u8p)), 4096)
         assert np.array_equal(got, ck.oracle_pvrtc(img.ravel(), 32, 32))
         assert meta == [fmt, 32, 32, 32, 32, 0, 5]
+
+
+@pytest.mark.gpu
+def test_compress_then_decompress_matches_reference_round_trip(api):
+    """Decompress() of the drop-in classes == oracle decode of oracle encode (and == the reference when present)."""
+    api.icapi_roundtrip.restype = C.c_long
+    api.icapi_roundtrip.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
+    for codec, fmt in ((0, ck.RGB), (0, ck.BGR), (1, ck.RGBA), (1, ck.BGRA), (2, ck.RGB)):
+        nc = ck.ncomp(fmt)
+        for (h, w) in ((16, 16), (9, 13), (40, 28)):
+            img = imagegen.make("smooth_noise", h, w, nc, seed=24)
+            out = np.zeros(h * w * 4, np.uint8)
+            n = api.icapi_roundtrip(codec, 2, fmt, h, w, img.ctypes.data_as(_u8p), out.ctypes.data_as(_u8p), out.size)
+            assert n == h * w * nc
+            blocks = ck.oracle_etc1(2, img.ravel(), h, w) if codec == 2 else ck.oracle_dxt(fmt, img.ravel(), h, w)
+            want = ck.oracle_decode(codec, blocks, h, w, swap_rb=1 if fmt in (ck.BGR, ck.BGRA) else 0)
+            assert np.array_equal(out[:n], want), (codec, fmt, h, w)
+            if ck.have_ref():
+                assert np.array_equal(ck.ref_decompress(codec, fmt, blocks, h, w), want)

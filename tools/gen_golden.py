@@ -73,6 +73,20 @@ def main():
     np.savez_compressed(out_path, **arrays)
     print("wrote %s: %d cases, %d bytes" % (out_path, len(index), os.path.getsize(out_path)))
 
+    # Decoder fixture: CRC-32 of the REFERENCE's Decompress() of every unpadded DXT/ETC golden output.
+    import zlib
+    crcs = {}
+    for i, meta in enumerate(index):
+        if meta["codec"] == "pvrtc" or meta["padded"]:
+            continue
+        codec = 2 if meta["codec"] == "etc" else (0 if meta["ncomp"] == 3 else 1)
+        px = ck.ref_decompress(codec, meta["format"], np.ascontiguousarray(arrays["out_%d" % i]), meta["h"], meta["w"])
+        assert px is not None, meta
+        crcs[str(i)] = zlib.crc32(px.tobytes())
+    crc_path = os.path.join(ROOT, "tests", "golden", "decode_crc_v1.json")
+    json.dump(crcs, open(crc_path, "w"))
+    print("wrote %s: %d decode checksums" % (crc_path, len(crcs)))
+
 
 if __name__ == "__main__":
     main()
