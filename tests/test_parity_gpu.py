@@ -254,3 +254,68 @@ def test_encode_decode_round_trip_full_size(icb):
     back = icb.decode_device(1, blocks, n, n).view(n, n, 4)
     err = (back.int() - img.int()).abs()
     assert int(err.max()) <= 24 and float(err.float().mean()) < 3.0
+
+
+def test_tma_path_small_wide_and_odd_stripes(icb):
+    """Forced TMA path on shapes smaller than a tile, much wider than a tile row, and stripes that start in the
+    middle of a tile row."""
+    for (h, w) in ((4, 4), (4, 16), (16, 16), (8, 4096), (12, 16388), (100, 260)):
+        img = imagegen.make("random", h, w, 4, seed=51)
+        for codec, want in ((0, ck.oracle_dxt1_rgba(img.ravel(), h, w)), (1, ck.oracle_dxt(ck.RGBA, img.ravel(), h, w))):
+            got = gpu_encode(icb, codec, ck.RGBA, img.ravel(), h, w, tma=1)
+            assert np.array_equal(got, want), (codec, h, w)
+    h, w = 160, 512
+    img = dev(imagegen.make("smooth_noise", h, w, 4, seed=52).ravel())
+    whole = icb.encode_device(1, ck.RGBA, img, h, w).cpu().numpy()
+    prev = icb.set_tma_mode(1)
+    try:
+        for (r0, r1) in ((0, 1), (1, 7), (7, 40), (3, 39), (39, 40)):
+            out = torch.empty((r1 - r0) * (w // 4) * 16, dtype=torch.uint8, device="cuda")
+            icb.encode_stripe_device(1, ck.RGBA, img.data_ptr(), h, w, w * 4, h, w, r0, r1, out)
+            assert np.array_equal(out.cpu().numpy(), whole[r0 * (w // 4) * 16:r1 * (w // 4) * 16]), (r0, r1)
+    finally:
+        icb.set_tma_mode(prev)
+
+
+def test_large_row_padding(icb):
+    """Row pitch far larger than the row (aligned and unaligned), device and host paths."""
+    for padding in (4096, 4099):
+        for fmt, codec in ((ck.RGBA, 1), (ck.RGB, 0), (ck.RGB, 2)):
+            nc = ck.ncomp(fmt)
+            img = imagegen.make("gradient", 24, 40, nc, seed=53)
+            buf, pitch = imagegen.with_row_padding(img, padding)
+            want = ck.oracle_etc1(2, buf, 24, 40, None, None, padding) if codec == 2 else ck.oracle_dxt(fmt, buf, 24, 40, None, None, padding)
+            assert np.array_equal(gpu_encode(icb, codec, fmt, buf, 24, 40, pitch=pitch), want), (padding, fmt, codec)
+            assert np.array_equal(icb.compress_host(codec, fmt, buf, 24, 40, padding=padding), want), (padding, fmt, codec)
+
+
+def test_host_path_is_thread_safe(icb):
+    """Concurrent Compress calls from several host threads (the reference is re-entrant; so is this build)."""
+    import threading
+    jobs = []
+    for i, (codec, fmt) in enumerate(((0, ck.RGB), (1, ck.RGBA), (2, ck.RGB), (3, ck.RGBA), (0, ck.BGR), (1, ck.BGRA))):
+        n = 64 if codec == 3 else 72 + 4 * i
+        img = imagegen.make("smooth_noise", n, n, ck.ncomp(fmt), seed=60 + i)
+        if codec == 3:
+            want = ck.oracle_pvrtc(img.ravel(), n, n)
+        elif codec == 2:
+            want = ck.oracle_etc1(2, img.ravel(), n, n)
+        else:
+            want = ck.oracle_dxt(fmt, img.ravel(), n, n)
+        jobs.append((codec, fmt, img, n, want))
+    failures = []
+
+    def worker(job):
+        codec, fmt, img, n, want = job
+        for _ in range(20):
+            got = icb.compress_host(codec, fmt, img.ravel(), n, n)
+            if not np.array_equal(got, want):
+                failures.append((codec, fmt))
+                return
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures
