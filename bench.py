@@ -109,7 +109,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "sampled_over": "timed region + 0.5 s of the same launches back to back (100 ms nvidia-smi period)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -295,6 +296,16 @@ def run_gpu_arm(args):
     barrier()
     launches = icb.launch_count() - launches_before
     total_ms = t_begin.elapsed_time(t_end)
+    # The timed region lasts milliseconds, shorter than one nvidia-smi sample: keep the identical launches going for
+    # ~0.5 s (untimed) so that the clock / throttle record is taken under this kernel's load, not at idle.
+    t_hold = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_hold < 0.5:
+        for _ in range(64):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     kernel_ms = sorted(a.elapsed_time(b) for a, b in ev)
     if world > 1:
         t = torch.tensor([total_ms], device="cuda")
@@ -353,7 +364,6 @@ def run_gpu_arm(args):
     L.icb_host_free(h_out_ptr)
 
     if rank == 0:
-        clocks = sampler.stop()
         peak, peak_src = measured_peak_gbs()
         algo_bytes = in_bytes + out_bytes  # read every source byte once, write every block once
         k_med = kernel_ms[len(kernel_ms) // 2]
