@@ -9,6 +9,7 @@
 
 #include "image_compression/public/compressed_image.h"
 #include "image_compression/public/dxtc_compressor.h"
+#include "image_compression/public/dxtc_to_etc_transcoder.h"
 #include "image_compression/public/etc_compressor.h"
 #include "image_compression/public/pvrtc_compressor.h"
 
@@ -102,6 +103,69 @@ long icref_decompress(int codec, int strategy, int format, unsigned h, unsigned 
   if (out.size() > dst_cap) return -1;
   std::memcpy(dst, out.data(), out.size());
   return static_cast<long>(out.size());
+}
+
+namespace {
+// Wraps a block stream in a CompressedImage with the metadata Compress() would have produced for an h x w image.
+struct Wrapped {
+  std::vector<unsigned char> storage;
+  CompressedImage image;
+  Wrapped(Compressor *c, int format, unsigned h, unsigned w, const unsigned char *blocks, size_t nbytes)
+      : storage(nbytes), image(nbytes, storage.data()) {
+    std::vector<unsigned char> dummy(static_cast<size_t>(h) * w * 4, 0);
+    ok = c->Compress(static_cast<CompressedImage::Format>(format), h, w, 0, dummy.data(), &image);
+    if (ok) std::memcpy(storage.data(), blocks, nbytes);
+  }
+  bool ok;
+};
+long emit(const CompressedImage &img, unsigned char *dst, size_t dst_cap, unsigned *meta) {
+  if (img.GetDataSize() > dst_cap) return -1;
+  std::memcpy(dst, img.GetData(), img.GetDataSize());
+  if (meta) {
+    const CompressedImage::Metadata &m = img.GetMetadata();
+    meta[0] = m.format; meta[1] = m.uncompressed_height; meta[2] = m.uncompressed_width;
+    meta[3] = m.compressed_height; meta[4] = m.compressed_width; meta[5] = m.padding_bytes_per_row;
+    meta[6] = static_cast<unsigned>(m.compressor_name.size());
+  }
+  return static_cast<long>(img.GetDataSize());
+}
+Compressor *pick(int codec, int strategy, DxtcCompressor *d, EtcCompressor *e) {
+  e->SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  return codec == 2 ? static_cast<Compressor *>(e) : static_cast<Compressor *>(d);
+}
+}  // namespace
+
+// op: 0 Downsample, 1 Pad(a, b = padded height, width), 2 CopySubimage(a,b,c,d = row, col, height, width)
+long icref_block_op(int op, int codec, int strategy, int format, unsigned h, unsigned w, unsigned a, unsigned b,
+                    unsigned c, unsigned d, const unsigned char *blocks, size_t nbytes, unsigned char *dst,
+                    size_t dst_cap, unsigned *meta) {
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  Compressor *comp = pick(codec, strategy, &dxt, &etc);
+  Wrapped in(comp, format, h, w, blocks, nbytes);
+  if (!in.ok) return 0;
+  CompressedImage out;
+  bool ok = false;
+  if (op == 0) ok = comp->Downsample(in.image, &out);
+  if (op == 1) ok = comp->Pad(in.image, a, b, &out);
+  if (op == 2) ok = comp->CopySubimage(in.image, a, b, c, d, &out);
+  if (!ok) return 0;
+  return emit(out, dst, dst_cap, meta);
+}
+
+long icref_solid(int codec, int format, unsigned h, unsigned w, const unsigned char *color, unsigned char *dst,
+                 size_t dst_cap, unsigned *meta) {
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  Compressor *comp = pick(codec, 2, &dxt, &etc);
+  CompressedImage out;
+  if (!comp->CreateSolidImage(static_cast<CompressedImage::Format>(format), h, w, color, &out)) return 0;
+  return emit(out, dst, dst_cap, meta);
+}
+
+void icref_transcode(unsigned char *blocks, size_t nbytes) {
+  CompressedImage image(nbytes, blocks);
+  image_codec_compression::TranscodeDxt1ToEtc1(&image);
 }
 
 size_t icref_size(int codec, int format, unsigned h, unsigned w) {

@@ -891,6 +891,215 @@ void orc_decode4x4(int codec, int swap_rb, uint32_t h, uint32_t w, uint32_t bloc
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Compressed-domain operations                                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+static void decode_any(int codec, const uint8_t *blk, uint8_t px[16][4]) {
+  if (codec == 2)
+    decode_etc1_block(blk, px);
+  else
+    decode_dxt_block(blk, codec == 1, 0, px); /* Downsample / transcode decode without channel swap */
+}
+
+static void encode_any(int codec, int strategy, const window_t *win, uint8_t *out) {
+  if (codec == 0) {
+    dxt1_encode(win, 0, 0, out);
+  } else if (codec == 1) {
+    dxt5_alpha_encode(win, out);
+    dxt1_encode(win, 0, 1, out + 8);
+  } else {
+    etc1_encode(win, strategy, out);
+  }
+}
+
+/* StoreDownsampledPixels4x4 (pixel4x4.h:152-162): the four 2x2 averages of px into the 2x2 corner (ty,tx) of win. */
+static void store_downsampled(uint8_t px[16][4], int ty, int tx, int has_alpha, window_t *win) {
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 2; ++c) {
+      int i00 = 4 * (2 * r) + 2 * c, i01 = i00 + 1, i10 = i00 + 4, i11 = i00 + 5;
+      int o = 4 * (ty + r) + tx + c;
+      win->r[o] = (px[i00][0] + px[i01][0] + px[i10][0] + px[i11][0]) / 4;
+      win->g[o] = (px[i00][1] + px[i01][1] + px[i10][1] + px[i11][1]) / 4;
+      win->b[o] = (px[i00][2] + px[i01][2] + px[i10][2] + px[i11][2]) / 4;
+      win->a[o] = has_alpha ? (px[i00][3] + px[i01][3] + px[i10][3] + px[i11][3]) / 4 : 0;
+    }
+}
+
+size_t orc_downsample(int codec, int strategy, uint32_t uh, uint32_t uw, const uint8_t *in, uint8_t *out) {
+  uint32_t rows = orc_num_blocks(uh), cols = orc_num_blocks(uw), bb = codec == 1 ? 16u : 8u;
+  int alpha = codec == 1;
+  if ((rows > 1 && rows % 2) || (cols > 1 && cols % 2)) return 0;
+  uint8_t px[16][4];
+  window_t win;
+  win.one_pixel = 0;
+  uint8_t *o = out;
+  if (rows > 1 && cols > 1) {
+    for (uint32_t r = 0; r < rows / 2; ++r)
+      for (uint32_t c = 0; c < cols / 2; ++c, o += bb) {
+        for (int qr = 0; qr < 2; ++qr)
+          for (int qc = 0; qc < 2; ++qc) {
+            decode_any(codec, in + ((size_t)(2 * r + qr) * cols + 2 * c + qc) * bb, px);
+            store_downsampled(px, 2 * qr, 2 * qc, alpha, &win);
+          }
+        encode_any(codec, strategy, &win, o);
+      }
+  } else if (rows > 1) {
+    for (uint32_t r = 0; r < rows / 2; ++r, o += bb) {
+      for (int qr = 0; qr < 2; ++qr) {
+        decode_any(codec, in + (size_t)(2 * r + qr) * bb, px);
+        store_downsampled(px, 2 * qr, 0, alpha, &win);
+        store_downsampled(px, 2 * qr, 2, alpha, &win);
+      }
+      encode_any(codec, strategy, &win, o);
+    }
+  } else if (cols > 1) {
+    for (uint32_t c = 0; c < cols / 2; ++c, o += bb) {
+      for (int qc = 0; qc < 2; ++qc) {
+        decode_any(codec, in + (size_t)(2 * c + qc) * bb, px);
+        store_downsampled(px, 0, 2 * qc, alpha, &win);
+        store_downsampled(px, 2, 2 * qc, alpha, &win);
+      }
+      encode_any(codec, strategy, &win, o);
+    }
+  } else {
+    if (uh == 3 || uw == 3) return 0;
+    decode_any(codec, in, px);
+    if (uw == 1) {
+      for (int r = 0; r < 4; ++r)
+        for (int c = 1; c < 4; ++c) memcpy(px[4 * r + c], px[4 * r], 4);
+    } else if (uw == 2) {
+      for (int r = 0; r < 4; ++r) {
+        memcpy(px[4 * r + 2], px[4 * r], 4);
+        memcpy(px[4 * r + 3], px[4 * r + 1], 4);
+      }
+    }
+    if (uh == 1) {
+      for (int c = 0; c < 4; ++c)
+        for (int r = 1; r < 4; ++r) memcpy(px[4 * r + c], px[c], 4);
+    } else if (uh == 2) {
+      for (int c = 0; c < 4; ++c) {
+        memcpy(px[8 + c], px[c], 4);
+        memcpy(px[12 + c], px[4 + c], 4);
+      }
+    }
+    for (int qr = 0; qr < 2; ++qr)
+      for (int qc = 0; qc < 2; ++qc) store_downsampled(px, 2 * qr, 2 * qc, alpha, &win);
+    encode_any(codec, strategy, &win, o);
+    o += bb;
+  }
+  return (size_t)(o - out);
+}
+
+void orc_solid_block(int codec, const uint8_t color[4], uint8_t *out) {
+  if (codec == 2) { /* CreateSolidBlock: differential mode, zero delta, codeword 0, indices 0 */
+    uint32_t hi = 2u;
+    set_bits(&hi, 27, 5, color[0] >> 3);
+    set_bits(&hi, 19, 5, color[1] >> 3);
+    set_bits(&hi, 11, 5, color[2] >> 3);
+    put_be32(out, hi);
+    put_be32(out + 4, 0);
+    return;
+  }
+  uint8_t *c = codec == 1 ? out + 8 : out;
+  int q = to565(color[0], color[1], color[2]);
+  c[0] = c[2] = (uint8_t)(q & 0xff);
+  c[1] = c[3] = (uint8_t)(q >> 8);
+  memset(c + 4, 0, 4);
+  if (codec == 1) {
+    out[0] = out[1] = color[3];
+    memset(out + 2, 0, 6);
+  }
+}
+
+/* kind: 0 = replicate the block's last column, 1 = its last row, 2 = its bottom-right pixel */
+static void pad_block(int codec, int strategy, int kind, const uint8_t *in, uint8_t *out) {
+  if (codec == 2) {
+    uint8_t px[16][4];
+    decode_etc1_block(in, px);
+    if (kind == 2) {
+      orc_solid_block(2, px[15], out);
+      return;
+    }
+    window_t win;
+    win.one_pixel = 0;
+    for (int y = 0; y < 4; ++y)
+      for (int x = 0; x < 4; ++x) {
+        const uint8_t *s = kind == 0 ? px[4 * y + 3] : px[12 + x];
+        win.r[4 * y + x] = s[0];
+        win.g[4 * y + x] = s[1];
+        win.b[4 * y + x] = s[2];
+        win.a[4 * y + x] = 0;
+      }
+    etc1_encode(&win, strategy, out);
+    return;
+  }
+  const uint8_t *cin = codec == 1 ? in + 8 : in;
+  uint8_t *cout = codec == 1 ? out + 8 : out;
+  memcpy(cout, cin, 4);
+  for (int r = 0; r < 4; ++r) {
+    uint8_t row = kind == 0 ? cin[4 + r] : cin[7];
+    cout[4 + r] = kind == 1 ? row : (uint8_t)(((row >> 6) & 3) * 0x55);
+  }
+  if (codec == 1) {
+    uint64_t bits = 0, outbits = 0;
+    for (int k = 0; k < 6; ++k) bits |= (uint64_t)in[2 + k] << (8 * k);
+    for (int i = 0; i < 16; ++i) {
+      int src = kind == 0 ? 4 * (i >> 2) + 3 : kind == 1 ? 12 + (i & 3) : 15;
+      outbits |= ((bits >> (3 * src)) & 7u) << (3 * i);
+    }
+    out[0] = in[0];
+    out[1] = in[1];
+    for (int k = 0; k < 6; ++k) out[2 + k] = (uint8_t)(outbits >> (8 * k));
+  }
+}
+
+size_t orc_pad(int codec, int strategy, uint32_t ch, uint32_t cw, uint32_t ph, uint32_t pw, const uint8_t *in,
+               uint8_t *out) {
+  uint32_t rows = orc_num_blocks(ch), cols = orc_num_blocks(cw), bb = codec == 1 ? 16u : 8u;
+  if (ch >= ph && cw >= pw) {
+    memcpy(out, in, (size_t)rows * cols * bb);
+    return (size_t)rows * cols * bb;
+  }
+  uint32_t prows = orc_num_blocks(ph), pcols = orc_num_blocks(pw);
+  for (uint32_t r = 0; r < rows; ++r) {
+    memcpy(out + (size_t)r * pcols * bb, in + (size_t)r * cols * bb, (size_t)cols * bb);
+    if (cols < pcols) {
+      uint8_t padb[16];
+      pad_block(codec, strategy, 0, in + ((size_t)r * cols + cols - 1) * bb, padb);
+      for (uint32_t c = cols; c < pcols; ++c) memcpy(out + ((size_t)r * pcols + c) * bb, padb, bb);
+    }
+  }
+  if (rows < prows) {
+    const uint8_t *last = in + (size_t)(rows - 1) * cols * bb;
+    uint8_t *first_pad_row = out + (size_t)rows * pcols * bb;
+    for (uint32_t c = 0; c < cols; ++c) pad_block(codec, strategy, 1, last + (size_t)c * bb, first_pad_row + (size_t)c * bb);
+    if (cols < pcols) {
+      uint8_t corner[16];
+      pad_block(codec, strategy, 2, last + (size_t)(cols - 1) * bb, corner);
+      for (uint32_t c = cols; c < pcols; ++c) memcpy(first_pad_row + (size_t)c * bb, corner, bb);
+    }
+    for (uint32_t r = rows + 1; r < prows; ++r) memcpy(out + (size_t)r * pcols * bb, first_pad_row, (size_t)pcols * bb);
+  }
+  return (size_t)prows * pcols * bb;
+}
+
+void orc_transcode_dxt1_to_etc1(uint8_t *blocks, size_t nblocks) {
+  uint8_t px[16][4];
+  window_t win;
+  win.one_pixel = 0;
+  for (size_t k = 0; k < nblocks; ++k) {
+    decode_dxt_block(blocks + 8 * k, 0, 0, px);
+    for (int i = 0; i < 16; ++i) {
+      win.r[i] = px[i][0];
+      win.g[i] = px[i][1];
+      win.b[i] = px[i][2];
+      win.a[i] = 0;
+    }
+    etc1_encode(&win, ORC_ETC_HEURISTIC, blocks + 8 * k);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Synthetic input + hash                                                     */
 /* ------------------------------------------------------------------------------------------------ */
 

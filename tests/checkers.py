@@ -44,6 +44,14 @@ def oracle():
         lib.orc_pvrtc2_compress.argtypes = [C.c_uint32, C.c_uint32, _u8p, _u8p]
         lib.orc_decode4x4.restype = None
         lib.orc_decode4x4.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_downsample.restype = C.c_size_t
+        lib.orc_downsample.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_pad.restype = C.c_size_t
+        lib.orc_pad.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p]
+        lib.orc_solid_block.restype = None
+        lib.orc_solid_block.argtypes = [C.c_int, _u8p, _u8p]
+        lib.orc_transcode_dxt1_to_etc1.restype = None
+        lib.orc_transcode_dxt1_to_etc1.argtypes = [_u8p, C.c_size_t]
         lib.orc_fill_synthetic.restype = None
         lib.orc_fill_synthetic.argtypes = [_u8p, C.c_size_t, C.c_uint64, C.c_uint64]
         lib.orc_fnv1a64.restype = C.c_uint64
@@ -73,6 +81,12 @@ def ref():
         lib.icref_etc_external.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t]
         lib.icref_decompress.restype = C.c_long
         lib.icref_decompress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, _u8p, C.c_size_t, _u8p, C.c_size_t]
+        lib.icref_block_op.restype = C.c_long
+        lib.icref_block_op.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_uint] * 6 + [_u8p, C.c_size_t, _u8p, C.c_size_t, u32p]
+        lib.icref_solid.restype = C.c_long
+        lib.icref_solid.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, _u8p, _u8p, C.c_size_t, u32p]
+        lib.icref_transcode.restype = None
+        lib.icref_transcode.argtypes = [_u8p, C.c_size_t]
         lib.icref_size.restype = C.c_size_t
         lib.icref_size.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint]
         _ref = lib
@@ -138,6 +152,39 @@ def ref_decompress(codec, fmt, blocks, h, w):
     return out[:n].copy() if n > 0 else None
 
 
+def block_bytes(codec):
+    return 16 if codec == 1 else 8
+
+
+def oracle_downsample(codec, blocks, uh, uw, strategy=ETC_SMALLER_ERROR):
+    """Compressed-domain 2:1 downsample of the blocks of a uh x uw image; None where the reference refuses."""
+    out = np.zeros(max(1, nblocks((uh + 1) // 2)) * max(1, nblocks((uw + 1) // 2)) * block_bytes(codec), np.uint8)
+    blocks = np.ascontiguousarray(blocks)
+    n = oracle().orc_downsample(codec, strategy, uh, uw, _ptr(blocks), _ptr(out))
+    return out[:n].copy() if n else None
+
+
+def oracle_pad(codec, blocks, ch, cw, ph, pw, strategy=ETC_SMALLER_ERROR):
+    rows, cols = max(nblocks(ch), nblocks(ph)), max(nblocks(cw), nblocks(pw))
+    out = np.zeros(rows * cols * block_bytes(codec), np.uint8)
+    blocks = np.ascontiguousarray(blocks)
+    n = oracle().orc_pad(codec, strategy, ch, cw, ph, pw, _ptr(blocks), _ptr(out))
+    return out[:n].copy()
+
+
+def oracle_solid_block(codec, color):
+    out = np.zeros(block_bytes(codec), np.uint8)
+    color = np.ascontiguousarray(np.asarray(list(color) + [0] * (4 - len(color)), np.uint8))
+    oracle().orc_solid_block(codec, _ptr(color), _ptr(out))
+    return out
+
+
+def oracle_transcode(blocks):
+    out = np.ascontiguousarray(blocks).copy()
+    oracle().orc_transcode_dxt1_to_etc1(_ptr(out), out.size // 8)
+    return out
+
+
 def synthetic(nbytes, seed, offset=0):
     out = np.zeros(nbytes, np.uint8)
     oracle().orc_fill_synthetic(_ptr(out), nbytes, seed, offset)
@@ -185,3 +232,34 @@ def ref_etc(strategy, img, h, w, padded=None, padding=0, fmt=RGB, want_meta=Fals
 def ref_pvrtc(img, h, w, padding=0, fmt=RGBA, want_meta=False):
     out, meta = _run_ref(ref().icref_pvrtc, (fmt, h, w, padding, _ptr(img)), h * w // 4 + 16)
     return (out, meta) if want_meta else out
+
+
+def _ref_block_op(op, codec, fmt, blocks, h, w, a=0, b=0, c=0, d=0, strategy=ETC_SMALLER_ERROR, cap=None):
+    blocks = np.ascontiguousarray(blocks)
+    cap = cap if cap is not None else blocks.size * 4 + 64
+    return _run_ref(ref().icref_block_op, (op, codec, strategy, fmt, h, w, a, b, c, d, _ptr(blocks), blocks.size), cap)
+
+
+def ref_downsample(codec, fmt, blocks, h, w, strategy=ETC_SMALLER_ERROR):
+    """The reference's Downsample() on the block stream Compress() made for an h x w image -> (bytes, meta)."""
+    return _ref_block_op(0, codec, fmt, blocks, h, w, strategy=strategy)
+
+
+def ref_pad(codec, fmt, blocks, h, w, ph, pw, strategy=ETC_SMALLER_ERROR):
+    cap = max(nblocks(h), nblocks(ph)) * max(nblocks(w), nblocks(pw)) * 16 + 64
+    return _ref_block_op(1, codec, fmt, blocks, h, w, ph, pw, strategy=strategy, cap=cap)
+
+
+def ref_copy_subimage(codec, fmt, blocks, h, w, row, col, sh, sw):
+    return _ref_block_op(2, codec, fmt, blocks, h, w, row, col, sh, sw)
+
+
+def ref_solid(codec, fmt, h, w, color):
+    color = np.ascontiguousarray(np.asarray(list(color) + [0] * (4 - len(color)), np.uint8))
+    return _run_ref(ref().icref_solid, (codec, fmt, h, w, _ptr(color)), nblocks(h) * nblocks(w) * 16 + 64)
+
+
+def ref_transcode(blocks):
+    out = np.ascontiguousarray(blocks).copy()
+    ref().icref_transcode(_ptr(out), out.size)
+    return out

@@ -171,3 +171,83 @@ def test_decode_golden(golden):
         px = ck.oracle_decode(codec, np.ascontiguousarray(blocks), meta["h"], meta["w"], swap_rb=swap)
         got[str(i)] = zlib.crc32(px.tobytes())
     assert got == want
+
+
+def _compress_any(codec, fmt, img, h, w, strategy=ck.ETC_SMALLER_ERROR):
+    return ck.oracle_etc1(strategy, img.ravel(), h, w) if codec == 2 else ck.oracle_dxt(fmt, img.ravel(), h, w)
+
+
+CODEC_FORMATS = ((0, ck.RGB), (0, ck.BGR), (1, ck.RGBA), (1, ck.BGRA), (2, ck.RGB))
+
+
+@pytest.mark.skipif(not ck.have_ref(), reason="compiled reference (oracle/_ref) only exists in the build container")
+class TestBlockOpsAgainstCompiledReference:
+    """Compressed-domain operations: oracle restatement vs the reference."""
+
+    def test_downsample(self):
+        sizes = ((8, 8), (16, 24), (32, 8), (8, 40), (13, 29), (5, 7), (4, 16), (24, 4), (3, 16), (16, 2), (4, 4),
+                 (2, 2), (1, 1), (1, 4), (4, 2), (2, 1), (3, 4), (4, 3), (12, 8), (8, 20), (64, 64))
+        for codec, fmt in CODEC_FORMATS:
+            for kind in ("random", "smooth_noise", "constant", "two_colour", "alpha_extremes", "dark"):
+                for (h, w) in sizes:
+                    img = imagegen.make(kind, h, w, ck.ncomp(fmt), seed=7)
+                    for st in ((2, 3) if codec == 2 else (2,)):
+                        blocks = _compress_any(codec, fmt, img, h, w, st)
+                        r, meta = ck.ref_downsample(codec, fmt, blocks, h, w, strategy=st)
+                        o = ck.oracle_downsample(codec, blocks, h, w, strategy=st)
+                        if r is None:
+                            assert o is None, (codec, fmt, kind, h, w)
+                            continue
+                        assert o is not None and np.array_equal(r, o), (codec, fmt, kind, h, w, st)
+                        assert (meta["uncompressed_height"], meta["uncompressed_width"]) == ((h + 1) // 2, (w + 1) // 2)
+
+    def test_downsample_random_blocks(self):
+        """Arbitrary bit patterns (3-colour DXT1 blocks, ETC differential overflow) go through decode -> encode."""
+        rng = np.random.default_rng(11)
+        for codec, fmt in CODEC_FORMATS:
+            for (h, w) in ((16, 16), (8, 32), (4, 4), (4, 8)):
+                blocks = rng.integers(0, 256, ck.nblocks(h) * ck.nblocks(w) * ck.block_bytes(codec), dtype=np.uint8)
+                r, _ = ck.ref_downsample(codec, fmt, blocks, h, w)
+                assert np.array_equal(r, ck.oracle_downsample(codec, blocks, h, w)), (codec, fmt, h, w)
+
+    def test_pad(self):
+        rng = np.random.default_rng(12)
+        for codec, fmt in CODEC_FORMATS:
+            for (h, w) in ((8, 8), (5, 7), (16, 4), (4, 4), (12, 20)):
+                for (ph, pw) in ((h + 9, w + 6), (h, w + 8), (h + 4, w), (h, w), (4, 4), (h + 1, w + 1), (32, 32)):
+                    if ph < 4 * ck.nblocks(h) and pw > 4 * ck.nblocks(w) or pw < 4 * ck.nblocks(w) and ph > 4 * ck.nblocks(h):
+                        continue  # the reference overruns its output buffer here (helper.h:419-440)
+                    for content in ("image", "random"):
+                        if content == "image":
+                            blocks = _compress_any(codec, fmt, imagegen.make("smooth_noise", h, w, ck.ncomp(fmt), 1), h, w)
+                        else:
+                            blocks = rng.integers(0, 256, ck.nblocks(h) * ck.nblocks(w) * ck.block_bytes(codec), dtype=np.uint8)
+                        for st in ((2, 3) if codec == 2 else (2,)):
+                            r, meta = ck.ref_pad(codec, fmt, blocks, h, w, ph, pw, strategy=st)
+                            o = ck.oracle_pad(codec, blocks, 4 * ck.nblocks(h), 4 * ck.nblocks(w), ph, pw, strategy=st)
+                            assert r is not None and np.array_equal(r, o), (codec, fmt, h, w, ph, pw, content, st)
+
+    def test_solid_and_transcode(self):
+        rng = np.random.default_rng(13)
+        for codec, fmt in CODEC_FORMATS:
+            for _ in range(40):
+                color = rng.integers(0, 256, 4, dtype=np.uint8)
+                r, meta = ck.ref_solid(codec, fmt, 9, 6, color)
+                blk = ck.oracle_solid_block(codec, color)
+                assert np.array_equal(r, np.tile(blk, 3 * 2)), (codec, fmt, color)
+        assert ck.oracle_solid_block(2, (100, 150, 200)).tobytes().hex() == "6090c80200000000"  # SURVEY.md 8c
+        for kind in ("random", "smooth_noise", "constant", "two_colour", "dark"):
+            img = imagegen.make(kind, 32, 24, 3, seed=2)
+            blocks = ck.oracle_dxt(ck.RGB, img.ravel(), 32, 24)
+            assert np.array_equal(ck.ref_transcode(blocks), ck.oracle_transcode(blocks)), kind
+        blocks = rng.integers(0, 256, 8 * 500, dtype=np.uint8)
+        assert np.array_equal(ck.ref_transcode(blocks), ck.oracle_transcode(blocks))
+
+    def test_copy_subimage_reference_rules(self):
+        img = imagegen.make("random", 16, 24, 3, 0)
+        blocks = ck.oracle_dxt(ck.RGB, img.ravel(), 16, 24)
+        r, meta = ck.ref_copy_subimage(0, ck.RGB, blocks, 16, 24, 4, 8, 8, 12)
+        want = blocks.reshape(4, 6, 8)[1:3, 2:5].ravel()
+        assert np.array_equal(r, want) and meta["uncompressed_height"] == 8 and meta["uncompressed_width"] == 12
+        assert ck.ref_copy_subimage(0, ck.RGB, blocks, 16, 24, 2, 8, 8, 12)[0] is None   # not a multiple of 4
+        assert ck.ref_copy_subimage(0, ck.RGB, blocks, 16, 24, 12, 8, 8, 12)[0] is None  # leaves the image
