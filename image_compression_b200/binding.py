@@ -39,6 +39,12 @@ PROTOTYPES = {
     "icb_compress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "icb_decode4x4": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "icb_decompress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "icb_downsample4x4": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "icb_pad4x4": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "icb_copy_subimage4x4": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "icb_fill_solid4x4": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "icb_transcode_dxt1_to_etc1": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "icb_blockop_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "icb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "icb_host_free": (None, [C.c_void_p]),
     "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -186,4 +192,73 @@ def compress_host(codec, fmt, src, h, w, padded=None, padding=0, strategy=ETC_SM
     if out is None:
         out = np.empty(size, np.uint8)
     _check(lib().icb_compress_host(codec, fmt, h, w, ph, pw, padding, strategy, src.ctypes.data, out.ctypes.data, out.size))
+    return out
+
+
+# ---- compressed-domain operations ---------------------------------------------
+
+OP_DOWNSAMPLE, OP_PAD, OP_COPY_SUBIMAGE, OP_SOLID, OP_TRANSCODE = 0, 1, 2, 3, 4
+
+
+def _nb(n):
+    return (n + 3) // 4
+
+
+def block_bytes(codec):
+    return 16 if codec == CODEC_DXT5 else 8
+
+
+def downsample_device(codec, blocks, h, w, strategy=ETC_SMALLER_ERROR, out=None, stream=None):
+    """Blocks of an h x w image -> blocks of the ceil(h/2) x ceil(w/2) image (decode, 2x2 average, re-encode)."""
+    import torch
+    if out is None:
+        out = torch.empty(_nb((h + 1) // 2) * _nb((w + 1) // 2) * block_bytes(codec), dtype=torch.uint8, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        _check(lib().icb_downsample4x4(codec, strategy, blocks.data_ptr(), h, w, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def pad_device(codec, blocks, ch, cw, ph, pw, strategy=ETC_SMALLER_ERROR, out=None, stream=None):
+    import torch
+    if out is None:
+        rows, cols = (_nb(ch), _nb(cw)) if (ch >= ph and cw >= pw) else (_nb(ph), _nb(pw))
+        out = torch.empty(rows * cols * block_bytes(codec), dtype=torch.uint8, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        _check(lib().icb_pad4x4(codec, strategy, blocks.data_ptr(), ch, cw, ph, pw, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def copy_subimage_device(codec, blocks, ch, cw, row, col, h, w, out=None, stream=None):
+    import torch
+    if out is None:
+        out = torch.empty(_nb(h) * _nb(w) * block_bytes(codec), dtype=torch.uint8, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        _check(lib().icb_copy_subimage4x4(codec, blocks.data_ptr(), ch, cw, row, col, h, w, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def fill_solid_device(codec, colour, h, w, device="cuda", out=None, stream=None):
+    import torch
+    if out is None:
+        out = torch.empty(_nb(h) * _nb(w) * block_bytes(codec), dtype=torch.uint8, device=device)
+    colour = bytes(list(colour) + [0] * (4 - len(colour)))
+    with torch.cuda.device(out.device):
+        _check(lib().icb_fill_solid4x4(codec, colour, h, w, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def transcode_dxt1_to_etc1_device(blocks, stream=None):
+    """In place."""
+    import torch
+    with torch.cuda.device(blocks.device):
+        _check(lib().icb_transcode_dxt1_to_etc1(blocks.data_ptr(), blocks.numel() // 8, _stream_ptr(stream)))
+    return blocks
+
+
+def blockop_host(op, codec, args, src, out_size, strategy=ETC_SMALLER_ERROR):
+    """Host-buffer form: numpy in, numpy out, through icb_blockop_host."""
+    out = np.empty(out_size, np.uint8)
+    arr = (C.c_uint32 * max(1, len(args)))(*args)
+    src_ptr, src_size = (src.ctypes.data, src.size) if src is not None else (None, 0)
+    _check(lib().icb_blockop_host(op, codec, strategy, arr, src_ptr, src_size, out.ctypes.data, out.size))
     return out

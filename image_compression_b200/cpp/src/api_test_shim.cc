@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "image_compression/public/dxtc_compressor.h"
+#include "image_compression/public/dxtc_to_etc_transcoder.h"
 #include "image_compression/public/etc_compressor.h"
 #include "image_compression/public/pvrtc_compressor.h"
 
@@ -68,6 +69,47 @@ __attribute__((visibility("default"))) long icapi_roundtrip(int codec, int strat
   if (out.size() > dst_cap) return -1;
   std::memcpy(dst, out.data(), out.size());
   return static_cast<long>(out.size());
+}
+// Compressed-domain operations through the classes, driven exactly like oracle/ref_shim.cc's icref_block_op:
+// the input CompressedImage is made by compressing a dummy h x w image into external storage (which sets the
+// metadata) and overwriting the storage with `blocks`.
+// op: 0 Downsample, 1 Pad(a, b), 2 CopySubimage(a, b, c, d), 3 CreateSolidImage(colour = blocks[0..3]), 4 Transcode
+__attribute__((visibility("default"))) long icapi_block_op(int op, int codec, int strategy, int format, unsigned h,
+                                                           unsigned w, unsigned a, unsigned b, unsigned c, unsigned d,
+                                                           const unsigned char *blocks, size_t nbytes,
+                                                           unsigned char *dst, size_t dst_cap, unsigned *meta) {
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  etc.SetCompressionStrategy(static_cast<EtcCompressor::CompressionStrategy>(strategy));
+  Compressor *comp = codec == 2 ? static_cast<Compressor *>(&etc) : static_cast<Compressor *>(&dxt);
+  const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);
+  CompressedImage out;
+  bool ok = false;
+  if (op == 3) {
+    ok = comp->CreateSolidImage(f, h, w, blocks, &out);
+  } else {
+    std::vector<unsigned char> storage(nbytes), dummy(static_cast<size_t>(h) * w * 4, 0);
+    CompressedImage in(nbytes, storage.data());
+    if (!comp->Compress(f, h, w, 0, dummy.data(), &in)) return 0;
+    std::memcpy(storage.data(), blocks, nbytes);
+    if (op == 0) ok = comp->Downsample(in, &out);
+    if (op == 1) ok = comp->Pad(in, a, b, &out);
+    if (op == 2) ok = comp->CopySubimage(in, a, b, c, d, &out);
+    if (op == 4) {
+      ok = TranscodeDxt1ToEtc1(&in);
+      if (ok) out.Duplicate(in);
+    }
+  }
+  if (!ok) return 0;
+  if (out.GetDataSize() > dst_cap) return -1;
+  std::memcpy(dst, out.GetData(), out.GetDataSize());
+  if (meta) {
+    const CompressedImage::Metadata &m = out.GetMetadata();
+    meta[0] = m.format; meta[1] = m.uncompressed_height; meta[2] = m.uncompressed_width;
+    meta[3] = m.compressed_height; meta[4] = m.compressed_width; meta[5] = m.padding_bytes_per_row;
+    meta[6] = static_cast<unsigned>(m.compressor_name.size());
+  }
+  return static_cast<long>(out.GetDataSize());
 }
 __attribute__((visibility("default"))) size_t icapi_size(int codec, int format, unsigned h, unsigned w) {
   const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);

@@ -8,6 +8,7 @@
 // ...and then one call through the C ABI (include/icb200.h, icb_compress_host) where the reference ran its
 // per-block CPU loop.  No CPU encoder exists in this library: if the CUDA call fails, Compress returns false.
 #include <algorithm>
+#include <cstring>
 #include <string>
 
 #include "icb200.h"
@@ -65,6 +66,71 @@ bool Decode4x4(int codec, const CompressedImage &image, std::vector<uint8> *out)
                              out->size()) == ICB_OK;
 }
 
+// ---- compressed-domain operations ---------------------------------------------
+// Each mirrors the reference's host logic (validity checks, sizes, metadata) and hands the block arithmetic to the
+// C ABI (icb_blockop_host).  CopySubimage is a pure row-wise memcpy of blocks -- no arithmetic -- and stays on the
+// host, as in the reference (a device-resident form, icb_copy_subimage4x4, exists for streams that live in HBM).
+
+// Compressor4x4Helper::Downsample (internal/compressor4x4_helper.h:264-391)
+bool Downsample4x4(int codec, size_t block_size, int strategy, const CompressedImage &image, CompressedImage *out) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  const uint32 rows = NumBlocks(m.uncompressed_height), cols = NumBlocks(m.uncompressed_width);
+  if ((rows > 1 && rows % 2 != 0) || (cols > 1 && cols % 2 != 0)) return false;
+  const uint32 dh = (m.uncompressed_height + 1) / 2, dw = (m.uncompressed_width + 1) / 2;
+  if (!PrepareOutput(m.compressor_name.c_str(), block_size, m.format, dh, dw, 0, out)) return false;
+  // the reference sets the output up first and only then refuses a 3-pixel single block (:335)
+  if (rows == 1 && cols == 1 && (m.uncompressed_height == 3 || m.uncompressed_width == 3)) return false;
+  const uint32 args[2] = {m.uncompressed_height, m.uncompressed_width};
+  return icb_blockop_host(ICB_OP_DOWNSAMPLE, codec, strategy, args, image.GetData(), image.GetDataSize(),
+                          out->GetMutableData(), out->GetDataSize()) == ICB_OK;
+}
+
+// Compressor4x4Helper::Pad (:393-477)
+bool Pad4x4(int codec, size_t block_size, int strategy, const CompressedImage &image, uint32 padded_height,
+            uint32 padded_width, CompressedImage *out) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  if (m.compressed_height >= padded_height && m.compressed_width >= padded_width) {
+    out->Duplicate(image);
+    return true;
+  }
+  // The reference overruns its output buffer when one dimension shrinks below the input's block count while the
+  // other grows; refuse before touching `out`.
+  if (NumBlocks(padded_height) < NumBlocks(m.compressed_height) || NumBlocks(padded_width) < NumBlocks(m.compressed_width))
+    return false;
+  if (!PrepareOutput(m.compressor_name.c_str(), block_size, m.format, padded_height, padded_width, 0, out)) return false;
+  const uint32 args[4] = {m.compressed_height, m.compressed_width, padded_height, padded_width};
+  return icb_blockop_host(ICB_OP_PAD, codec, strategy, args, image.GetData(), image.GetDataSize(), out->GetMutableData(),
+                          out->GetDataSize()) == ICB_OK;
+}
+
+// Compressor4x4Helper::CreateSolidImage (:522-545)
+bool Solid4x4(int codec, const char *name, size_t block_size, CompressedImage::Format format, uint32 height,
+              uint32 width, const uint8 *color, CompressedImage *out) {
+  if (!PrepareOutput(name, block_size, format, height, width, 0, out)) return false;
+  if (out->GetDataSize() == 0) return true;  // zero-sized image: nothing to fill (the reference loops zero times)
+  const uint32 packed = color[0] | (color[1] << 8) | (color[2] << 16) |
+                        (codec == ICB_CODEC_DXT5 ? static_cast<uint32>(color[3]) << 24 : 0u);
+  const uint32 args[3] = {height, width, packed};
+  return icb_blockop_host(ICB_OP_SOLID, codec, 0, args, NULL, 0, out->GetMutableData(), out->GetDataSize()) == ICB_OK;
+}
+
+// Compressor4x4Helper::CopySubimage (:547-592)
+bool CopySubimage4x4(size_t block_size, const CompressedImage &image, uint32 start_row, uint32 start_column,
+                     uint32 height, uint32 width, CompressedImage *out) {
+  const CompressedImage::Metadata &m = image.GetMetadata();
+  if (start_row % 4 != 0 || start_column % 4 != 0 || height % 4 != 0 || width % 4 != 0 ||
+      start_row > m.compressed_height || start_column > m.compressed_width ||
+      start_row + height > m.compressed_height || start_column + width > m.compressed_width)
+    return false;
+  if (!PrepareOutput(m.compressor_name.c_str(), block_size, m.format, height, width, 0, out)) return false;
+  const size_t src_cols = NumBlocks(m.compressed_width), dst_cols = NumBlocks(width);
+  const uint8 *src = image.GetData() + (static_cast<size_t>(start_row / 4) * src_cols + start_column / 4) * block_size;
+  uint8 *dst = out->GetMutableData();
+  for (uint32 r = 0; r < NumBlocks(height); ++r, src += src_cols * block_size, dst += dst_cols * block_size)
+    std::memcpy(dst, src, dst_cols * block_size);
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -112,14 +178,31 @@ bool DxtcCompressor::Decompress(const CompressedImage &image, std::vector<uint8>
   return Decode4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, image, decompressed_buffer);
 }
 
-// Outside the GPU paths built so far; see DESIGN.md ("next" rows of SURVEY.md section 8f).
-bool DxtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
-bool DxtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
-bool DxtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
-  return false;
+bool DxtcCompressor::Downsample(const CompressedImage &image, CompressedImage *downsampled_image) {
+  if (!IsValidCompressedImage(image) || !downsampled_image) return false;
+  const bool dxt1 = GetNumFormatComponents(image.GetMetadata().format) == 3;
+  return Downsample4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, dxt1 ? 8 : 16, 0, image, downsampled_image);
 }
-bool DxtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint32, uint32, CompressedImage *) {
-  return false;
+
+bool DxtcCompressor::Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width,
+                         CompressedImage *padded_image) {
+  if (!IsValidCompressedImage(image) || !padded_image) return false;
+  const bool dxt1 = GetNumFormatComponents(image.GetMetadata().format) == 3;
+  return Pad4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, dxt1 ? 8 : 16, 0, image, padded_height, padded_width, padded_image);
+}
+
+bool DxtcCompressor::CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,
+                                      CompressedImage *image) {
+  if (!image) return false;
+  const bool dxt1 = GetNumFormatComponents(format) == 3;
+  return Solid4x4(dxt1 ? ICB_CODEC_DXT1 : ICB_CODEC_DXT5, "dxtc", dxt1 ? 8 : 16, format, height, width, color, image);
+}
+
+bool DxtcCompressor::CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height,
+                                  uint32 width, CompressedImage *subimage) {
+  if (!IsValidCompressedImage(image) || !subimage) return false;
+  return CopySubimage4x4(GetNumFormatComponents(image.GetMetadata().format) == 3 ? 8 : 16, image, start_row,
+                         start_column, height, width, subimage);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -163,13 +246,28 @@ bool EtcCompressor::Decompress(const CompressedImage &image, std::vector<uint8> 
   if (!IsValidCompressedImage(image) || !decompressed_buffer) return false;
   return Decode4x4(ICB_CODEC_ETC1, image, decompressed_buffer);
 }
-bool EtcCompressor::Downsample(const CompressedImage &, CompressedImage *) { return false; }
-bool EtcCompressor::Pad(const CompressedImage &, uint32, uint32, CompressedImage *) { return false; }
-bool EtcCompressor::CreateSolidImage(CompressedImage::Format, uint32, uint32, const uint8 *, CompressedImage *) {
-  return false;
+
+bool EtcCompressor::Downsample(const CompressedImage &image, CompressedImage *downsampled_image) {
+  if (!IsValidCompressedImage(image) || !downsampled_image) return false;
+  return Downsample4x4(ICB_CODEC_ETC1, 8, static_cast<int>(compression_strategy_), image, downsampled_image);
 }
-bool EtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint32, uint32, CompressedImage *) {
-  return false;
+
+bool EtcCompressor::Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width,
+                        CompressedImage *padded_image) {
+  if (!IsValidCompressedImage(image) || !padded_image) return false;
+  return Pad4x4(ICB_CODEC_ETC1, 8, static_cast<int>(compression_strategy_), image, padded_height, padded_width, padded_image);
+}
+
+bool EtcCompressor::CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,
+                                     CompressedImage *image) {
+  if (!image || format != CompressedImage::kRGB) return false;
+  return Solid4x4(ICB_CODEC_ETC1, "etc", 8, format, height, width, color, image);
+}
+
+bool EtcCompressor::CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height,
+                                 uint32 width, CompressedImage *subimage) {
+  if (!IsValidCompressedImage(image) || !subimage) return false;
+  return CopySubimage4x4(8, image, start_row, start_column, height, width, subimage);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -227,6 +325,15 @@ bool PvrtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint
   return false;
 }
 
-bool TranscodeDxt1ToEtc1(CompressedImage *) { return false; }
+// internal/dxtc_to_etc_transcoder.cc:29-40: every 8 bytes of the image are read as a DXT1 block and overwritten with
+// the ETC1 (heuristic strategy) encoding of its 16 decoded pixels.  Like the reference, the metadata is left alone.
+// The reference returns void; this build returns whether the GPU call succeeded (the data is untouched if not).
+bool TranscodeDxt1ToEtc1(CompressedImage *image) {
+  if (!image || !image->GetMutableData()) return false;
+  const size_t bytes = image->GetDataSize() / 8 * 8;
+  if (bytes == 0) return true;
+  return icb_blockop_host(ICB_OP_TRANSCODE, ICB_CODEC_DXT1, ICB_ETC_HEURISTIC, NULL, image->GetData(), bytes,
+                          image->GetMutableData(), bytes) == ICB_OK;
+}
 
 }  // namespace image_codec_compression

@@ -14,6 +14,7 @@
 
 #include "../../include/icb200.h"
 #include "block4x4_kernels.cuh"
+#include "blockops_kernels.cuh"
 #include "decode4x4_kernels.cuh"
 #include "pvrtc_kernels.cuh"
 
@@ -436,6 +437,203 @@ int icb_decompress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t 
   if (int s = icb_decode4x4(codec, pipe.d_dst, h, w, block_cols, swap_rb, pipe.d_src, w * ncomp, pipe.compute)) return s;
   ICB_CUDA(cudaMemcpyAsync(dst, pipe.d_src, need_out, cudaMemcpyDeviceToHost, pipe.compute));
   ICB_CUDA(cudaStreamSynchronize(pipe.compute));
+  return ICB_OK;
+}
+
+// ---- compressed-domain operations ----------------------------------------------------------------------------
+
+static inline uint32_t blocks_of(uint32_t pixels) { return (pixels + 3) / 4; }
+
+static int blockop_grid(uint64_t total, int threads, uint32_t *grid) {
+  DeviceInfo info;
+  if (int s = device_info(&info)) return s;
+  const uint64_t want = (total + threads - 1) / threads;
+  *grid = static_cast<uint32_t>(want < static_cast<uint64_t>(info.sm_count) * 32 ? want : info.sm_count * 32);
+  return ICB_OK;
+}
+
+static int check_4x4_codec(int codec, int strategy) {
+  if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_INVALID, "codec %d is not a 4x4 block codec", codec);
+  if (strategy < 0 || strategy > 3) return fail(ICB_ERR_INVALID, "unknown ETC strategy %d", strategy);
+  return ICB_OK;
+}
+
+int icb_downsample4x4(int codec, int strategy, const void *d_blocks, uint32_t h, uint32_t w, void *d_dst, void *stream) {
+  if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+  if (int s = check_4x4_codec(codec, strategy)) return s;
+  icb::Downsample4x4Params p;
+  p.in = static_cast<const uint8_t *>(d_blocks);
+  p.out = static_cast<uint8_t *>(d_dst);
+  p.in_rows = blocks_of(h);
+  p.in_cols = blocks_of(w);
+  // compressor4x4_helper.h:281-284: even block counts, except a single block
+  if ((p.in_rows > 1 && p.in_rows % 2) || (p.in_cols > 1 && p.in_cols % 2))
+    return fail(ICB_ERR_UNSUPPORTED, "Downsample needs an even number of blocks per dimension (or one), got %ux%u", p.in_rows, p.in_cols);
+  if (p.in_rows == 1 && p.in_cols == 1 && (h == 3 || w == 3))  // :335
+    return fail(ICB_ERR_UNSUPPORTED, "Downsample of a single block refuses a 3-pixel dimension");
+  p.out_rows = p.in_rows > 1 ? p.in_rows / 2 : 1;
+  p.out_cols = p.in_cols > 1 ? p.in_cols / 2 : 1;
+  p.height = h;
+  p.width = w;
+  p.etc_strategy = strategy;
+  uint32_t grid;
+  if (int s = blockop_grid(static_cast<uint64_t>(p.out_rows) * p.out_cols, icb::kBlockOpThreads, &grid)) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (codec == ICB_CODEC_DXT1) icb::downsample4x4_kernel<icb::kCodecDxt1><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  if (codec == ICB_CODEC_DXT5) icb::downsample4x4_kernel<icb::kCodecDxt5><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  if (codec == ICB_CODEC_ETC1) icb::downsample4x4_kernel<icb::kCodecEtc1><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+int icb_pad4x4(int codec, int strategy, const void *d_blocks, uint32_t ch, uint32_t cw, uint32_t ph, uint32_t pw,
+               void *d_dst, void *stream) {
+  if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (ch == 0 || cw == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+  if (int s = check_4x4_codec(codec, strategy)) return s;
+  const size_t block_bytes = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  icb::Pad4x4Params p;
+  p.in = static_cast<const uint8_t *>(d_blocks);
+  p.out = static_cast<uint8_t *>(d_dst);
+  p.in_rows = blocks_of(ch);
+  p.in_cols = blocks_of(cw);
+  if (ch >= ph && cw >= pw) {  // nothing to pad: the reference duplicates the image (compressor4x4_helper.h:404-408)
+    ICB_CUDA(cudaMemcpyAsync(d_dst, d_blocks, static_cast<size_t>(p.in_rows) * p.in_cols * block_bytes, cudaMemcpyDeviceToDevice, st));
+    return ICB_OK;
+  }
+  p.out_rows = blocks_of(ph);
+  p.out_cols = blocks_of(pw);
+  if (p.out_rows < p.in_rows || p.out_cols < p.in_cols)
+    return fail(ICB_ERR_UNSUPPORTED, "Pad to %ux%u would shrink one dimension of a %ux%u image while growing the other", ph, pw, ch, cw);
+  p.etc_strategy = strategy;
+  uint32_t grid;
+  if (int s = blockop_grid(static_cast<uint64_t>(p.out_rows) * p.out_cols, icb::kBlockOpThreads, &grid)) return s;
+  if (codec == ICB_CODEC_DXT1) icb::pad4x4_kernel<icb::kCodecDxt1><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  if (codec == ICB_CODEC_DXT5) icb::pad4x4_kernel<icb::kCodecDxt5><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  if (codec == ICB_CODEC_ETC1) icb::pad4x4_kernel<icb::kCodecEtc1><<<grid, icb::kBlockOpThreads, 0, st>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+int icb_copy_subimage4x4(int codec, const void *d_blocks, uint32_t ch, uint32_t cw, uint32_t row, uint32_t col, uint32_t h,
+                         uint32_t w, void *d_dst, void *stream) {
+  if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (int s = check_4x4_codec(codec, 0)) return s;
+  // compressor4x4_helper.h:556-565
+  if (row % 4 || col % 4 || h % 4 || w % 4 || row > ch || col > cw || static_cast<uint64_t>(row) + h > ch ||
+      static_cast<uint64_t>(col) + w > cw)
+    return fail(ICB_ERR_INVALID, "subimage %ux%u at (%u,%u) is not block-aligned inside %ux%u", h, w, row, col, ch, cw);
+  if (h == 0 || w == 0) return ICB_OK;
+  const size_t bb = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  const uint8_t *src = static_cast<const uint8_t *>(d_blocks) + (static_cast<size_t>(row / 4) * blocks_of(cw) + col / 4) * bb;
+  ICB_CUDA(cudaMemcpy2DAsync(d_dst, (w / 4) * bb, src, blocks_of(cw) * bb, (w / 4) * bb, h / 4, cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+  return ICB_OK;
+}
+
+int icb_fill_solid4x4(int codec, const uint8_t *colour, uint32_t h, uint32_t w, void *d_dst, void *stream) {
+  if (!d_dst || !colour) return fail(ICB_ERR_INVALID, "null pointer");
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+  if (int s = check_4x4_codec(codec, 0)) return s;
+  const uint32_t packed = colour[0] | (colour[1] << 8) | (colour[2] << 16) |
+                          (codec == ICB_CODEC_DXT5 ? static_cast<uint32_t>(colour[3]) << 24 : 0u);
+  const uint64_t n = static_cast<uint64_t>(blocks_of(h)) * blocks_of(w);
+  uint32_t grid;
+  if (int s = blockop_grid(n, 256, &grid)) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t *out = static_cast<uint8_t *>(d_dst);
+  if (codec == ICB_CODEC_DXT1) icb::fill_solid4x4_kernel<icb::kCodecDxt1><<<grid, 256, 0, st>>>(out, n, packed);
+  if (codec == ICB_CODEC_DXT5) icb::fill_solid4x4_kernel<icb::kCodecDxt5><<<grid, 256, 0, st>>>(out, n, packed);
+  if (codec == ICB_CODEC_ETC1) icb::fill_solid4x4_kernel<icb::kCodecEtc1><<<grid, 256, 0, st>>>(out, n, packed);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+int icb_transcode_dxt1_to_etc1(void *d_blocks, size_t num_blocks, void *stream) {
+  if (num_blocks == 0) return ICB_OK;
+  if (!d_blocks) return fail(ICB_ERR_INVALID, "null device pointer");
+  uint32_t grid;
+  if (int s = blockop_grid(num_blocks, icb::kBlockOpThreads, &grid)) return s;
+  icb::transcode_dxt1_to_etc1_kernel<<<grid, icb::kBlockOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint8_t *>(d_blocks), num_blocks);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ICB_CUDA(cudaGetLastError());
+  return ICB_OK;
+}
+
+int icb_blockop_host(int op, int codec, int strategy, const uint32_t *args, const void *src, size_t src_size, void *dst,
+                     size_t dst_size) {
+  if (!dst || (op != ICB_OP_SOLID && !src)) return fail(ICB_ERR_INVALID, "null buffer");
+  if (op != ICB_OP_TRANSCODE && !args) return fail(ICB_ERR_INVALID, "null argument list");
+  if (op == ICB_OP_TRANSCODE) codec = ICB_CODEC_DXT1;
+  if (int s = check_4x4_codec(codec, strategy)) return s;
+  const size_t bb = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  size_t need_in = 0, need_out = 0;
+  switch (op) {
+    case ICB_OP_DOWNSAMPLE:
+      if (args[0] == 0 || args[1] == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+      need_in = static_cast<size_t>(blocks_of(args[0])) * blocks_of(args[1]) * bb;
+      need_out = static_cast<size_t>(blocks_of((args[0] + 1) / 2)) * blocks_of((args[1] + 1) / 2) * bb;
+      break;
+    case ICB_OP_PAD: {
+      if (args[0] == 0 || args[1] == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+      need_in = static_cast<size_t>(blocks_of(args[0])) * blocks_of(args[1]) * bb;
+      const bool copy = args[0] >= args[2] && args[1] >= args[3];
+      need_out = copy ? need_in : static_cast<size_t>(blocks_of(args[2])) * blocks_of(args[3]) * bb;
+      break;
+    }
+    case ICB_OP_COPY_SUBIMAGE:
+      need_in = static_cast<size_t>(blocks_of(args[0])) * blocks_of(args[1]) * bb;
+      need_out = static_cast<size_t>(blocks_of(args[4])) * blocks_of(args[5]) * bb;
+      break;
+    case ICB_OP_SOLID:
+      if (args[0] == 0 || args[1] == 0) return fail(ICB_ERR_INVALID, "zero dimension");
+      need_out = static_cast<size_t>(blocks_of(args[0])) * blocks_of(args[1]) * bb;
+      break;
+    case ICB_OP_TRANSCODE:
+      need_in = need_out = src_size / 8 * 8;
+      break;
+    default:
+      return fail(ICB_ERR_INVALID, "unknown block operation %d", op);
+  }
+  if (op != ICB_OP_SOLID && src_size < need_in) return fail(ICB_ERR_SIZE, "source is %zu bytes, need %zu", src_size, need_in);
+  if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
+  if (int s = t_pipe.prepare()) return s;
+  HostPipe &pipe = t_pipe;
+  if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_in > 16 ? need_in : 16)) return s;
+  if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_out > 16 ? need_out : 16)) return s;
+  cudaStream_t st = pipe.compute;
+  if (need_in) ICB_CUDA(cudaMemcpyAsync(pipe.d_src, src, need_in, cudaMemcpyHostToDevice, st));
+  int s = ICB_OK;
+  void *result = pipe.d_dst;
+  switch (op) {
+    case ICB_OP_DOWNSAMPLE: s = icb_downsample4x4(codec, strategy, pipe.d_src, args[0], args[1], pipe.d_dst, st); break;
+    case ICB_OP_PAD: s = icb_pad4x4(codec, strategy, pipe.d_src, args[0], args[1], args[2], args[3], pipe.d_dst, st); break;
+    case ICB_OP_COPY_SUBIMAGE:
+      s = icb_copy_subimage4x4(codec, pipe.d_src, args[0], args[1], args[2], args[3], args[4], args[5], pipe.d_dst, st);
+      break;
+    case ICB_OP_SOLID: {
+      const uint8_t colour[4] = {static_cast<uint8_t>(args[2]), static_cast<uint8_t>(args[2] >> 8),
+                                 static_cast<uint8_t>(args[2] >> 16), static_cast<uint8_t>(args[2] >> 24)};
+      s = icb_fill_solid4x4(codec, colour, args[0], args[1], pipe.d_dst, st);
+      break;
+    }
+    case ICB_OP_TRANSCODE:
+      s = icb_transcode_dxt1_to_etc1(pipe.d_src, need_in / 8, st);
+      result = pipe.d_src;
+      break;
+  }
+  if (s != ICB_OK) {
+    cudaStreamSynchronize(st);
+    return s;
+  }
+  if (need_out) ICB_CUDA(cudaMemcpyAsync(dst, result, need_out, cudaMemcpyDeviceToHost, st));
+  ICB_CUDA(cudaStreamSynchronize(st));
   return ICB_OK;
 }
 

@@ -129,6 +129,57 @@ ICB_API int icb_decode4x4(int codec, const void *d_blocks, uint32_t height, uint
 ICB_API int icb_decompress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t block_cols,
                                 const void *blocks, size_t blocks_size, void *dst, size_t dst_size);
 
+/*
+ * Compressed-domain operations on DXT1 / DXT5 / ETC1 block streams (codec = ICB_CODEC_DXT1 | DXT5 | ETC1), the
+ * callers either side of the compress path.  Device-resident and asynchronous like
+ * the encoders; a stream of blocks that lives in HBM gets its mip chain, padding and ETC1 twin without visiting
+ * the host.  etc_strategy is only read for ICB_CODEC_ETC1 (the re-encode step).
+ *
+ * icb_downsample4x4      Compressor4x4Helper::Downsample (internal/compressor4x4_helper.h:264-391, 594-636):
+ *                        d_blocks holds ceil(height/4) * ceil(width/4) blocks of a height x width image; d_dst
+ *                        receives the blocks of the ceil(height/2) x ceil(width/2) image.  ICB_ERR_UNSUPPORTED where
+ *                        the reference returns false (an odd block count > 1 in a dimension; a 3-pixel dimension of a
+ *                        single-block image).
+ * icb_pad4x4             Compressor4x4Helper::Pad (:393-477) with the codecs' pad blocks
+ *                        (internal/dxtc_compressor.cc:594-696, internal/etc_compressor.cc:645-698).  compressed_* is
+ *                        the size of the input grid in pixels (a multiple of 4), padded_* the size asked for; d_dst
+ *                        receives ceil(padded_height/4) * ceil(padded_width/4) blocks.  When both padded sizes are <=
+ *                        the compressed ones the blocks are copied unchanged (the reference's Duplicate).  The
+ *                        reference overruns its output when one padded dimension has FEWER blocks than the input and
+ *                        the other more; that case is refused with ICB_ERR_UNSUPPORTED.
+ * icb_copy_subimage4x4   Compressor4x4Helper::CopySubimage (:547-592): all four values multiples of 4 and inside the
+ *                        compressed_height x compressed_width grid, else ICB_ERR_INVALID.
+ * icb_fill_solid4x4      CreateSolidImage (internal/dxtc_compressor.cc:820-840, internal/etc_compressor.cc:595-617,
+ *                        772-785): colour = 3 (DXT1, ETC1) or 4 (DXT5) bytes in the order the caller would pass them
+ *                        to the reference; fills ceil(height/4) * ceil(width/4) identical blocks.
+ * icb_transcode_dxt1_to_etc1  TranscodeDxt1ToEtc1 (internal/dxtc_to_etc_transcoder.cc:29-40): in place, num_blocks
+ *                        8-byte blocks, ETC1 heuristic strategy.
+ */
+ICB_API int icb_downsample4x4(int codec, int etc_strategy, const void *d_blocks, uint32_t height, uint32_t width,
+                              void *d_dst, void *stream);
+ICB_API int icb_pad4x4(int codec, int etc_strategy, const void *d_blocks, uint32_t compressed_height,
+                       uint32_t compressed_width, uint32_t padded_height, uint32_t padded_width, void *d_dst,
+                       void *stream);
+ICB_API int icb_copy_subimage4x4(int codec, const void *d_blocks, uint32_t compressed_height, uint32_t compressed_width,
+                                 uint32_t start_row, uint32_t start_column, uint32_t height, uint32_t width, void *d_dst,
+                                 void *stream);
+ICB_API int icb_fill_solid4x4(int codec, const uint8_t *colour, uint32_t height, uint32_t width, void *d_dst,
+                              void *stream);
+ICB_API int icb_transcode_dxt1_to_etc1(void *d_blocks, size_t num_blocks, void *stream);
+
+/*
+ * Host-buffer forms of the operations above (what Compressor::Downsample / Pad / CreateSolidImage and
+ * TranscodeDxt1ToEtc1 hand their buffers to).  Blocking.  dst_size must equal the size of the result exactly.
+ */
+typedef enum icb_block_op { ICB_OP_DOWNSAMPLE = 0, ICB_OP_PAD = 1, ICB_OP_COPY_SUBIMAGE = 2, ICB_OP_SOLID = 3, ICB_OP_TRANSCODE = 4 } icb_block_op;
+/*
+ * args by op:  DOWNSAMPLE {height, width}            PAD {compressed_height, compressed_width, padded_height, padded_width}
+ *              COPY_SUBIMAGE {compressed_height, compressed_width, start_row, start_column, height, width}
+ *              SOLID {height, width, colour bytes packed little-endian}          TRANSCODE {} (src may equal dst)
+ */
+ICB_API int icb_blockop_host(int op, int codec, int etc_strategy, const uint32_t *args, const void *src, size_t src_size,
+                             void *dst, size_t dst_size);
+
 /* Page-locked host memory for icb_compress_host callers. */
 ICB_API void *icb_host_alloc(size_t bytes);
 ICB_API void icb_host_free(void *p);

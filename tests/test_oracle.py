@@ -251,3 +251,32 @@ class TestBlockOpsAgainstCompiledReference:
         assert np.array_equal(r, want) and meta["uncompressed_height"] == 8 and meta["uncompressed_width"] == 12
         assert ck.ref_copy_subimage(0, ck.RGB, blocks, 16, 24, 2, 8, 8, 12)[0] is None   # not a multiple of 4
         assert ck.ref_copy_subimage(0, ck.RGB, blocks, 16, 24, 12, 8, 8, 12)[0] is None  # leaves the image
+
+
+def test_oracle_block_ops_match_golden(golden_ops):
+    """The restated compressed-domain operations against reference outputs frozen by tools/gen_golden_ops.py."""
+    assert len(golden_ops) > 150
+    seen = set()
+    for meta, src, want in golden_ops:
+        op, codec = meta["op"], meta["codec"]
+        seen.add(op)
+        src = np.ascontiguousarray(src)
+        if op == "downsample":
+            got = ck.oracle_downsample(codec, src, meta["h"], meta["w"], strategy=meta["strategy"])
+            assert (got is None) == meta["refused"], meta
+        elif op == "pad":
+            got = ck.oracle_pad(codec, src, 4 * ck.nblocks(meta["h"]), 4 * ck.nblocks(meta["w"]), meta["ph"], meta["pw"],
+                                strategy=meta["strategy"])
+        elif op == "copy_subimage":
+            if meta["refused"]:
+                continue  # argument rules live in the host classes (tests/test_cpp_api.py)
+            bb, cols = ck.block_bytes(codec), ck.nblocks(meta["w"])
+            grid = src.reshape(ck.nblocks(meta["h"]), cols, bb)
+            got = grid[meta["row"] // 4:(meta["row"] + meta["sh"]) // 4, meta["col"] // 4:(meta["col"] + meta["sw"]) // 4].ravel()
+        elif op == "solid":
+            got = np.tile(ck.oracle_solid_block(codec, src), ck.nblocks(meta["h"]) * ck.nblocks(meta["w"]))
+        else:
+            got = ck.oracle_transcode(src)
+        if not meta["refused"]:
+            assert np.array_equal(got, want), meta
+    assert seen == {"downsample", "pad", "copy_subimage", "solid", "transcode"}
