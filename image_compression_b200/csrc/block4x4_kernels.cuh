@@ -6,12 +6,14 @@
 // (internal/pixel4x4.h:45-67, internal/pixel4x4.cc:24-59).
 //
 // Two drivers:
-//   encode4x4_tma_kernel      the fast path.  Persistent CTAs; one elected producer thread streams 2-D pixel
-//                             tiles HBM -> shared memory with TMA (cp.async.bulk.tensor) through a ring of
-//                             mbarrier-guarded stages; consumer warps read their block's four rows with 128-bit
-//                             (or 3x32-bit for RGB888) conflict-free shared loads, encode in registers and write
-//                             8/16 B per lane, coalesced.  Needs a 16-byte aligned base and pitch.
-//   encode4x4_generic_kernel  any pointer / pitch / size, and the pad region of CompressAndPad: byte loads with
+//   encode4x4_tma_kernel      the fast path, for every 64 x 4-block tile that lies entirely inside the image.
+//                             Persistent CTAs; one elected producer thread streams 2-D pixel tiles HBM -> shared
+//                             memory with TMA (cp.async.bulk.tensor) through a ring of mbarrier-guarded stages;
+//                             consumer warps read their block's four rows with 128-bit (or 3x32-bit for RGB888)
+//                             conflict-free shared loads, encode in registers and write 8/16 B per lane, coalesced.
+//                             Needs a 16-byte aligned base and pitch.
+//   encode4x4_generic_kernel  any pointer / pitch / size: the ragged right and bottom strips the tiles do not
+//                             cover, unaligned sources and the pad region of CompressAndPad.  Byte loads with
 //                             clamped coordinates straight from global memory.
 #pragma once
 #include <cuda.h>
@@ -53,15 +55,16 @@ struct CodecTraits<kCodecEtc1> {
 
 // Encodes 16 gathered pixels and stores the block.  px bytes are (c0,c1,c2,c3) in memory order; for 3-component
 // sources c3 is zero.
-template <int kCodec, typename Fetch>
+// kFullWarp: the caller guarantees that all 32 lanes of the warp are here (lets warp votes skip the active-mask query).
+template <int kCodec, bool kFullWarp = false, typename Fetch>
 __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch fetch, bool one_pixel, int swap_rb,
                                                  int etc_strategy, const uint4 *alpha_table, uint8_t *out) {
   if constexpr (kCodec == kCodecDxt1) {
-    const uint2 c = dxt1_encode_block(px, swap_rb != 0, false, fetch);
+    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, false, fetch);
     *reinterpret_cast<uint2 *>(out) = c;
   } else if constexpr (kCodec == kCodecDxt5) {
     const uint2 a = dxt5_encode_alpha(px, one_pixel, alpha_table);
-    const uint2 c = dxt1_encode_block(px, swap_rb != 0, true, fetch);
+    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch);
     *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
   } else {
     const uint2 e = etc1_encode_block(px, etc_strategy);
@@ -133,6 +136,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity), "r"(0x989680)
       : "memory");
 }
+// The producer's wait for a free ring slot.  It is nearly always early (the ring is full while the encoders work),
+// and ncu shows that the suspend-hinted wait above still comes back every few cycles: in the slower codecs the one
+// producer warp burnt ~14 % of all issued instructions polling.  Sleeping between polls costs nothing -- the ring
+// holds 2-3 tiles of slack, a refill that starts 0.2 us late is invisible.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 // 2-D tiled bulk tensor load, global -> shared, completion on an mbarrier; streaming (evict-first) L2 policy.
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, uint32_t bar, int32_t x, int32_t y,
                                             uint64_t policy) {
@@ -161,6 +184,29 @@ struct TileShape {
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
 };
 
+// Shared-memory loads by 32-bit shared-window address (no generic pointers: the tile base stays one register and the
+// stage / row offsets fold into the instruction's immediate).
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// The TMA kernel only ever sees blocks whose windows lie entirely inside the image (the launcher hands ragged edge
+// blocks and pad regions to the generic kernel), so it has no clamping and no bounds checks.  It covers block rows
+// [row0,row1) x columns [col0,col1), each extent at least one tile; tiles are numbered row-major, tiles_x per row,
+// and the last tile of a row / column is shifted back so that it ends exactly at col1 / row1 -- the blocks it
+// shares with its neighbour are simply encoded twice, to the same bytes.
 template <int kCodec, int kNcomp, int kTmaStages>
 __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
@@ -169,10 +215,13 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // layout: kTmaStages tiles, then kTmaStages "full" barriers, then kTmaStages "empty" barriers
   // (kTmaStages trades bytes in flight per CTA against resident CTAs per SM; the launcher picks)
-  const uint32_t tiles_s = smem_u32(smem_raw);
+  // (volatile: keeps the shared-window base in a register instead of re-deriving it from SR_CgaCtaId per tile)
+  uint32_t tiles_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
   const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, empty_s = full_s + kTmaStages * 8;
   constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
+  constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
   const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
   // DXT5 keeps its 8 KB crossing-point table behind the ring
   const uint4 *alpha_table = reinterpret_cast<const uint4 *>(smem_raw + kTmaStages * (Shape::kBytes + 16));
@@ -182,124 +231,136 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     for (uint32_t i = threadIdx.x; i < kDxt5AlphaTableBytes / 16; i += blockDim.x) dst[i] = src[i];
   }
 
-  if (threadIdx.x == 0) {
+  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
+  const uint32_t warp = threadIdx.x >> 5;
+  // ---- producer: one lane of the last warp streams this CTA's tiles through the ring.  It also sets the barriers
+  // up and fills the ring BEFORE the CTA-wide sync, so the first tiles are already in flight while the other warps
+  // are still starting (and, for DXT5, copying the crossing table).
+  const bool is_producer = threadIdx.x == Shape::kConsumerThreads;
+  uint32_t p_stage = 0, p_phase = 0, p_tile = blockIdx.x;
+  const uint64_t policy = is_producer ? l2_evict_first_policy() : 0ull;  // the source is read exactly once
+  auto produce_one = [&]() {
+    mbar_wait_relaxed(empty_s + 8 * p_stage, p_phase ^ 1u);  // passes at once on the first trip round the ring
+    mbar_arrive_expect_tx(full_s + 8 * p_stage, Shape::kBytes);
+    const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, p.col1 - Shape::kBlocksX);
+    const uint32_t br = min(p.row0 + ty * Shape::kBlocksY, p.row1 - Shape::kBlocksY);
+    tma_load_2d(tiles_s + p_stage * Shape::kBytes, &src_map, full_s + 8 * p_stage, static_cast<int32_t>(bc * kNcomp),
+                static_cast<int32_t>(br * 4u), policy);
+    if (++p_stage == kTmaStages) {
+      p_stage = 0;
+      p_phase ^= 1u;
+    }
+    p_tile += gridDim.x;
+    tx += step_x;  // next tile of this CTA: tile + gridDim.x, kept as (tx, ty) without dividing
+    ty += step_y;
+    if (tx >= tiles_x) {
+      tx -= tiles_x;
+      ++ty;
+    }
+  };
+  // Programmatic dependent launch: let the next kernel in the stream start its own launch and prologue while this
+  // one is still running, and do not touch global memory before the previous kernel has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (is_producer) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&src_map) : "memory");
     for (int s = 0; s < kTmaStages; ++s) {
       mbar_init(full_s + 8 * s, 1);
       mbar_init(empty_s + 8 * s, kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // Only this thread waits for the previous kernel: every other thread's first global access (a block store)
+    // comes after it has consumed a tile, i.e. after this thread has passed the wait and issued the load.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int s = 0; s < kTmaStages && p_tile < num_tiles; ++s) produce_one();
   }
   __syncthreads();
-
-  uint32_t stage = 0, phase = 0;
-  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
-  const uint32_t warp = threadIdx.x >> 5;
   if (warp == kConsumerWarps) {
-    // ---- producer warp: one lane streams this CTA's tiles through the ring
-    if ((threadIdx.x & 31) == 0) {
-      const uint64_t policy = l2_evict_first_policy();
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(empty_s + 8 * stage, phase ^ 1u);
-        mbar_arrive_expect_tx(full_s + 8 * stage, Shape::kBytes);
-        tma_load_2d(tiles_s + stage * Shape::kBytes, &src_map, full_s + 8 * stage,
-                    static_cast<int32_t>((p.col0 + tx * Shape::kBlocksX) * kNcomp),
-                    static_cast<int32_t>((p.row0 + ty * Shape::kBlocksY) * 4u), policy);
-        if (++stage == kTmaStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        tx += step_x;  // next tile of this CTA: tile + gridDim.x, kept as (tx, ty) without dividing
-        ty += step_y;
-        if (tx >= tiles_x) {
-          tx -= tiles_x;
-          ++ty;
-        }
-      }
-    }
+    if (is_producer)
+      while (p_tile < num_tiles) produce_one();
     return;
   }
 
   // ---- consumer warps: thread t owns block (t / kBlocksX, t % kBlocksX) of every tile
   const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
-  const uint32_t own_off = (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;  // byte offset of the window in a tile
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint32_t tile_br = p.row0 + ty * Shape::kBlocksY, tile_bc = p.col0 + tx * Shape::kBlocksX;
-    const uint8_t *tile_bytes = smem_raw + stage * Shape::kBytes;
-    // Whole tile inside the image and inside this launch's block range: no clamping, no bounds checks.
-    const bool tile_inside = (tile_br + Shape::kBlocksY) * 4u <= p.height && (tile_bc + Shape::kBlocksX) * 4u <= p.width &&
-                             tile_br + Shape::kBlocksY <= p.row1 && tile_bc + Shape::kBlocksX <= p.col1;
-    // Pixel i of this thread's window, re-read from the tile (the encoders look two pixels up by index).
-    auto fetch_inside = [&](uint32_t i) {
-      if constexpr (kNcomp == 4) {
-        return *reinterpret_cast<const uint32_t *>(tile_bytes + own_off + (i >> 2) * (Shape::kRowWords * 4) + (i & 3u) * 4u);
-      } else {
-        const uint8_t *q = tile_bytes + own_off + (i >> 2) * (Shape::kRowWords * 4) + (i & 3u) * 3u;
-        return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
-      }
-    };
-    // Same with clamp-to-edge replication for tiles that the image edge cuts through.  The clamped coordinate
-    // never leaves the tile because every encoded window starts inside the image.
-    auto fetch_edge = [&](uint32_t i) {
-      const uint32_t ymax = min(p.height - 1u - tile_br * 4u, static_cast<uint32_t>(Shape::kRows - 1));
-      const uint32_t xmax = min(p.width - 1u - tile_bc * 4u, static_cast<uint32_t>(Shape::kBlocksX * 4 - 1));
-      const uint32_t y = min(lby * 4u + (i >> 2), ymax), x = min(lbx * 4u + (i & 3u), xmax);
-      if constexpr (kNcomp == 4) {
-        return *reinterpret_cast<const uint32_t *>(tile_bytes + (y * Shape::kRowWords + x) * 4u);
-      } else {
-        const uint8_t *q = tile_bytes + y * (Shape::kRowWords * 4) + x * 3u;
-        return static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8) | (static_cast<uint32_t>(q[2]) << 16);
-      }
-    };
-    mbar_wait(full_s + 8 * stage, phase);
+  // shared-window address of this thread's window in stage 0
+  const uint32_t win0 = tiles_s + (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;
+  // This thread's block in a tile whose first block is (0,0); the launcher checks that a row of blocks fits 32 bits.
+  uint8_t *const out_origin = p.dst + (static_cast<size_t>(lby) * p.grid_cols + lbx) * kBlockBytes;
+  const uint32_t out_row_bytes = p.grid_cols * kBlockBytes;
+  const uint32_t last_bc = p.col1 - Shape::kBlocksX, last_br = p.row1 - Shape::kBlocksY;
+  const bool swap_rb = p.swap_rb != 0;
+  // The ring is walked with the stage as a compile-time constant (barrier and tile addresses become immediates)
+  // where the encoder is small; ETC1's exhaustive search is ~5000 instructions, three copies of which would not
+  // fit the instruction cache, so it keeps a run-time stage.
+  constexpr int kUnroll = kCodec == kCodecEtc1 ? 1 : kTmaStages;
+  uint32_t phase = 0, tile = blockIdx.x, rt_stage = 0;
+  while (true) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t stage = kUnroll == 1 ? rt_stage : static_cast<uint32_t>(u);
+      if (tile >= num_tiles) return;  // uniform over the CTA's consumers; nothing after the loop needs them
+      const uint32_t win = win0 + stage * Shape::kBytes;
+      // Pixel i (< 16) of this thread's window, re-read from the tile (the encoders look two pixels up by index).
+      auto fetch = [&](uint32_t i) {
+        if constexpr (kNcomp == 4) {
+          // (i >> 2) rows of 1024 bytes + (i & 3) pixels of 4 bytes, as one multiply and one mask
+          static_assert(kRowBytes == 1024, "offset trick assumes 1 KB tile rows");
+          return lds_u32(win + ((i * 0x104u) & 0xc0cu));
+        } else {
+          const uint32_t q = win + (i >> 2) * kRowBytes + (i & 3u) * 3u;
+          return lds_u8(q) | (lds_u8(q + 1) << 8) | (lds_u8(q + 2) << 16);
+        }
+      };
+      const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
+      uint8_t *out = out_origin + static_cast<size_t>(br) * out_row_bytes + bc * kBlockBytes;
+      mbar_wait(full_s + 8 * stage, phase);
 
-    uint8_t *out = p.dst + (static_cast<size_t>(tile_br + lby) * p.grid_cols + tile_bc + lbx) * kBlockBytes;
-    if (tile_inside) {
       if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
         // RGB888 -> DXT1 never needs the unpacked pixels: luminance keys come straight from the row words
         uint32_t rows[4][3];
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(tile_bytes + own_off + y * (Shape::kRowWords * 4));
-          rows[y][0] = w[0]; rows[y][1] = w[1]; rows[y][2] = w[2];
+          rows[y][0] = lds_u32(win + y * kRowBytes);
+          rows[y][1] = lds_u32(win + y * kRowBytes + 4);
+          rows[y][2] = lds_u32(win + y * kRowBytes + 8);
         }
-        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows(rows, p.swap_rb != 0, false, fetch_inside);
+        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch);
       } else {
         uint32_t px[16];
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-          const uint8_t *row = tile_bytes + own_off + y * (Shape::kRowWords * 4);
           if constexpr (kNcomp == 4) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(row);
+            const uint4 v = lds_v4(win + y * kRowBytes);
             px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
-          } else {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(row);  // 12 bytes = four packed RGB pixels
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          } else {  // 12 bytes = four packed RGB pixels
+            const uint32_t w0 = lds_u32(win + y * kRowBytes), w1 = lds_u32(win + y * kRowBytes + 4),
+                           w2 = lds_u32(win + y * kRowBytes + 8);
             px[4 * y + 0] = w0 & 0x00ffffffu;
             px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
             px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
             px[4 * y + 3] = w2 >> 8;
           }
         }
-        encode_and_store<kCodec>(px, fetch_inside, false, p.swap_rb, p.etc_strategy, alpha_table, out);
+        encode_and_store<kCodec, true>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
       }
-    } else if (tile_br + lby < p.row1 && tile_bc + lbx < p.col1) {
-      uint32_t px[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) px[i] = fetch_edge(i);
-      encode_and_store<kCodec>(px, fetch_edge, false, p.swap_rb, p.etc_strategy, alpha_table, out);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
+      tile += gridDim.x;
+      tx += step_x;
+      ty += step_y;
+      if (tx >= tiles_x) {
+        tx -= tiles_x;
+        ++ty;
+      }
+      if constexpr (kUnroll == 1) {
+        if (++rt_stage == kTmaStages) {
+          rt_stage = 0;
+          phase ^= 1u;
+        }
+      }
     }
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
-    if (++stage == kTmaStages) {
-      stage = 0;
-      phase ^= 1u;
-    }
-    tx += step_x;
-    ty += step_y;
-    if (tx >= tiles_x) {
-      tx -= tiles_x;
-      ++ty;
-    }
+    if constexpr (kUnroll != 1) phase ^= 1u;
   }
 }
 

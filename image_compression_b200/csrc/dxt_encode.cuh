@@ -134,7 +134,7 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 // kf[i] = 0x4B000000 + 16*lum(pixel i): read as a float it is 2^23 + 16*lum, which the index search consumes as is.
 constexpr uint32_t kDxtLumBias = 0x4b000000u;
 
-template <typename Fetch>
+template <bool kFullWarp, typename Fetch>
 __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch) {
   // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
   // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
@@ -155,8 +155,34 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
+  // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
+  // where the warp has not yet diverged on "is this block constant".
+  const bool constant = c0 == c1;
+  if (c0 < c1) {
+    uint32_t t = p0; p0 = p1; p1 = t;
+    t = c0; c0 = c1; c1 = t;
+    t = lum0; lum0 = lum1; lum1 = t;
+  }
+  // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
+  // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
+  const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
+  const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
+  const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
+  constexpr uint32_t kThird = 683u << 21;
+  const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
+                        16u * __umulhi(2u * b0 + b1, kThird);
+  const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
+                        16u * __umulhi(b0 + 2u * b1, kThird);
+  // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
+  // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
+  // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
+  // midpoints have to be computed.  (Constant blocks vote too; whatever they say only selects which path the
+  // other lanes take, and both paths are exact.)
+  const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
+  const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
+  const bool all_regular = __all_sync(kFullWarp ? 0xffffffffu : __activemask(), rising || falling);
   uint32_t bits;
-  if (c0 == c1) {
+  if (constant) {
     // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
     // memory-order colour.
     const uint64_t packed = dxt_const_colour(p0, always4);
@@ -164,29 +190,8 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
     bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
   } else {
-    if (c0 < c1) {
-      uint32_t t = p0; p0 = p1; p1 = t;
-      t = c0; c0 = c1; c1 = t;
-      t = lum0; lum0 = lum1; lum1 = t;
-    }
-    // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
-    // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
-    const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
-    const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
-    const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
-    constexpr uint32_t kThird = 683u << 21;
-    const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
-                          16u * __umulhi(2u * b0 + b1, kThird);
-    const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
-                          16u * __umulhi(b0 + 2u * b1, kThird);
     float acc0, cross[3], step[3];
-    // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
-    // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
-    // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
-    // midpoints have to be computed.
-    const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
-    const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
-    if (__all_sync(__activemask(), rising || falling)) {
+    if (all_regular) {
       // ascending sequence: rising 0,2,3,1  falling 1,3,2,0 ; a tie goes to the smaller index
       const uint32_t a0 = rising ? lum0 : lum1, a1 = rising ? lum2 : lum3, a2 = rising ? lum3 : lum2, a3 = rising ? lum1 : lum0;
       const uint32_t h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
@@ -232,18 +237,18 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
 }
 
 // Keys from 16 packed pixels (bytes c0,c1,c2,x in memory order; x ignored).
-template <typename Fetch>
+template <bool kFullWarp = false, typename Fetch>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
   uint32_t kf[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
-  return dxt1_encode_from_keys(kf, swap_rb, always4, fetch);
+  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch);
 }
 
 // Keys straight from four rows of packed RGB888 (three 32-bit words = four pixels per row): the byte weights of
 // IDP.4A do the unpacking, a pixel that straddles two words is two chained IDPs.  rows[y][0..2] = the 12 bytes.
-template <typename Fetch>
+template <bool kFullWarp = false, typename Fetch>
 __device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[4][3], bool swap_rb, bool always4, Fetch fetch) {
   const uint32_t w = dxt_lum_weights(swap_rb);  // bytes (w0, w1, w2, 0) for memory-order channels 0,1,2
   const uint32_t w0 = w & 0xffu, w1 = (w >> 8) & 0xffu, w2 = (w >> 16) & 0xffu;
@@ -259,7 +264,7 @@ __device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[
     kf[4 * y + 2] = __dp4a(rows[y][2], wc_hi, __dp4a(rows[y][1], wc_lo, kDxtLumBias));
     kf[4 * y + 3] = __dp4a(rows[y][2], wd, kDxtLumBias);
   }
-  return dxt1_encode_from_keys(kf, swap_rb, always4, fetch);
+  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch);
 }
 
 // ---------------------------------------------------------------------------------------------------------

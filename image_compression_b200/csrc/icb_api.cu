@@ -102,6 +102,8 @@ int launch_generic(const Encode4x4Params &p, int sm_count, cudaStream_t stream) 
 template <int kCodec, int kNcomp>
 int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   using Shape = icb::TileShape<kNcomp>;
+  if (static_cast<uint64_t>(p.grid_cols) * icb::CodecTraits<kCodec>::kBlockBytes > 0xffffffffull)
+    return fail(ICB_ERR_INVALID, "image too wide");
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled not available from this driver");
   // The image rows as 32-bit words: width words for RGBA8888, 3*width/4 for RGB888 (width % 4 == 0 here).
@@ -150,9 +152,21 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   const uint32_t num_tiles = static_cast<uint32_t>(num_tiles64);
   const uint32_t max_ctas = static_cast<uint32_t>(sm_count * cfg.ctas_per_sm);
   const uint32_t grid = num_tiles < max_ctas ? num_tiles : max_ctas;
-  cfg.kernel<<<grid, kThreads, cfg.smem, stream>>>(map, p, tiles_x, num_tiles);
+  // Launched with programmatic stream serialization: the kernel's launch latency and prologue overlap the tail of
+  // whatever kernel precedes it in the stream; it waits (griddepcontrol.wait) for that kernel to complete before it
+  // reads or writes global memory, so stream order is preserved for every caller.
+  cudaLaunchConfig_t launch = {};
+  launch.gridDim = dim3(grid);
+  launch.blockDim = dim3(kThreads);
+  launch.dynamicSmemBytes = cfg.smem;
+  launch.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  launch.attrs = attr;
+  launch.numAttrs = getenv("ICB_NO_PDL") ? 0 : 1;
+  ICB_CUDA(cudaLaunchKernelEx(&launch, cfg.kernel, map, p, tiles_x, num_tiles));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  ICB_CUDA(cudaGetLastError());
   return ICB_OK;
 }
 
@@ -161,7 +175,6 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
                     cudaStream_t stream) {
   DeviceInfo info;
   if (int s = device_info(&info)) return s;
-  const uint32_t rows_in = (p.height + 3) / 4, cols_in = (p.width + 3) / 4;  // blocks whose origin is inside
   const uint32_t grid_rows = (coded_h + 3) / 4, grid_cols = (coded_w + 3) / 4;
   if (r1 > grid_rows || r0 > r1) return fail(ICB_ERR_INVALID, "block row range [%u,%u) outside grid of %u rows", r0, r1, grid_rows);
   p.grid_cols = grid_cols;
@@ -174,20 +187,35 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
   if (mode == 1 && !aligned) return fail(ICB_ERR_INVALID, "TMA path forced but source base/pitch is not 16-byte aligned");
   const bool use_tma = aligned && mode != 0;
 
-  const uint32_t in_r1 = r1 < rows_in ? r1 : rows_in;
-  if (r0 < in_r1) {  // windows whose origin lies inside the image
-    p.row0 = r0; p.row1 = in_r1; p.col0 = 0; p.col1 = cols_in;
-    if (int s = use_tma ? launch_tma<kCodec, kNcomp>(p, info.sm_count, stream)
-                        : launch_generic<kCodec, kNcomp>(p, info.sm_count, stream))
-      return s;
-    if (grid_cols > cols_in) {  // CompressAndPad: columns to the right of the image
-      p.col0 = cols_in; p.col1 = grid_cols;
+  // Split of the launch's block rows [r0, r1) x all grid columns:
+  //   A  blocks whose 4x4 window lies inside the image, if they span at least one tile each way
+  //      ............................................. TMA kernel     rows [r0, a_r1) x cols [0, a_c1)
+  //   B  right of A, same rows ....................... generic kernel rows [r0, a_r1) x cols [a_c1, grid_cols)
+  //   C  everything below A .......................... generic kernel rows [a_r1, r1) x cols [0, grid_cols)
+  // (B and C are the ragged image edge, whose windows clamp, and CompressAndPad's pad region.)
+  using Shape = icb::TileShape<kNcomp>;
+  uint32_t a_r1 = r0, a_c1 = 0;
+  if (use_tma) {
+    const uint32_t full_rows = p.height / 4, full_cols = p.width / 4;  // blocks that need no clamping
+    const uint32_t top = r1 < full_rows ? r1 : full_rows;
+    // RGB888: a tile must start on a 16-byte boundary of its row (TMA faults otherwise), i.e. on a multiple of
+    // four blocks; the last, shifted tile starts at a_c1 - kBlocksX, so a_c1 is rounded down accordingly.
+    const uint32_t usable_cols = kNcomp == 3 ? full_cols & ~3u : full_cols;
+    if (top >= r0 + Shape::kBlocksY && usable_cols >= Shape::kBlocksX) {
+      a_r1 = top;
+      a_c1 = usable_cols;
+    }
+  }
+  if (a_r1 > r0) {
+    p.row0 = r0; p.row1 = a_r1; p.col0 = 0; p.col1 = a_c1;
+    if (int s = launch_tma<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
+    if (a_c1 < grid_cols) {
+      p.col0 = a_c1; p.col1 = grid_cols;
       if (int s = launch_generic<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
     }
   }
-  const uint32_t below_r0 = r0 > rows_in ? r0 : rows_in;
-  if (below_r0 < r1) {  // CompressAndPad: rows below the image
-    p.row0 = below_r0; p.row1 = r1; p.col0 = 0; p.col1 = grid_cols;
+  if (a_r1 < r1) {
+    p.row0 = a_r1; p.row1 = r1; p.col0 = 0; p.col1 = grid_cols;
     if (int s = launch_generic<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
   }
   return ICB_OK;
@@ -713,7 +741,8 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   if (chunks < 1) chunks = 1;
   if (chunks > HostPipe::kMaxChunks) chunks = HostPipe::kMaxChunks;
   if (chunks > grid_rows) chunks = grid_rows;
-  const uint32_t rows_per_chunk = (grid_rows + chunks - 1) / chunks;
+  // whole tile rows per chunk (4 block rows), so that only the last chunk can leave rows to the generic kernel
+  const uint32_t rows_per_chunk = ((grid_rows + chunks - 1) / chunks + 3) / 4 * 4;
   const uint8_t *hsrc = static_cast<const uint8_t *>(src);
   uint8_t *hdst = static_cast<uint8_t *>(dst);
   uint32_t chunk = 0;
