@@ -253,7 +253,10 @@ def run_gpu_arm(args):
     my_px_rows = (r1 - r0) * 4
     in_bytes = my_px_rows * pitch
     out_bytes = int(my_px_rows * n * wl["out_bpp"])
-    nbuf = 2  # rotate so that consecutive steps never re-read lines still in the 126 MB L2
+    # Rotate over enough buffer pairs that a buffer is reused only after >= 1.5 x the 126 MB L2 of other traffic has
+    # passed through: 2 for the 8192^2 workloads (302+ MB per step), 4-5 for the 4096^2 ones (59-71 MB per step).
+    l2_bytes = 126 << 20
+    nbuf = max(2, 1 + -(-3 * l2_bytes // (2 * (in_bytes + out_bytes))))
     srcs = [torch.empty(in_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     dsts = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     for i, s in enumerate(srcs):
@@ -394,7 +397,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "image": "%dx%d per GPU (%dx%d job, block-row stripes)" % (n, n, n, total_rows),
-                       "input": "splitmix64 byte stream, resident in HBM", "l2": "%d MB input per step > 126 MB L2, %d rotating buffers" % (in_bytes >> 20, nbuf),
+                       "input": "splitmix64 byte stream, resident in HBM", "l2": "%d rotating buffer pairs, %d MB of other traffic between two uses of a buffer (126 MB L2)" % (nbuf, ((nbuf - 1) * (in_bytes + out_bytes)) >> 20),
                        "parallelism": "stripe%d" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "peak_source": peak_src,

@@ -189,22 +189,39 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     c0 = static_cast<uint32_t>(packed) & 0xffffu;
     c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
     bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
+  } else if (all_regular) {
+    // Ascending index sequence along the luminance line: rising 0,2,3,1, falling 1,3,2,0; a tie goes to the smaller
+    // index.  Crossing points h1 < h2 < h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
+    // index bit is set exactly between the outer crossings and the low bit flips at the middle one:
+    //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 16]
+    //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(+-v -+ h2 ...)
+    // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
+    // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
+    const uint32_t a0 = rising ? lum0 : lum1, a1 = rising ? lum2 : lum3, a2 = rising ? lum3 : lum2, a3 = rising ? lum1 : lum0;
+    const uint32_t h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
+    const uint32_t h2 = ((a1 + a2 + (rising ? 32u : 16u)) >> 1) & ~15u;    // 2->3 stays on tie, 3->2 moves
+    const uint32_t h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
+    const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 16u) >> 1));
+    const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1 - 16u) >> 1) + 1u) - 8388608.0f;  // R + 1
+    const float sgn = rising ? 1.0f : -1.0f;
+    const float k2 = __uint_as_float(rising ? 0xcb000000u + h2 - 1u : kDxtLumBias + h2);
+    float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = __uint_as_float(kf[i]);
+      const float u = __saturatef(rp1 - fabsf(v - mid));
+      const float t = __saturatef(fmaf(v, sgn, k2));
+      const float z = fmaf(u, 2.0f, t);
+      const float scale = static_cast<float>(1u << (2 * (i & 7)));
+      if (i < 8)
+        acc_lo = fmaf(z, scale, acc_lo);
+      else
+        acc_hi = fmaf(z, scale, acc_hi);
+    }
+    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410);
   } else {
     float acc0, cross[3], step[3];
-    if (all_regular) {
-      // ascending sequence: rising 0,2,3,1  falling 1,3,2,0 ; a tie goes to the smaller index
-      const uint32_t a0 = rising ? lum0 : lum1, a1 = rising ? lum2 : lum3, a2 = rising ? lum3 : lum2, a3 = rising ? lum1 : lum0;
-      const uint32_t h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
-      const uint32_t h2 = ((a1 + a2 + (rising ? 32u : 16u)) >> 1) & ~15u;    // 2->3 stays on tie, 3->2 moves
-      const uint32_t h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
-      cross[0] = __uint_as_float(kDxtLumBias + h1 - 1u);
-      cross[1] = __uint_as_float(kDxtLumBias + h2 - 1u);
-      cross[2] = __uint_as_float(kDxtLumBias + h3 - 1u);
-      step[0] = 2.0f;
-      step[1] = rising ? 1.0f : 3.0f;  // 2->3 is +1, 3->2 is -1 = +3 (mod 4)
-      step[2] = 2.0f;                  // 3->1 and 2->0 are both -2 = +2 (mod 4)
-      acc0 = __uint_as_float(kDxtLumBias + (rising ? 0u : 1u));
-    } else {
+    {
       // General case (flat blocks, crossed or equal candidates): sort the candidates as keys 16*L_c + c.
       uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
       sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
