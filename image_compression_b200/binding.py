@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libicb200.so")
+    # ICB200_LIB: another build of the same library (kernel A/B experiments, tools/build_variants.sh)
+    return os.environ.get("ICB200_LIB") or os.path.join(_HERE, "lib", "libicb200.so")
 
 
 class IcbError(RuntimeError):

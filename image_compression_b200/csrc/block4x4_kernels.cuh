@@ -56,17 +56,33 @@ struct CodecTraits<kCodecEtc1> {
 // Encodes 16 gathered pixels and stores the block.  px bytes are (c0,c1,c2,c3) in memory order; for 3-component
 // sources c3 is zero.
 // kFullWarp: the caller guarantees that all 32 lanes of the warp are here (lets warp votes skip the active-mask query).
-template <int kCodec, bool kFullWarp = false, typename Fetch>
+// release(): called once, as soon as the encoder no longer needs `fetch` (see dxt_encode.cuh).
+template <int kCodec, bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch fetch, bool one_pixel, int swap_rb,
-                                                 int etc_strategy, const uint4 *alpha_table, uint8_t *out) {
+                                                 int etc_strategy, const uint4 *alpha_table, uint8_t *out,
+                                                 Release release = Release()) {
   if constexpr (kCodec == kCodecDxt1) {
-    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, false, fetch);
+#ifdef ICB_PROBE_ENCODER
+    // Measurement builds only (tools/build_variants.sh): no encoder, every pixel still loaded and 8 bytes stored, to
+    // find the streaming ceiling of the TMA driver itself.
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a ^= px[i];
+      b += px[i + 8];
+    }
+    release();
+    *reinterpret_cast<uint2 *>(out) = make_uint2(a, b);
+#else
+    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, false, fetch, release);
     *reinterpret_cast<uint2 *>(out) = c;
+#endif
   } else if constexpr (kCodec == kCodecDxt5) {
+    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch, release);  // colour first: releases early
     const uint2 a = dxt5_encode_alpha(px, one_pixel, alpha_table);
-    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch);
     *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
   } else {
+    release();  // every pixel is already in registers
     const uint2 e = etc1_encode_block(px, etc_strategy);
     *reinterpret_cast<uint2 *>(out) = e;
   }
@@ -136,10 +152,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity), "r"(0x989680)
       : "memory");
 }
-// The producer's wait for a free ring slot.  It is nearly always early (the ring is full while the encoders work),
-// and ncu shows that the suspend-hinted wait above still comes back every few cycles: in the slower codecs the one
-// producer warp burnt ~14 % of all issued instructions polling.  Sleeping between polls costs nothing -- the ring
-// holds 2-3 tiles of slack, a refill that starts 0.2 us late is invisible.
+// The producer's wait for a free ring slot.  It is nearly always early (the ring is full while the encoders work).
+// Neither the suspend-hinted wait above nor this nanosleep really parks the warp -- ncu's source view shows the loop
+// coming round every ~7 ns whatever the sleep argument (50 ns .. 1 us measured the same; 5 us was slower) -- but
+// this form measured fastest, and the polling warp mostly fills issue slots the encoders leave idle (see the ring
+// kernel below for the variant without any polling).
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t done;
   while (true) {
@@ -363,5 +380,159 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
     if constexpr (kUnroll != 1) phase ^= 1u;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA driver without a producer warp
+// ---------------------------------------------------------------------------------------------------------
+//
+// Same tiles, ring and consumer code as encode4x4_tma_kernel, but nobody polls for free ring slots: every warp
+// counts itself off a per-stage counter as soon as it has read its last pixel from a tile (one shared-memory atomic
+// per warp per tile, issued from inside the encoder through the `release` hook), and the warp that counts last
+// refills the slot on the spot -- expect_tx + one TMA load of tile (current + stages * grid).  Dropping the producer
+// warp frees its register share (256 instead of 288 threads per CTA: 64 registers per thread at four CTAs per SM),
+// which is what DXT5 needs: with the producer warp it is limited to three CTAs per SM (72 registers), here it runs
+// four, with a two-stage ring (early release makes two stages enough) and its crossing table read through L1.
+// Measured on B200 (8192^2): DXT5 103.5 -> 94.2 us.  DXT1 does not gain (51.6 us with the producer warp, 52.8-54.0
+// here: its polling warp fills otherwise idle issue slots and the 56-register code is a little tighter), so the
+// launcher keeps the producer-warp kernel for DXT1 and ETC1 (ICB_DRIVER=ring|producer overrides for experiments).
+
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
+template <int kCodec, int kNcomp, int kTmaStages>
+__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads, kCodec == kCodecEtc1 ? 3 : 4)
+    encode4x4_ring_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
+                          uint32_t num_tiles) {
+  using Shape = TileShape<kNcomp>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), then per stage a done-counter (8 bytes)
+  uint32_t tiles_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
+  const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, count_s = full_s + kTmaStages * 8;
+  constexpr uint32_t kWarps = Shape::kConsumerThreads / 32;
+  static_assert((kWarps & (kWarps - 1)) == 0, "the done-counter is tested modulo the warp count");
+  constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
+  constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
+  const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
+  // DXT5's 8 KB crossing table is read from global memory (one 16-byte load per block, L1-resident): a shared-memory
+  // copy would cost the fourth resident CTA per SM.
+  const uint4 *alpha_table = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
+  const uint32_t last_bc = p.col1 - Shape::kBlocksX, last_br = p.row1 - Shape::kBlocksY;
+
+  // Loads tile number `t` into ring slot `stage` (one thread).  Tiles are numbered row-major, tiles_x per row; the last
+  // tile of a row / column is shifted back so that it ends exactly at col1 / row1.
+  auto load_tile = [&](uint32_t t, uint32_t stage) {
+    const uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
+    const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
+    mbar_arrive_expect_tx(full_s + 8 * stage, Shape::kBytes);
+    tma_load_2d(tiles_s + stage * Shape::kBytes, &src_map, full_s + 8 * stage, static_cast<int32_t>(bc * kNcomp),
+                static_cast<int32_t>(br * 4u), l2_evict_first_policy());  // the source is read exactly once
+  };
+
+  // Programmatic dependent launch: the next kernel in the stream may start its prologue now; this one touches global
+  // memory only after the previous kernel has completed (thread 0 waits before the first load, and every other
+  // thread's first global access is a store that follows a tile thread 0 loaded).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&src_map) : "memory");
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(full_s + 8 * s, 1);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_s + 8 * s), "r"(0u) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (uint32_t s = 0, t = blockIdx.x; s < kTmaStages && t < num_tiles; ++s, t += gridDim.x) load_tile(t, s);
+  }
+  __syncthreads();
+
+  // thread t owns block (t / kBlocksX, t % kBlocksX) of every tile
+  const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
+  const uint32_t win0 = tiles_s + (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;
+  uint8_t *const out_origin = p.dst + (static_cast<size_t>(lby) * p.grid_cols + lbx) * kBlockBytes;
+  const uint32_t out_row_bytes = p.grid_cols * kBlockBytes;
+  const bool swap_rb = p.swap_rb != 0;
+  const uint32_t refill_stride = kTmaStages * gridDim.x;
+  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
+  constexpr int kUnroll = kCodec == kCodecEtc1 ? 1 : kTmaStages;  // see encode4x4_tma_kernel
+  uint32_t phase = 0, tile = blockIdx.x, rt_stage = 0;
+  while (true) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t stage = kUnroll == 1 ? rt_stage : static_cast<uint32_t>(u);
+      if (tile >= num_tiles) return;
+      const uint32_t win = win0 + stage * Shape::kBytes;
+      auto fetch = [&](uint32_t i) {
+        if constexpr (kNcomp == 4) {
+          static_assert(kRowBytes == 1024 || kNcomp != 4, "offset trick assumes 1 KB tile rows");
+          return lds_u32(win + ((i * 0x104u) & 0xc0cu));
+        } else {
+          const uint32_t q = win + (i >> 2) * kRowBytes + (i & 3u) * 3u;
+          return lds_u8(q) | (lds_u8(q + 1) << 8) | (lds_u8(q + 2) << 16);
+        }
+      };
+      const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
+      uint8_t *out = out_origin + static_cast<size_t>(br) * out_row_bytes + bc * kBlockBytes;
+      // Done with this slot (called by the encoder as soon as it has read its last pixel from the tile): count this
+      // warp off; the last warp to do so refills the slot.  The acq_rel atomic (MEMBAR.CTA + ATOMS) completes this
+      // warp's shared-memory reads before the count and makes every warp's reads happen-before the refill.
+      auto release = [&]() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+          const uint32_t old = atom_add_acq_rel_shared(count_s + 8 * stage, 1u);
+          if ((old & (kWarps - 1)) == kWarps - 1 && tile + refill_stride < num_tiles) load_tile(tile + refill_stride, stage);
+        }
+        __syncwarp();
+      };
+      mbar_wait(full_s + 8 * stage, phase);
+
+      if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
+        uint32_t rows[4][3];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          rows[y][0] = lds_u32(win + y * kRowBytes);
+          rows[y][1] = lds_u32(win + y * kRowBytes + 4);
+          rows[y][2] = lds_u32(win + y * kRowBytes + 8);
+        }
+        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch, release);
+      } else {
+        uint32_t px[16];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          if constexpr (kNcomp == 4) {
+            const uint4 v = lds_v4(win + y * kRowBytes);
+            px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
+          } else {
+            const uint32_t w0 = lds_u32(win + y * kRowBytes), w1 = lds_u32(win + y * kRowBytes + 4),
+                           w2 = lds_u32(win + y * kRowBytes + 8);
+            px[4 * y + 0] = w0 & 0x00ffffffu;
+            px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+            px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
+            px[4 * y + 3] = w2 >> 8;
+          }
+        }
+        encode_and_store<kCodec, true>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out, release);
+      }
+      tile += gridDim.x;
+      tx += step_x;
+      ty += step_y;
+      if (tx >= tiles_x) {
+        tx -= tiles_x;
+        ++ty;
+      }
+      if constexpr (kUnroll == 1) {
+        if (++rt_stage == kTmaStages) {
+          rt_stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    if constexpr (kUnroll != 1) phase ^= 1u;
+  }
+}
+
 
 }  // namespace icb

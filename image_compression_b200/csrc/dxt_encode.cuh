@@ -134,8 +134,15 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 // kf[i] = 0x4B000000 + 16*lum(pixel i): read as a float it is 2^23 + 16*lum, which the index search consumes as is.
 constexpr uint32_t kDxtLumBias = 0x4b000000u;
 
-template <bool kFullWarp, typename Fetch>
-__device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch) {
+// A caller that stages pixels in a buffer it wants back early passes `release`; it is called once, right after the
+// two base colours have been re-read through `fetch` (nothing reads the staged pixels after that).
+struct NoRelease {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+template <bool kFullWarp, typename Fetch, typename Release = NoRelease>
+__device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch,
+                                                       Release release = Release()) {
   // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
   // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
   // folds two more registers (four pixels) per instruction.
@@ -152,6 +159,7 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   mx = __vmaxu2(mx, pk[7] ^ 0x000f000fu);
   const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
   uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
+  release();
   uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
@@ -254,19 +262,21 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
 }
 
 // Keys from 16 packed pixels (bytes c0,c1,c2,x in memory order; x ignored).
-template <bool kFullWarp = false, typename Fetch>
-__device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch) {
+template <bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
+__device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch,
+                                                   Release release = Release()) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
   uint32_t kf[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
-  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch);
+  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
 }
 
 // Keys straight from four rows of packed RGB888 (three 32-bit words = four pixels per row): the byte weights of
 // IDP.4A do the unpacking, a pixel that straddles two words is two chained IDPs.  rows[y][0..2] = the 12 bytes.
-template <bool kFullWarp = false, typename Fetch>
-__device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[4][3], bool swap_rb, bool always4, Fetch fetch) {
+template <bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
+__device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[4][3], bool swap_rb, bool always4, Fetch fetch,
+                                                         Release release = Release()) {
   const uint32_t w = dxt_lum_weights(swap_rb);  // bytes (w0, w1, w2, 0) for memory-order channels 0,1,2
   const uint32_t w0 = w & 0xffu, w1 = (w >> 8) & 0xffu, w2 = (w >> 16) & 0xffu;
   const uint32_t wa = w;                                   // pixel 0: word 0 bytes 0,1,2
@@ -281,7 +291,7 @@ __device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[
     kf[4 * y + 2] = __dp4a(rows[y][2], wc_hi, __dp4a(rows[y][1], wc_lo, kDxtLumBias));
     kf[4 * y + 3] = __dp4a(rows[y][2], wd, kDxtLumBias);
   }
-  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch);
+  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
 }
 
 // ---------------------------------------------------------------------------------------------------------

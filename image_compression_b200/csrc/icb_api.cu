@@ -117,30 +117,45 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
 
-  // Ring depth: 3 or 4 stages.  Fewer stages leave shared memory for one more resident CTA per SM; pick the
-  // depth that gives the most resident warps (ties -> deeper ring).  ICB_TMA_STAGES=3|4 overrides for experiments.
-  constexpr int kThreads = Shape::kConsumerThreads + 32;
+  // Driver and ring depth.  DXT5 runs the producer-less ring kernel with two stages (four CTAs per SM, see
+  // block4x4_kernels.cuh); DXT1 and ETC1 run the producer-warp kernel with 3 or 4 stages, whichever gives the most
+  // resident CTAs (ties -> deeper ring).  ICB_DRIVER=ring|producer and ICB_TMA_STAGES=2|3|4 override for experiments.
   struct Config {
     void (*kernel)(const CUtensorMap, const Encode4x4Params, uint32_t, uint32_t);
     size_t smem;
     int ctas_per_sm;
+    int threads;
   };
   static thread_local Config chosen[64] = {};
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
   if (chosen[dev].kernel == nullptr) {
-    constexpr size_t kExtra = kCodec == icb::kCodecDxt5 ? icb::kDxt5AlphaTableBytes : 0;  // DXT5 crossing table
-    Config cand[2] = {{icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * (Shape::kBytes + 16) + kExtra, 0},
-                      {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * (Shape::kBytes + 16) + kExtra, 0}};
-    const char *force = getenv("ICB_TMA_STAGES");
-    int best = -1;
-    for (int c = 0; c < 2; ++c) {
-      ICB_CUDA(cudaFuncSetAttribute(cand[c].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cand[c].smem)));
-      ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cand[c].ctas_per_sm, cand[c].kernel, kThreads, cand[c].smem));
-      if (cand[c].ctas_per_sm < 1) cand[c].ctas_per_sm = 1;
-      if (force && atoi(force) == (c == 0 ? 4 : 3)) best = c;
+    const int kRingThreads = Shape::kConsumerThreads, kProducerThreads = Shape::kConsumerThreads + 32;
+    constexpr size_t kStage = Shape::kBytes + 16;  // tile + its barrier / counter words
+    constexpr size_t kTable = kCodec == icb::kCodecDxt5 ? icb::kDxt5AlphaTableBytes : 0;  // producer kernel: table in smem
+    const char *driver = getenv("ICB_DRIVER"), *force = getenv("ICB_TMA_STAGES");
+    const bool ring = driver ? strcmp(driver, "ring") == 0 : kCodec == icb::kCodecDxt5;
+    Config cand[3];
+    int n = 0;
+    if (ring) {
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 2>, 2 * kStage, 0, kRingThreads};
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 3>, 3 * kStage, 0, kRingThreads};
+    } else {
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * kStage + kTable, 0, kProducerThreads};
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * kStage + kTable, 0, kProducerThreads};
     }
-    if (best < 0) best = cand[1].ctas_per_sm > cand[0].ctas_per_sm ? 1 : 0;
+    int best = -1;
+    for (int c = 0; c < n; ++c) {
+      ICB_CUDA(cudaFuncSetAttribute(cand[c].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cand[c].smem)));
+      ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cand[c].ctas_per_sm, cand[c].kernel, cand[c].threads, cand[c].smem));
+      if (cand[c].ctas_per_sm < 1) cand[c].ctas_per_sm = 1;
+      if (force && static_cast<size_t>(atoi(force)) * kStage + (ring ? 0 : kTable) == cand[c].smem) best = c;
+    }
+    if (best < 0) {
+      best = 0;  // first candidate unless a later one fits more CTAs per SM
+      for (int c = 1; c < n; ++c)
+        if (cand[c].ctas_per_sm > cand[best].ctas_per_sm) best = c;
+    }
     chosen[dev] = cand[best];
   }
   const Config cfg = chosen[dev];
@@ -148,7 +163,7 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   const uint32_t tiles_y = (p.row1 - p.row0 + Shape::kBlocksY - 1) / Shape::kBlocksY;
   const uint64_t num_tiles64 = static_cast<uint64_t>(tiles_x) * tiles_y;
   if (num_tiles64 == 0) return ICB_OK;
-  if (num_tiles64 > 0xffffffffull) return fail(ICB_ERR_INVALID, "image too large");
+  if (num_tiles64 > 0x7fffffffull) return fail(ICB_ERR_INVALID, "image too large");
   const uint32_t num_tiles = static_cast<uint32_t>(num_tiles64);
   const uint32_t max_ctas = static_cast<uint32_t>(sm_count * cfg.ctas_per_sm);
   const uint32_t grid = num_tiles < max_ctas ? num_tiles : max_ctas;
@@ -157,7 +172,7 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   // reads or writes global memory, so stream order is preserved for every caller.
   cudaLaunchConfig_t launch = {};
   launch.gridDim = dim3(grid);
-  launch.blockDim = dim3(kThreads);
+  launch.blockDim = dim3(cfg.threads);
   launch.dynamicSmemBytes = cfg.smem;
   launch.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -1,5 +1,4 @@
 #!/bin/bash
-# A/B timing of driver configurations on the GPU box.  Usage: bash tools/gpu_ab.sh <tag>
 TAG=$1; OUT=gpurun_out/$TAG; mkdir -p $OUT
 run() {  # name, workload, env...
   name=$1; wl=$2; shift 2
@@ -13,15 +12,16 @@ except Exception as e:
     print("$name $wl failed", e); print(open("$OUT/${name}_$wl.err").read()[-1500:])
 PY
 }
+V=$PWD/image_compression_b200/lib/variants
 timeout 700 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_gpu.log
-for wl in dxt1_rgba8 dxt5_rgba8 dxt1_rgb8 etc1_rgb8; do
-  run ring_default $wl A=1
+ICB200_LIB=$V/libicb200_mbar.so timeout 700 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu_mbar.log 2>&1; echo "pytest(mbar) exit $?"; tail -2 $OUT/pytest_gpu_mbar.log
+for wl in dxt1_rgba8 dxt5_rgba8 dxt1_rgb8; do
+  run early_acqrel $wl A=1
+  run early_acqrel_2st $wl ICB_TMA_STAGES=2
+  run early_mbar $wl ICB200_LIB=$V/libicb200_mbar.so
+  run early_mbar_2st $wl ICB200_LIB=$V/libicb200_mbar.so ICB_TMA_STAGES=2
+  run late_mbar $wl ICB200_LIB=$V/libicb200_mbar_late.so
   run producer_warp $wl ICB_PRODUCER_WARP=1
-  run ring_4stages $wl ICB_TMA_STAGES=4
 done
-run ring_2stages dxt1_rgba8 ICB_TMA_STAGES=2
-run ring_2stages dxt1_rgb8 ICB_TMA_STAGES=2
-run probe_ring3 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so
-run probe_ring4 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_TMA_STAGES=4
-run probe_ring2 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_TMA_STAGES=2
-run probe_producer dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_PRODUCER_WARP=1
+run early_acqrel etc1_rgb8 A=1
+run early_mbar etc1_rgb8 ICB200_LIB=$V/libicb200_mbar.so
