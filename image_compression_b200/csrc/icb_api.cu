@@ -130,7 +130,6 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
   if (chosen[dev].kernel == nullptr) {
-    const int kRingThreads = Shape::kConsumerThreads, kProducerThreads = Shape::kConsumerThreads + 32;
     constexpr size_t kStage = Shape::kBytes + 16;  // tile + its barrier / counter words
     constexpr size_t kTable = kCodec == icb::kCodecDxt5 ? icb::kDxt5AlphaTableBytes : 0;  // producer kernel: table in smem
     const char *driver = getenv("ICB_DRIVER"), *force = getenv("ICB_TMA_STAGES");
@@ -138,11 +137,11 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
     Config cand[3];
     int n = 0;
     if (ring) {
-      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 2>, 2 * kStage, 0, kRingThreads};
-      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 3>, 3 * kStage, 0, kRingThreads};
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 2>, 2 * kStage, 0, Shape::kConsumerThreads};
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 3>, 3 * kStage, 0, Shape::kConsumerThreads};
     } else {
-      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * kStage + kTable, 0, kProducerThreads};
-      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * kStage + kTable, 0, kProducerThreads};
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
     }
     int best = -1;
     for (int c = 0; c < n; ++c) {
