@@ -46,6 +46,11 @@ PROTOTYPES = {
     "icb_fill_solid4x4": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "icb_transcode_dxt1_to_etc1": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "icb_blockop_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "icb_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "icb_device_free": (C.c_int, [C.c_void_p]),
+    "icb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "icb_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "icb_ipc_close": (C.c_int, [C.c_void_p]),
     "icb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "icb_host_free": (None, [C.c_void_p]),
     "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -141,10 +146,12 @@ from .sharding import stripe_rows  # noqa: E402,F401  (re-exported)
 def encode_stripe_device(codec, fmt, src_base_ptr, h, w, pitch, coded_h, coded_w, r0, r1, out, strategy=ETC_SMALLER_ERROR,
                          stream=None):
     """Encodes block rows [r0, r1).  src_base_ptr is the (possibly virtual) address of pixel (0,0) of the whole
-    image; only the rows the stripe reads must be resident.  `out` receives the stripe's blocks."""
+    image; only the rows the stripe reads must be resident.  `out` receives the stripe's blocks: a uint8 tensor, or
+    a raw device address (int) -- e.g. a peer-mapped one from sharding.PeerStream."""
     swap = 1 if fmt in (BGR, BGRA) else 0
+    out_ptr = out if isinstance(out, int) else out.data_ptr()
     _check(lib().icb_encode4x4_stripe(codec, ncomp_of(fmt), C.c_void_p(src_base_ptr), h, w, pitch, coded_h, coded_w, swap,
-                                      strategy, r0, r1, out.data_ptr(), _stream_ptr(stream)))
+                                      strategy, r0, r1, C.c_void_p(out_ptr), _stream_ptr(stream)))
     return out
 
 

@@ -705,6 +705,44 @@ void icb_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
+// ---- peer-mapped output (multi-GPU stripe path) -----------------------------------------------------------
+
+int icb_device_alloc(size_t bytes, void **d_ptr) {
+  if (!d_ptr || bytes == 0) return fail(ICB_ERR_INVALID, "null result pointer or zero size");
+  *d_ptr = nullptr;
+  ICB_CUDA(cudaMalloc(d_ptr, bytes));
+  return ICB_OK;
+}
+
+int icb_device_free(void *d_ptr) {
+  if (d_ptr) ICB_CUDA(cudaFree(d_ptr));
+  return ICB_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == ICB_IPC_HANDLE_BYTES, "icb200.h promises a 64-byte handle");
+
+int icb_ipc_export(const void *d_ptr, void *handle) {
+  if (!d_ptr || !handle) return fail(ICB_ERR_INVALID, "null pointer");
+  cudaIpcMemHandle_t h;
+  ICB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+  memcpy(handle, &h, sizeof(h));
+  return ICB_OK;
+}
+
+int icb_ipc_open(const void *handle, void **d_ptr) {
+  if (!handle || !d_ptr) return fail(ICB_ERR_INVALID, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  *d_ptr = nullptr;
+  ICB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ICB_OK;
+}
+
+int icb_ipc_close(void *d_ptr) {
+  if (d_ptr) ICB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return ICB_OK;
+}
+
 int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t padded_h, uint32_t padded_w,
                       uint32_t padding, int strategy, const void *src, void *dst, size_t dst_size) {
   // Same rejections, in the same order of concern, as the reference entry points

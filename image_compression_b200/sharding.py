@@ -1,7 +1,11 @@
 """Row-stripe sharding of the 4x4 codecs across ranks: every 4x4 block depends only on its own
 16 texels, output blocks are in raster order, so a stripe of whole block rows is one contiguous byte range of the
 output.  No data-path collective is needed to encode; `gather_blocks` reassembles the packed stream on one rank
-(NCCL on GPUs, gloo in the CPU tests)."""
+(NCCL on GPUs, gloo in the CPU tests).  `PeerStream` is the B200-native form of that gather: the owner's output
+buffer is mapped into every rank over NVLink (CUDA IPC) and each rank's encoder stores its blocks straight into it,
+so the gather is fused into the encode kernel's epilogue and costs no separate pass."""
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -31,3 +35,63 @@ def gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, group=None):
     if rank != dst:
         return None
     return torch.cat([p[:n] for p, n in zip(parts, sizes)])
+
+
+class PeerStream:
+    """The packed block stream of one sharded image, owned by rank `dst` and store-mapped into every other rank.
+
+        ps = PeerStream(total_bytes, dst=0)            # collective: allocates on dst, ships the IPC handle, maps it
+        icb.encode_stripe_device(..., out=ps.stripe_ptr(byte_offset_of_my_stripe))
+        ps.complete()                                   # collective: every rank's stores have landed on dst
+        whole = ps.tensor()                             # on dst: uint8 view of the whole stream (a copy); None elsewhere
+        ps.close()
+
+    One process per GPU (torch.distributed initialised, NCCL backend); the handle travels through a broadcast."""
+
+    def __init__(self, total_bytes, dst=0, group=None):
+        from . import binding
+        self._lib = binding.lib()
+        self._check = binding._check
+        self.total_bytes, self.dst, self.group = int(total_bytes), dst, group
+        self.rank = dist.get_rank(group)
+        self.owner = self.rank == dst
+        self._base = C.c_void_p()
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if self.owner:
+            self._check(self._lib.icb_device_alloc(self.total_bytes, C.byref(self._base)))
+            buf = (C.c_uint8 * 64)()
+            self._check(self._lib.icb_ipc_export(self._base, buf))
+            handle = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        wire = handle.to(dev)
+        dist.broadcast(wire, src=dst, group=group)
+        if not self.owner:
+            raw = C.create_string_buffer(wire.cpu().numpy().tobytes(), 64)
+            self._check(self._lib.icb_ipc_open(raw, C.byref(self._base)))
+
+    def stripe_ptr(self, byte_offset):
+        assert 0 <= byte_offset <= self.total_bytes
+        return self._base.value + int(byte_offset)
+
+    def complete(self):
+        """Every rank: wait for the local encoder, then meet the others; after this the owner holds the whole stream."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def tensor(self):
+        if not self.owner:
+            return None
+        class _Span:  # zero-copy view of the cudaMalloc'ed stream for torch
+            __cuda_array_interface__ = {"shape": (self.total_bytes,), "typestr": "|u1", "data": (self._base.value, False),
+                                        "version": 3}
+        return torch.as_tensor(_Span(), device="cuda").clone()
+
+    def close(self):
+        if self._base.value:
+            if self.owner:
+                dist.barrier(group=self.group)  # nobody still has it mapped
+                self._check(self._lib.icb_device_free(self._base))
+            else:
+                self._check(self._lib.icb_ipc_close(self._base))
+                dist.barrier(group=self.group)
+            self._base = C.c_void_p()

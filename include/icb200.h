@@ -180,6 +180,22 @@ typedef enum icb_block_op { ICB_OP_DOWNSAMPLE = 0, ICB_OP_PAD = 1, ICB_OP_COPY_S
 ICB_API int icb_blockop_host(int op, int codec, int etc_strategy, const uint32_t *args, const void *src, size_t src_size,
                              void *dst, size_t dst_size);
 
+/*
+ * Peer-mapped output for the multi-GPU stripe path ("B200-native alternative" to the NCCL gather
+ * of the packed block stream): the rank that wants the whole stream allocates it with icb_device_alloc and exports
+ * it; every other rank (one process per GPU) opens the handle and passes `mapped + byte offset of its stripe` as d_dst
+ * of icb_encode4x4_stripe.  The encoder's block stores then travel over NVLink straight into the owner's buffer --
+ * the gather is fused into the kernel's epilogue and overlaps the encode -- and the stream is complete on the owner
+ * once every rank's stream has been synchronised.  icb_device_alloc is a plain cudaMalloc (pool sub-allocations
+ * cannot be exported); the handle is ICB_IPC_HANDLE_BYTES opaque bytes to ship through any channel.
+ */
+#define ICB_IPC_HANDLE_BYTES 64
+ICB_API int icb_device_alloc(size_t bytes, void **d_ptr);
+ICB_API int icb_device_free(void *d_ptr);
+ICB_API int icb_ipc_export(const void *d_ptr, void *handle);
+ICB_API int icb_ipc_open(const void *handle, void **d_ptr);
+ICB_API int icb_ipc_close(void *d_ptr);
+
 /* Page-locked host memory for icb_compress_host callers. */
 ICB_API void *icb_host_alloc(size_t bytes);
 ICB_API void icb_host_free(void *p);

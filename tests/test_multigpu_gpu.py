@@ -1,0 +1,74 @@
+"""Two-GPU check of the stripe path on real devices (skipped on a one-GPU box): each rank encodes its block-row stripe
+(a) into local memory, gathered with NCCL, and (b) straight into rank 0's buffer through the peer mapping
+(sharding.PeerStream, the fused gather); both must equal the oracle's encoding of the whole image."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import checkers as ck
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    import torch.distributed as dist
+
+    import image_compression_b200 as icb
+    from image_compression_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ok = True
+    for codec, fmt, nc, bb, h, w in ((icb.CODEC_DXT1, icb.RGBA, 4, 8, 1024, 512), (icb.CODEC_DXT5, icb.RGBA, 4, 16, 520, 256),
+                                     (icb.CODEC_DXT1, icb.RGB, 3, 8, 260, 512), (icb.CODEC_ETC1, icb.RGB, 3, 8, 64, 256)):
+        pitch = w * nc
+        whole = ck.synthetic(h * pitch, 5)
+        grid_rows, grid_cols = h // 4, w // 4
+        r0, r1 = sharding.stripe_rows(grid_rows, rank, world)
+        mine = torch.from_numpy(whole[r0 * 4 * pitch:r1 * 4 * pitch].copy()).cuda()
+        base = mine.data_ptr() - r0 * 4 * pitch
+        local = torch.empty((r1 - r0) * grid_cols * bb, dtype=torch.uint8, device="cuda")
+        icb.encode_stripe_device(codec, fmt, base, h, w, pitch, h, w, r0, r1, local)
+        ps = sharding.PeerStream(grid_rows * grid_cols * bb, dst=0)
+        icb.encode_stripe_device(codec, fmt, base, h, w, pitch, h, w, r0, r1, ps.stripe_ptr(r0 * grid_cols * bb))
+        ps.complete()
+        gathered = sharding.gather_blocks(local, grid_rows, grid_cols, bb, dst=0)
+        if rank == 0:
+            if codec == icb.CODEC_ETC1:
+                want = ck.oracle_etc1(ck.ETC_SMALLER_ERROR, whole, h, w)
+            elif nc == 4 and codec == icb.CODEC_DXT1:
+                want = ck.oracle_dxt1_rgba(whole, h, w)
+            else:
+                want = ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, whole, h, w)
+            ok = ok and np.array_equal(gathered.cpu().numpy(), want) and np.array_equal(ps.tensor().cpu().numpy(), want)
+        ps.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        results.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_stripes_nccl_gather_and_peer_stores_match_oracle():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert results.get(timeout=5) == 1
