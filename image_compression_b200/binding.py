@@ -37,6 +37,7 @@ PROTOTYPES = {
     "icb_encode4x4_stripe": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "icb_pvrtc2_scratch_size": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "icb_pvrtc2_encode_rgba8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "icb_pvrtc2_encode_stripe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "icb_compress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "icb_decode4x4": (C.c_int, [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "icb_decompress_host": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
@@ -162,6 +163,17 @@ def pvrtc_encode_device(src, h, w, out=None, scratch=None, stream=None):
     with torch.cuda.device(src.device):
         _check(lib().icb_pvrtc2_encode_rgba8(src.data_ptr(), h, w, out.data_ptr(),
                                              scratch.data_ptr() if scratch is not None else None, _stream_ptr(stream)))
+    return out
+
+
+def pvrtc_encode_stripe_device(rows, first_pixel, h, w, r0, r1, out, scratch=None, stream=None):
+    """Block rows [r0, r1) of an h x w image.  rows: uint8 tensor with image rows 4*(r0-1) .. 4*(r1+1)-1 (wrapped),
+    first_pixel: 4-byte uint8 tensor holding pixel (0,0), out: the WHOLE image's block buffer (tensor or raw address)."""
+    import torch
+    with torch.cuda.device(rows.device):
+        out_ptr = out if isinstance(out, int) else out.data_ptr()
+        _check(lib().icb_pvrtc2_encode_stripe(rows.data_ptr(), first_pixel.data_ptr(), h, w, r0, r1, C.c_void_p(out_ptr),
+                                              scratch.data_ptr() if scratch is not None else None, _stream_ptr(stream)))
     return out
 
 

@@ -401,34 +401,71 @@ size_t icb_pvrtc2_scratch_size(uint32_t h, uint32_t w) {
   return static_cast<size_t>(w / 8) * (h / 4) * 4 * 2 + static_cast<size_t>(w / 8) * h * 2;
 }
 
-int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_dst, void *d_scratch, void *stream) {
-  if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
-  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero image dimension");
-  if ((w & (w - 1)) || (h & (h - 1)) || w != h || w % 8 != 0 || h % 4 != 0)
-    return fail(ICB_ERR_UNSUPPORTED, "PVRTC needs a square power-of-two image of at least 8x8, got %ux%u", h, w);
-  if (reinterpret_cast<uintptr_t>(d_src) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+namespace {
+// Shared by the whole-image and the stripe entry points: block rows [r0, r1) of an h x w image whose resident pixel
+// rows start at image row src_row0 (see PvrtcParams).
+int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint32_t w, uint32_t src_row0, uint32_t r0,
+                 uint32_t r1, bool whole, void *d_dst, void *d_scratch, cudaStream_t st) {
   DeviceInfo info;
   if (int s = device_info(&info)) return s;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   void *scratch = d_scratch;
   if (!scratch) ICB_CUDA(cudaMallocAsync(&scratch, icb_pvrtc2_scratch_size(h, w), st));
   icb::PvrtcParams p;
-  const uint32_t nblocks = (w / 8) * (h / 4);
+  const uint32_t lw = w / 8, lh = h / 4, nblocks = lw * lh;
   p.src = static_cast<const uint32_t *>(d_src);
+  p.first_pixel = static_cast<const uint32_t *>(d_first_pixel);
   p.low_a = static_cast<uint32_t *>(scratch);
   p.low_b = p.low_a + nblocks;
   p.mod = reinterpret_cast<uint16_t *>(p.low_b + nblocks);
   p.dst = static_cast<uint2 *>(d_dst);
   p.width = w;
   p.height = h;
-  const uint32_t grid = (nblocks + 127) / 128;
-  icb::pvrtc_morph_kernel<<<grid, 128, 0, st>>>(p);
-  icb::pvrtc_modulate_kernel<<<(nblocks * 4 + 255) / 256, 256, 0, st>>>(p);
-  icb::pvrtc_pack_kernel<<<grid, 128, 0, st>>>(p);
+  p.src_row0 = src_row0;
+  if (whole) {
+    p.morph_row0 = 0; p.morph_rows = lh;
+    p.mod_row0 = 0; p.mod_rows = h;
+  } else {
+    p.morph_row0 = (r0 + lh - 1) & (lh - 1); p.morph_rows = r1 - r0 + 2;
+    p.mod_row0 = 4 * r0; p.mod_rows = 4 * (r1 - r0) + 1;
+  }
+  p.pack_row0 = r0; p.pack_rows = r1 - r0;
+  icb::pvrtc_morph_kernel<<<(lw * p.morph_rows + 127) / 128, 128, 0, st>>>(p);
+  icb::pvrtc_modulate_kernel<<<(lw * p.mod_rows + 255) / 256, 256, 0, st>>>(p);
+  icb::pvrtc_pack_kernel<<<(lw * p.pack_rows + 127) / 128, 128, 0, st>>>(p);
   g_launches.fetch_add(3, std::memory_order_relaxed);
   ICB_CUDA(cudaGetLastError());
   if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));
   return ICB_OK;
+}
+
+int pvrtc_check_shape(uint32_t h, uint32_t w) {
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero image dimension");
+  if ((w & (w - 1)) || (h & (h - 1)) || w != h || w % 8 != 0 || h % 4 != 0)
+    return fail(ICB_ERR_UNSUPPORTED, "PVRTC needs a square power-of-two image of at least 8x8, got %ux%u", h, w);
+  return ICB_OK;
+}
+}  // namespace
+
+int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_dst, void *d_scratch, void *stream) {
+  if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (int s = pvrtc_check_shape(h, w)) return s;
+  if (reinterpret_cast<uintptr_t>(d_src) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+  return pvrtc_launch(d_src, d_src, h, w, 0, 0, h / 4, true, d_dst, d_scratch, static_cast<cudaStream_t>(stream));
+}
+
+int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pixel, uint32_t h, uint32_t w, uint32_t block_row_begin,
+                             uint32_t block_row_end, void *d_dst, void *d_scratch, void *stream) {
+  if (!d_rows || !d_first_pixel || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (int s = pvrtc_check_shape(h, w)) return s;
+  if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+  const uint32_t lh = h / 4;
+  if (block_row_begin >= block_row_end || block_row_end > lh)
+    return fail(ICB_ERR_INVALID, "block row range [%u,%u) outside grid of %u rows", block_row_begin, block_row_end, lh);
+  if (block_row_end - block_row_begin + 2 > lh)
+    return fail(ICB_ERR_INVALID, "a stripe plus its two halo block rows must not exceed the image (use icb_pvrtc2_encode_rgba8)");
+  const uint32_t src_row0 = 4 * ((block_row_begin + lh - 1) & (lh - 1));
+  return pvrtc_launch(d_rows, d_first_pixel, h, w, src_row0, block_row_begin, block_row_end, false, d_dst, d_scratch,
+                      static_cast<cudaStream_t>(stream));
 }
 
 int icb_decode4x4(int codec, const void *d_blocks, uint32_t h, uint32_t w, uint32_t block_cols, int swap_rb, void *d_dst,

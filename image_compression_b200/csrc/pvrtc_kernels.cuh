@@ -16,21 +16,37 @@
 
 namespace icb {
 
+// Whole image: src holds all rows, src_row0 = 0, every range covers the image.  Row stripe (one rank of a sharded
+// image): src holds only the pixel rows of block rows [r0 - 1, r1 + 1) -- the stripe plus one
+// block row of halo above and below, wrapped round the torus -- starting at image row src_row0 = 4 * (r0 - 1) mod h;
+// Morph runs over those r1 - r0 + 2 block rows (the halo blocks are recomputed, not exchanged), Modulate over pixel
+// rows [4 r0, 4 r1] (the extra row is the one the last block row's mode decision looks at), Pack over [r0, r1).
+// Scratch images are indexed by absolute position in both cases, and so is the Z-ordered output.
 struct PvrtcParams {
-  const uint32_t *src;  // RGBA8 pixels, row-major, no padding
-  uint32_t *low_a;      // (w/8) x (h/4) A colours
-  uint32_t *low_b;      // (w/8) x (h/4) B colours
-  uint16_t *mod;        // h x (w/8) words: 2-bit modulation of pixels 8*bx .. 8*bx+7 of row y
-  uint2 *dst;           // w*h/32 blocks in Z-order
+  const uint32_t *src;          // RGBA8 pixels, row-major, no padding; row 0 of this buffer is image row src_row0
+  const uint32_t *first_pixel;  // image pixel (0,0): quirk P1 (pvrtc_compressor.cc:255-329) needs it in every block
+  uint32_t *low_a;              // (w/8) x (h/4) A colours
+  uint32_t *low_b;              // (w/8) x (h/4) B colours
+  uint16_t *mod;                // h x (w/8) words: 2-bit modulation of pixels 8*bx .. 8*bx+7 of row y
+  uint2 *dst;                   // w*h/32 blocks in Z-order
   uint32_t width, height;
+  uint32_t src_row0;            // image row held in row 0 of src
+  uint32_t morph_row0, morph_rows;  // block rows Morph covers: morph_row0 .. +morph_rows (mod h/4)
+  uint32_t mod_row0, mod_rows;      // pixel rows Modulate covers (mod h)
+  uint32_t pack_row0, pack_rows;    // block rows Pack covers
 };
+
+// Address of image row y (absolute, < height) in the resident rows.
+__device__ __forceinline__ const uint32_t *pv_src_row(const PvrtcParams &p, uint32_t y) {
+  return p.src + static_cast<size_t>((y - p.src_row0) & (p.height - 1u)) * p.width;
+}
 
 __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= lw * lh) return;
-  const uint32_t bx = t % lw, by = t / lw;
-  const uint32_t *origin = p.src + static_cast<size_t>(by * 4) * p.width + bx * 8;
+  if (t >= lw * p.morph_rows) return;
+  const uint32_t bx = t % lw, by = (p.morph_row0 + t / lw) & (lh - 1u);
+  const uint32_t *origin = pv_src_row(p, by * 4u) + bx * 8;  // a block's four rows are contiguous in the buffer
   uint32_t px[32];
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
@@ -41,16 +57,16 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   }
   auto fetch = [&](uint32_t j) { return __ldg(origin + static_cast<size_t>(j >> 3) * p.width + (j & 7u)); };
   uint32_t ca, cb;
-  pv_block_extremes(px, __ldg(p.src), fetch, &ca, &cb);
-  p.low_a[t] = ca;
-  p.low_b[t] = cb;
+  pv_block_extremes(px, __ldg(p.first_pixel), fetch, &ca, &cb);
+  p.low_a[by * lw + bx] = ca;
+  p.low_b[by * lw + bx] = cb;
 }
 
 __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= lw * p.height) return;
-  const uint32_t bx = t % lw, y = t / lw;
+  if (t >= lw * p.mod_rows) return;
+  const uint32_t bx = t % lw, y = (p.mod_row0 + t / lw) & (p.height - 1u);
   // Low-resolution rows/columns this pixel row interpolates between, wrapped (pvrtc_compressor.cc:216-223).
   const uint32_t top = ((y - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
   const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
@@ -65,7 +81,7 @@ __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p
     vb[i].rb = bt.rb * (4u - fy) + bb.rb * fy;
     vb[i].ga = bt.ga * (4u - fy) + bb.ga * fy;
   }
-  const uint4 *row = reinterpret_cast<const uint4 *>(p.src + static_cast<size_t>(y) * p.width + bx * 8);
+  const uint4 *row = reinterpret_cast<const uint4 *>(pv_src_row(p, y) + bx * 8);
   const uint4 u = __ldg(row), v = __ldg(row + 1);
   const uint32_t px[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
   uint32_t bits = 0;
@@ -78,14 +94,14 @@ __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p
     const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
     bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
   }
-  p.mod[t] = static_cast<uint16_t>(bits);
+  p.mod[y * lw + bx] = static_cast<uint16_t>(bits);
 }
 
 __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= lw * lh) return;
-  const uint32_t bx = t % lw, by = t / lw;
+  if (t >= lw * p.pack_rows) return;
+  const uint32_t bx = t % lw, by = (p.pack_row0 + t / lw) & (lh - 1u);
   const uint32_t right_bx = (bx + 1u) & (lw - 1u);
   uint32_t row[5], right[4];
 #pragma unroll
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   }
   bool one_bpp;
   const uint32_t mod_bits = pv_pack_modulation(row, right, &one_bpp);
-  const uint32_t colours = pv_pack_colours(__ldg(p.low_a + t), __ldg(p.low_b + t), one_bpp);
+  const uint32_t colours = pv_pack_colours(p.low_a[by * lw + bx], p.low_b[by * lw + bx], one_bpp);
   p.dst[pv_z_index(bx, by)] = make_uint2(mod_bits, colours);
 }
 

@@ -13,7 +13,7 @@
  *       
  *   icb_etc1_encode_rgb8
  *       EtcCompressor::Compress / CompressAndPad (internal/etc_compressor.cc:747-758, 787-800)
- *   icb_pvrtc2_encode_rgba8
+ *   icb_pvrtc2_encode_rgba8 / icb_pvrtc2_encode_stripe
  *       CompressPVRTC_RGBA_2BPP behind PvrtcCompressor::Compress (internal/pvrtc_compressor.cc:586-597, 636-667)
  *   icb_compress_host
  *       what XxxCompressor::Compress hands its buffer to: host pixels in, host blocks out
@@ -106,6 +106,20 @@ ICB_API int icb_encode4x4_stripe(int codec, int format_components, const void *d
 ICB_API size_t icb_pvrtc2_scratch_size(uint32_t height, uint32_t width);
 ICB_API int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t height, uint32_t width, void *d_dst, void *d_scratch,
                             void *stream);
+/*
+ * Row-stripe form for sharding one image over several GPUs: encodes block rows
+ * [block_row_begin, block_row_end) (8x4 blocks: height/4 block rows).  PVRTC is not block-local -- a pixel blends the
+ * A/B colours of the neighbouring blocks, toroidally -- so d_rows holds the stripe's pixel rows PLUS one block row (4
+ * pixel rows) of halo above and below: image rows 4*(begin-1) .. 4*(end+1)-1, wrapped modulo height, in that order,
+ * contiguous, width*4 bytes each.  The halo blocks' colours are recomputed locally; nothing is exchanged between
+ * ranks.  d_first_pixel points at a device copy of image pixel (0,0) (4 bytes), which the reference's extreme search
+ * can pick in any block (quirk P1, internal/pvrtc_compressor.cc:255-329).  d_dst is the WHOLE image's block buffer
+ * (width*height/4 bytes, Z-order): the stripe's blocks are stored at their final positions, so with a peer-mapped
+ * d_dst (icb_ipc_open) the ranks assemble the image without a gather.  d_scratch as above (same size), or NULL.
+ * The stripe plus its halo must not exceed the image: end - begin + 2 <= height/4.
+ */
+ICB_API int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pixel, uint32_t height, uint32_t width,
+                             uint32_t block_row_begin, uint32_t block_row_end, void *d_dst, void *d_scratch, void *stream);
 
 /*
  * Host-buffer path: validates like the reference's Compress / CompressAndPad, stages src to the device in

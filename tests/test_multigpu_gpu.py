@@ -1,6 +1,6 @@
 """Two-GPU check of the stripe path on real devices (skipped on a one-GPU box): each rank encodes its block-row stripe
 (a) into local memory, gathered with NCCL, and (b) straight into rank 0's buffer through the peer mapping
-(sharding.PeerStream, the fused gather); both must equal the oracle's encoding of the whole image."""
+(sharding.PeerStream, the fused gather); both must equal the oracle's encoding of the whole image.  PVRTC: halo stripes, Z-order stores into rank 0's buffer."""
 import os
 import socket
 
@@ -52,6 +52,20 @@ def _worker(rank, world, port, results):
                 want = ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, whole, h, w)
             ok = ok and np.array_equal(gathered.cpu().numpy(), want) and np.array_equal(ps.tensor().cpu().numpy(), want)
         ps.close()
+    # PVRTC: stripes with a one-block-row halo each side, blocks stored at their Z-order slots of rank 0's buffer
+    n = 256
+    img = ck.synthetic(n * n * 4, 6)
+    lh = n // 4
+    r0, r1 = sharding.stripe_rows(lh, rank, world)
+    ys = [(4 * (r0 - 1) + k) % n for k in range(4 * (r1 - r0 + 2))]
+    rows = torch.from_numpy(np.ascontiguousarray(img.reshape(n, n * 4)[ys]).ravel()).cuda()
+    first = torch.from_numpy(img[:4].copy()).cuda()
+    ps = sharding.PeerStream(n * n // 4, dst=0)
+    icb.pvrtc_encode_stripe_device(rows, first, n, n, r0, r1, ps.stripe_ptr(0))
+    ps.complete()
+    if rank == 0:
+        ok = ok and np.array_equal(ps.tensor().cpu().numpy(), ck.oracle_pvrtc(img, n, n))
+    ps.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -319,3 +319,72 @@ def test_host_path_is_thread_safe(icb):
     for t in threads:
         t.join()
     assert not failures
+
+
+_DRIVER_SNIPPET = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, "tests")
+import checkers as ck, imagegen
+import image_compression_b200 as icb
+for kind in ("random", "smooth_noise", "two_colour"):
+    for (h, w) in ((64, 256), (40, 516), (260, 1024), (72, 1280)):
+        rgba = imagegen.make(kind, h, w, 4, seed=7)
+        rgb = np.ascontiguousarray(rgba[..., :3])
+        cases = [(0, ck.RGBA, rgba, ck.oracle_dxt1_rgba(rgba.ravel(), h, w)), (1, ck.RGBA, rgba, ck.oracle_dxt(ck.RGBA, rgba.ravel(), h, w)),
+                 (0, ck.RGB, rgb, ck.oracle_dxt(ck.RGB, rgb.ravel(), h, w)), (2, ck.RGB, rgb, ck.oracle_etc1(2, rgb.ravel(), h, w))]
+        for codec, fmt, img, want in cases:
+            got = icb.encode_device(codec, fmt, torch.from_numpy(img.ravel().copy()).cuda(), h, w).cpu().numpy()
+            assert np.array_equal(got, want), (kind, h, w, codec, fmt)
+print("driver ok")
+"""
+
+
+@pytest.mark.parametrize("driver,stages", [("ring", "2"), ("ring", "3"), ("producer", "3"), ("producer", "4")])
+def test_both_ring_drivers_every_codec(icb, driver, stages):
+    """The launcher picks one ring-refill scheme per codec (producer warp for DXT1/ETC1, counted release for DXT5);
+    ICB_DRIVER / ICB_TMA_STAGES force the other combinations, which must stay bit-exact too.  The choice is cached
+    per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ICB_DRIVER=driver, ICB_TMA_STAGES=stages)
+    res = subprocess.run([sys.executable, "-c", _DRIVER_SNIPPET], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "driver ok" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def _pvrtc_stripe_rows(img, h, w, r0, r1):
+    """Image rows 4*(r0-1) .. 4*(r1+1)-1, wrapped: what icb_pvrtc2_encode_stripe wants resident."""
+    ys = [(4 * (r0 - 1) + k) % h for k in range(4 * (r1 - r0 + 2))]
+    return np.ascontiguousarray(img.reshape(h, w * 4)[ys]).ravel()
+
+
+@pytest.mark.parametrize("n,parts", [(64, 2), (64, 4), (256, 2), (256, 8), (512, 3), (32, 2)])
+def test_pvrtc_stripes_assemble_whole_image(icb, n, parts):
+    """Every rank of a sharded PVRTC encode holds only its block rows plus one halo block row each side (wrapped) and
+    pixel (0,0); each stripe's blocks land at their Z-order slots of the whole-image buffer.  The union must equal the
+    reference (oracle) encoding of the whole image -- including quirk P1 blocks, which read pixel (0,0)."""
+    from image_compression_b200 import sharding
+    for kind in ("random", "zero_channel", "alpha_extremes", "smooth_noise"):
+        img = imagegen.make(kind, n, n, 4, seed=61).ravel()
+        want = ck.oracle_pvrtc(img, n, n)
+        out = torch.zeros(n * n // 4, dtype=torch.uint8, device="cuda")
+        first = dev(img[:4])
+        lh = n // 4
+        for r in range(parts):
+            r0, r1 = sharding.stripe_rows(lh, r, parts)
+            if r1 - r0 + 2 > lh:
+                pytest.skip("stripe + halo larger than the image")
+            icb.pvrtc_encode_stripe_device(dev(_pvrtc_stripe_rows(img, n, n, r0, r1)), first, n, n, r0, r1, out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want), (kind, n, parts)
+
+
+def test_pvrtc_stripe_rejections(icb):
+    rows = torch.zeros(64 * 4 * 4 * 6, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64 * 64 // 4, dtype=torch.uint8, device="cuda")
+    first = torch.zeros(4, dtype=torch.uint8, device="cuda")
+    for (h, w, r0, r1) in ((64, 64, 0, 16), (64, 64, 3, 3), (64, 64, 5, 17), (48, 48, 0, 2), (64, 32, 0, 2)):
+        with pytest.raises(icb.IcbError):
+            icb.pvrtc_encode_stripe_device(rows, first, h, w, r0, r1, out)

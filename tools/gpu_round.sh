@@ -20,5 +20,5 @@ done
 for wl in dxt1_rgba8 dxt5_rgba8; do
   ICB_NO_PDL=1 timeout 300 python bench.py --workload $wl --steps 50 --warmup 5 --no-cpu-baseline > $OUT/bench_${wl}_nopdl.json 2> $OUT/bench_${wl}_nopdl.err; show $OUT/bench_${wl}_nopdl.json "$wl (no PDL)"
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"encode4x4_tma" -s 4 -c 1 -o $OUT/prof_dxt1_rgba8 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"encode4x4_(tma|ring)" -s 4 -c 1 -o $OUT/prof_dxt1_rgba8 \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu.log 2>&1; echo "ncu exit $?"
