@@ -39,6 +39,29 @@ WORKLOADS = {
 }
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner to fd 1 at some
+    debug levels) do not know that: point fd 1 at stderr for the duration of the run and keep the real stdout for the
+    result line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -215,12 +238,34 @@ def run_reference_arm(args):
         "e2e": {"value": cpu["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One rank per GPU: run (and therefore allocate the pinned staging buffers of the end-to-end leg) on the CPUs NVML
+    reports as local to this rank's GPU, so that eight ranks do not pull their H2D traffic through one socket.
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is unavailable (nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
 
 def run_gpu_arm(args):
     import ctypes as C
@@ -236,6 +281,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
@@ -442,7 +488,8 @@ def run_gpu_arm(args):
                          "kernel_ms_isolated_source": "separate pass, each launch between its own two events",
                          "read_only_frac": (in_bytes / (k_avg * 1e-3) / 1e9) / peak},
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "icb_compress_host (pinned host buffers)", "output_equals_device_path": e2e_check},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "icb_compress_host (pinned host buffers)", "output_equals_device_path": e2e_check,
+                    "cpus_bound_to_gpu_numa_node": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -452,7 +499,7 @@ def run_gpu_arm(args):
             line["gather"] = gather
         if fused:
             line["fused_gather"] = fused
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -467,6 +514,7 @@ def main():
     ap.add_argument("--workload", default="dxt1_rgba8", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

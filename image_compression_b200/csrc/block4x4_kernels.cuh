@@ -225,7 +225,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // and the last tile of a row / column is shifted back so that it ends exactly at col1 / row1 -- the blocks it
 // shares with its neighbour are simply encoded twice, to the same bytes.
 template <int kCodec, int kNcomp, int kTmaStages>
-__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32)
+__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32, kCodec == kCodecDxt1 ? 4 : 3)
     encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                          uint32_t num_tiles) {
   using Shape = TileShape<kNcomp>;
