@@ -486,9 +486,13 @@ int icb_decode4x4(int codec, const void *d_blocks, uint32_t h, uint32_t w, uint3
   p.block_cols = block_cols;
   p.block_rows = (h + 3) / 4;
   p.swap_rb = swap_rb ? 1 : 0;
-  const uint64_t total = static_cast<uint64_t>(p.block_rows) * block_cols;
-  const uint64_t want = (total + 127) / 128;
-  const uint32_t grid = static_cast<uint32_t>(want < static_cast<uint64_t>(info.sm_count) * 32 ? want : info.sm_count * 32);
+  // x covers the block columns 128 at a time; y strides the block rows with enough CTAs to fill the GPU
+  const uint32_t gx = (block_cols + 127) / 128;
+  uint32_t gy = gx ? (static_cast<uint32_t>(info.sm_count) * 32 + gx - 1) / gx : 0;
+  if (gy > p.block_rows) gy = p.block_rows;
+  if (gy > 65535u) gy = 65535u;
+  if (gx == 0 || gy == 0) return ICB_OK;
+  const dim3 grid(gx, gy);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (codec == ICB_CODEC_DXT1) icb::decode4x4_kernel<0><<<grid, 128, 0, st>>>(p);
   if (codec == ICB_CODEC_DXT5) icb::decode4x4_kernel<1><<<grid, 128, 0, st>>>(p);
