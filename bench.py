@@ -471,7 +471,8 @@ def run_gpu_arm(args):
         # average launch duration over the timed region (this rank's own clock): the step IS the launch
         k_avg = t_begin.elapsed_time(t_end) / steps
         achieved = algo_bytes / (k_avg * 1e-3) / 1e9
-        cpu = cpu_reference_throughput(args.workload, 2, 1) if not args.no_cpu_baseline else None
+        # the CPU baseline is a one-GPU-run item (rank 0, N = 1): at N > 1 the ranks are pinned to their GPU's NUMA node
+        cpu = cpu_reference_throughput(args.workload, 2, 1) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if args.workload == "dxt1_rgba8" else "Mpixels/sec " + wl["desc"],
             "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
