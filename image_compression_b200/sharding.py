@@ -22,6 +22,15 @@ def stripe_bytes(grid_rows, grid_cols, block_bytes, rank, world):
     return (r1 - r0) * grid_cols * block_bytes
 
 
+def pvrtc_stripe_row_indices(height, r0, r1):
+    """Image rows a rank must hold to encode PVRTC block rows [r0, r1) (8x4 blocks, height/4 block rows): the
+    stripe plus one block row of halo above and below, wrapped round the torus, in the order
+    icb_pvrtc2_encode_stripe expects them (first row = 4*(r0-1) mod height)."""
+    lh = height // 4
+    assert 0 <= r0 < r1 <= lh and r1 - r0 + 2 <= lh
+    return [(4 * (r0 - 1) + k) % height for k in range(4 * (r1 - r0 + 2))]
+
+
 def gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, group=None):
     """Gathers every rank's stripe of packed blocks (uint8 tensor) onto `dst`; returns the whole stream there and
     None elsewhere.  Equal stripes use one gather; uneven ones are padded to the largest stripe and trimmed."""

@@ -57,7 +57,7 @@ def _worker(rank, world, port, results):
     img = ck.synthetic(n * n * 4, 6)
     lh = n // 4
     r0, r1 = sharding.stripe_rows(lh, rank, world)
-    ys = [(4 * (r0 - 1) + k) % n for k in range(4 * (r1 - r0 + 2))]
+    ys = sharding.pvrtc_stripe_row_indices(n, r0, r1)
     rows = torch.from_numpy(np.ascontiguousarray(img.reshape(n, n * 4)[ys]).ravel()).cuda()
     first = torch.from_numpy(img[:4].copy()).cuda()
     ps = sharding.PeerStream(n * n // 4, dst=0)

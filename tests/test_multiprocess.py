@@ -69,3 +69,23 @@ def test_stripe_partition_properties():
             assert spans[0][0] == 0 and spans[-1][1] == rows
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert sum(sharding.stripe_bytes(rows, 5, 8, r, world) for r in range(world)) == rows * 5 * 8
+
+
+def test_pvrtc_stripe_rows_wrap_and_cover():
+    """Halo stripes: every rank's resident rows start one block row above its stripe (wrapped), cover the stripe in
+    order, end one block row below it (wrapped); together the stripes' own rows tile the image exactly once."""
+    from image_compression_b200 import sharding
+    for h in (32, 64, 256):
+        lh = h // 4
+        for world in (2, 3, 4, 8):
+            if lh // world + 3 > lh:
+                continue
+            own = []
+            for r in range(world):
+                r0, r1 = sharding.stripe_rows(lh, r, world)
+                rows = sharding.pvrtc_stripe_row_indices(h, r0, r1)
+                assert len(rows) == 4 * (r1 - r0 + 2) and len(set(rows)) == len(rows)
+                assert rows[0] == (4 * (r0 - 1)) % h and rows[-1] == (4 * (r1 + 1) - 1) % h
+                assert rows[4:-4] == list(range(4 * r0, 4 * r1))
+                own += rows[4:-4]
+            assert own == list(range(h))

@@ -356,8 +356,8 @@ def test_both_ring_drivers_every_codec(icb, driver, stages):
 
 def _pvrtc_stripe_rows(img, h, w, r0, r1):
     """Image rows 4*(r0-1) .. 4*(r1+1)-1, wrapped: what icb_pvrtc2_encode_stripe wants resident."""
-    ys = [(4 * (r0 - 1) + k) % h for k in range(4 * (r1 - r0 + 2))]
-    return np.ascontiguousarray(img.reshape(h, w * 4)[ys]).ravel()
+    from image_compression_b200 import sharding
+    return np.ascontiguousarray(img.reshape(h, w * 4)[sharding.pvrtc_stripe_row_indices(h, r0, r1)]).ravel()
 
 
 @pytest.mark.parametrize("n,parts", [(64, 2), (64, 4), (256, 2), (256, 8), (512, 3), (32, 2)])
