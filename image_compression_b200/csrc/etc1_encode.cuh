@@ -77,6 +77,37 @@ __device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[1
   return best;
 }
 
+// The same for BOTH sub-blocks of one orientation at once.  Building the clamped candidates is a quarter of the
+// integer-pipe work of the exhaustive search when done channel by channel (three VIADDMNMX + two packing operations
+// per candidate); the two sub-blocks meet the same modifier at the same time, so their channels ride in 16-bit lanes
+// -- (r, b) of each base in one register, (g of base 1, g of base 2) in a third -- and one VIADDMNMX.S16x2.RELU adds,
+// caps at 255 and floors at 0 in both lanes: three of those plus two byte permutes make a PAIR of candidates.
+template <uint32_t kMask1, uint32_t kMask2>
+__device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16], uint32_t base1, uint32_t base2,
+                                                       uint32_t *key1, uint32_t *key2) {
+  const uint32_t rb1 = base1 & 0x00ff00ffu, rb2 = base2 & 0x00ff00ffu;
+  const uint32_t g12 = __byte_perm(base1, base2, 0x3531);  // (g1, 0, g2, 0): the bases' top bytes are zero
+  uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu;
+#pragma unroll
+  for (int cw = 0; cw < 8; ++cw) {
+    EtcCandidates k1, k2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mag = (j & 1) ? etc_large(cw) : etc_small(cw);
+      const uint32_t m2 = (static_cast<uint32_t>((j & 2) ? -mag : mag) & 0xffffu) * 0x10001u;
+      const uint32_t c_rb1 = __viaddmin_s16x2_relu(rb1, m2, 0x00ff00ffu);
+      const uint32_t c_rb2 = __viaddmin_s16x2_relu(rb2, m2, 0x00ff00ffu);
+      const uint32_t c_g12 = __viaddmin_s16x2_relu(g12, m2, 0x00ff00ffu);
+      k1.c[j] = __byte_perm(c_rb1, c_g12, 0x1240);  // (r, g1, b, 0)
+      k2.c[j] = __byte_perm(c_rb2, c_g12, 0x1260);  // (r, g2, b, 0)
+    }
+    best1 = min(best1, etc_codeword_error<kMask1>(px, k1) * 8u + static_cast<uint32_t>(cw));
+    best2 = min(best2, etc_codeword_error<kMask2>(px, k2) * 8u + static_cast<uint32_t>(cw));
+  }
+  *key1 = best1;
+  *key2 = best2;
+}
+
 // FindCodewordHeuristic: codeword from the largest per-channel mean absolute deviation; key as above.
 template <uint32_t kMask>
 __device__ __forceinline__ uint32_t etc_heuristic_codeword_key(const uint32_t (&px)[16], uint32_t base_rgb) {
@@ -184,14 +215,8 @@ __device__ __forceinline__ uint2 etc1_encode_block(const uint32_t (&px)[16], int
     }
   } else {
     uint32_t lr1 = 0, lr2 = 0, tb1 = 0, tb2 = 0;
-    if (strategy != kEtcSplitHorizontally) {
-      lr1 = etc_best_codeword_key<kLeft>(px, lr.base1);
-      lr2 = etc_best_codeword_key<kRight>(px, lr.base2);
-    }
-    if (strategy != kEtcSplitVertically) {
-      tb1 = etc_best_codeword_key<kTop>(px, tb.base1);
-      tb2 = etc_best_codeword_key<kBottom>(px, tb.base2);
-    }
+    if (strategy != kEtcSplitHorizontally) etc_best_codeword_keys<kLeft, kRight>(px, lr.base1, lr.base2, &lr1, &lr2);
+    if (strategy != kEtcSplitVertically) etc_best_codeword_keys<kTop, kBottom>(px, tb.base1, tb.base2, &tb1, &tb2);
     // kSmallerError keeps the unflipped block unless the flipped one is strictly better (etc_compressor.cc:583)
     flip = strategy == kEtcSplitHorizontally ||
            (strategy == kEtcSmallerError && (tb1 >> 3) + (tb2 >> 3) < (lr1 >> 3) + (lr2 >> 3));
