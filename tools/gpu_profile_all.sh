@@ -5,7 +5,7 @@ TAG=$1; shift
 WLS=${@:-"dxt1_rgba8 dxt5_rgba8 dxt1_rgb8 etc1_rgb8 pvrtc2_rgba8"}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 for wl in $WLS; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"encode4x4_(tma|ring)|pvrtc" -s 6 -c 1 -f -o $OUT/prof_$wl \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"encode4x4_(tma|ring)|pvrtc" -s 6 -c $([ $wl = pvrtc2_rgba8 ] && echo 3 || echo 1) -f -o $OUT/prof_$wl \
       python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_$wl.log 2>&1; echo "ncu $wl exit $?"
   python tools/ncu_summary.py $OUT/prof_$wl.ncu-rep > $OUT/summary_$wl.txt 2>&1
   ncu -i $OUT/prof_$wl.ncu-rep --page source --csv > $OUT/source_$wl.csv 2>/dev/null
