@@ -4,6 +4,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <unistd.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -298,7 +301,43 @@ __global__ void fill_synthetic_kernel(uint8_t *dst, size_t bytes, uint64_t seed,
 // through the driver's single-threaded bounce buffer (measured on the B200 box: 10 GB/s, 26 ms for an 8192^2 RGBA8
 // image against 5 ms from pinned memory), so the host pipeline stages such buffers itself: worker threads copy each
 // chunk into a ring of pinned buffers while the previous chunk's DMA is in flight, and the packed blocks come back
-// the same way (26 -> 8.7 ms with 16 threads).  Pinned or registered caller memory (icb_host_alloc) skips all of this.
+// the same way, with streaming stores (26 -> 6.9 ms).  Pinned or registered caller memory (icb_host_alloc) skips all of this.
+// memcpy with streaming (non-temporal) stores for the bulk: the destination of a staging copy is read next by the DMA
+// engine (or much later by the caller), never by this core, so write-allocating its lines only costs a third memory
+// stream.  Falls back to memcpy off x86-64 / without AVX2 and for short copies.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_streaming_avx2(uint8_t *dst, const uint8_t *src, size_t n) {
+  const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head) {
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+  }
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+#endif
+void copy_bulk(uint8_t *dst, const uint8_t *src, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && n >= 4096) {
+    copy_streaming_avx2(dst, src, n);
+    return;
+  }
+#endif
+  memcpy(dst, src, n);
+}
+
 class CopyPool {
  public:
   static CopyPool &get() {
@@ -336,11 +375,11 @@ class CopyPool {
     size_t src_pitch, row_bytes, rows;
   };
   CopyPool() {
-    // Copy bandwidth scales with threads well past eight on the B200 hosts (8 threads: 35 GB/s, 16: the PCIe rate is
-    // nearly reached), and a copy burst lasts milliseconds: use the machine, up to 16 threads including the caller.
-    int n = static_cast<int>(std::thread::hardware_concurrency()) - 1;
+    // With streaming stores eight threads already carry 40 GB/s (sixteen measured the same): half the cores, at
+    // most eight including the caller.  ICB_STAGING_THREADS overrides (0 = leave pageable copies to the driver).
+    int n = static_cast<int>(std::thread::hardware_concurrency()) / 2 - 1;
     if (const char *e = getenv("ICB_STAGING_THREADS")) n = atoi(e) - 1;
-    if (n > 15) n = 15;
+    if (n > 7) n = 7;
     pid_ = getpid();
     for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
     for (auto &t : threads_) t.detach();
@@ -349,9 +388,9 @@ class CopyPool {
     const size_t r0 = j.rows * part / parts, r1 = j.rows * (part + 1) / parts;
     if (r1 <= r0) return;
     if (j.dst_pitch == j.src_pitch) {  // one contiguous span, the last row without its padding
-      memcpy(j.dst + r0 * j.dst_pitch, j.src + r0 * j.src_pitch, (r1 - r0 - 1) * j.src_pitch + j.row_bytes);
+      copy_bulk(j.dst + r0 * j.dst_pitch, j.src + r0 * j.src_pitch, (r1 - r0 - 1) * j.src_pitch + j.row_bytes);
     } else {
-      for (size_t r = r0; r < r1; ++r) memcpy(j.dst + r * j.dst_pitch, j.src + r * j.src_pitch, j.row_bytes);
+      for (size_t r = r0; r < r1; ++r) copy_bulk(j.dst + r * j.dst_pitch, j.src + r * j.src_pitch, j.row_bytes);
     }
   }
   void worker(int part) {

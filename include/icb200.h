@@ -125,7 +125,9 @@ ICB_API int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pix
  * Host-buffer path: validates like the reference's Compress / CompressAndPad, stages src to the device in
  * chunks overlapped with the kernels, and copies the blocks back.  padded_height / padded_width: 0 for Compress.
  * dst_size must equal the required size exactly (ICB_ERR_SIZE otherwise), mirroring SetUpCompressedImage
- * (internal/compressor4x4_helper.cc:22-43).  Blocking.  Pinned src/dst (icb_host_alloc) avoids a staging copy.
+ * (internal/compressor4x4_helper.cc:22-43).  Blocking.  Pinned src/dst (icb_host_alloc) are DMA'd directly; ordinary
+ * pageable memory is staged through pinned buffers by a small pool of copy threads (ICB_STAGING_THREADS=n overrides
+ * their number, 0 leaves pageable copies to the CUDA driver).
  */
 ICB_API int icb_compress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t padded_height,
                       uint32_t padded_width, uint32_t padding_bytes_per_row, int etc_strategy, const void *src,
