@@ -1,27 +1,23 @@
 #!/bin/bash
-# A/B timing of driver configurations on the GPU box.  Usage: bash tools/gpu_ab.sh <tag>
-TAG=$1; OUT=gpurun_out/$TAG; mkdir -p $OUT
-run() {  # name, workload, env...
-  name=$1; wl=$2; shift 2
-  env "$@" timeout 200 python bench.py --workload $wl --steps 30 --warmup 5 --no-cpu-baseline > $OUT/${name}_$wl.json 2> $OUT/${name}_$wl.err
-  python - <<PY
-import json
+# A/B timing of kernel / driver configurations on the GPU box, one bench line each.
+#   bash tools/gpu_ab.sh <tag> <workload> NAME[:ENV=VAL,ENV=VAL...] ...
+# e.g. after `tools/build_variants.sh probe "-DICB_PROBE_ENCODER"`:
+#   bash tools/gpu_ab.sh ab1 dxt1_rgba8 default ring:ICB_DRIVER=ring ring2:ICB_DRIVER=ring,ICB_TMA_STAGES=2 \
+#        probe:ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so
+TAG=$1; WL=$2; shift 2
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+for spec in "$@"; do
+  name=${spec%%:*}; envs=""
+  [ "$spec" != "$name" ] && envs=$(echo "${spec#*:}" | tr ',' ' ')
+  env $envs timeout 200 python bench.py --workload $WL --steps 30 --warmup 5 --no-cpu-baseline > $OUT/${name}_$WL.json 2> $OUT/${name}_$WL.err
+  python - "$OUT/${name}_$WL.json" "$name" "$WL" <<'PY'
+import json, sys
 try:
-    d=json.load(open("$OUT/${name}_$wl.json")); r=d["roofline"]
-    print("%-22s %-12s b2b %.2f us  iso-med %.2f  min %.2f  frac %.3f  e2e-ok %s clocks %s %s" % ("$name", "$wl", r["kernel_ms_avg"]*1e3, r["kernel_ms_isolated_median"]*1e3, r["kernel_ms_min"]*1e3, r["frac"], d["e2e"]["output_equals_device_path"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
+    d = json.load(open(sys.argv[1])); r = d["roofline"]
+    print("%-22s %-12s b2b %.2f us  iso-med %.2f  min %.2f  frac %.3f  e2e-ok %s clocks %s %s" % (
+        sys.argv[2], sys.argv[3], r["kernel_ms_avg"] * 1e3, r["kernel_ms_isolated_median"] * 1e3, r["kernel_ms_min"] * 1e3,
+        r["frac"], d["e2e"]["output_equals_device_path"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
 except Exception as e:
-    print("$name $wl failed", e); print(open("$OUT/${name}_$wl.err").read()[-1500:])
+    print(sys.argv[2], sys.argv[3], "failed", e)
 PY
-}
-timeout 700 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_gpu.log
-for wl in dxt1_rgba8 dxt5_rgba8 dxt1_rgb8 etc1_rgb8; do
-  run ring_default $wl A=1
-  run producer_warp $wl ICB_PRODUCER_WARP=1
-  run ring_4stages $wl ICB_TMA_STAGES=4
 done
-run ring_2stages dxt1_rgba8 ICB_TMA_STAGES=2
-run ring_2stages dxt1_rgb8 ICB_TMA_STAGES=2
-run probe_ring3 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so
-run probe_ring4 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_TMA_STAGES=4
-run probe_ring2 dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_TMA_STAGES=2
-run probe_producer dxt1_rgba8 ICB200_LIB=$PWD/image_compression_b200/lib/variants/libicb200_probe.so ICB_PRODUCER_WARP=1
