@@ -402,12 +402,17 @@ def run_gpu_arm(args):
 
     # ---- fused gather: every rank's encoder stores its blocks straight into rank 0's buffer over NVLink (peer-mapped
     # output, sharding.PeerStream); timed like `value` (K steps between two events, max over ranks), reported separately
-    fused = None
+    fused, ps = None, None
     if world > 1 and codec != 3:
         from image_compression_b200 import sharding
         block_bytes = 16 if codec == 1 else 8
         total_out = grid_rows * (n // 4) * block_bytes
-        ps = sharding.PeerStream(total_out, dst=0)
+        try:
+            ps = sharding.PeerStream(total_out, dst=0)  # collective; fails on every rank or on none
+        except RuntimeError as e:
+            ps = None
+            fused = {"unavailable": str(e)}
+    if ps is not None:
         my_out = ps.stripe_ptr(r0 * (n // 4) * block_bytes)
 
         def step_peer(i):

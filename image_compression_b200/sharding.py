@@ -74,9 +74,19 @@ class PeerStream:
         dev = torch.device("cuda", torch.cuda.current_device())
         wire = handle.to(dev)
         dist.broadcast(wire, src=dst, group=group)
+        error = None
         if not self.owner:
             raw = C.create_string_buffer(wire.cpu().numpy().tobytes(), 64)
-            self._check(self._lib.icb_ipc_open(raw, C.byref(self._base)))
+            try:
+                self._check(self._lib.icb_ipc_open(raw, C.byref(self._base)))
+            except Exception as e:  # e.g. no peer access between the two GPUs
+                error = e
+        # every rank learns whether every mapping succeeded, so that nobody is left waiting in a later collective
+        ok = torch.tensor([0 if error else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError("PeerStream: mapping rank %d's buffer failed on at least one rank%s" % (dst, (": %s" % error) if error else ""))
 
     def stripe_ptr(self, byte_offset):
         assert 0 <= byte_offset <= self.total_bytes
@@ -96,11 +106,13 @@ class PeerStream:
         return torch.as_tensor(_Span(), device="cuda").clone()
 
     def close(self):
-        if self._base.value:
-            if self.owner:
-                dist.barrier(group=self.group)  # nobody still has it mapped
-                self._check(self._lib.icb_device_free(self._base))
-            else:
-                self._check(self._lib.icb_ipc_close(self._base))
-                dist.barrier(group=self.group)
-            self._base = C.c_void_p()
+        """Collective: every rank unmaps, then the owner frees (nobody may still have the buffer mapped)."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        if not self.owner and self._base.value:
+            self._check(self._lib.icb_ipc_close(self._base))
+        dist.barrier(group=self.group)
+        if self.owner and self._base.value:
+            self._check(self._lib.icb_device_free(self._base))
+        self._base = C.c_void_p()
