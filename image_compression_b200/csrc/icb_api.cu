@@ -47,6 +47,30 @@ int fail(int status, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(ICB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
   } while (0)
 
+// ---- stream-ordered scratch memory -------------------------------------------------------------------------
+// Scratch the library allocates on a caller's stream (PVRTC without a caller-provided buffer) comes from the library's
+// own memory pool, which keeps freed blocks instead of returning them to the driver at the next synchronisation: the
+// default pool's release threshold of zero turns every call after a sync into a fresh device allocation.
+int scratch_pool(cudaMemPool_t *out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  ICB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    ICB_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+    uint64_t keep = ~0ull;
+    ICB_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  *out = pools[dev];
+  return ICB_OK;
+}
+
 // ---- per-device facts ------------------------------------------------------------------------------------
 
 struct DeviceInfo {
@@ -636,7 +660,11 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   DeviceInfo info;
   if (int s = device_info(&info)) return s;
   void *scratch = d_scratch;
-  if (!scratch) ICB_CUDA(cudaMallocAsync(&scratch, icb_pvrtc2_scratch_size(h, w), st));
+  if (!scratch) {
+    cudaMemPool_t pool;
+    if (int s = scratch_pool(&pool)) return s;
+    ICB_CUDA(cudaMallocFromPoolAsync(&scratch, icb_pvrtc2_scratch_size(h, w), pool, st));
+  }
   icb::PvrtcParams p;
   const uint32_t lw = w / 8, lh = h / 4, nblocks = lw * lh;
   p.src = static_cast<const uint32_t *>(d_src);

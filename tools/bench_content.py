@@ -1,0 +1,37 @@
+"""Kernel time of every encoder on different image content (random, smooth, gradients, dark, checkerboard, constant,
+two-colour): the DXT index search has a warp-uniform fast path and a general path, constant blocks take a table path,
+so speed may depend on the data; output is bit-exact either way.  Run on the GPU box: python tools/bench_content.py"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import imagegen  # noqa: E402
+import image_compression_b200 as icb  # noqa: E402
+
+n = 4096
+cases = (("dxt1_rgba8", icb.CODEC_DXT1, icb.RGBA, 4), ("dxt1_rgb8", icb.CODEC_DXT1, icb.RGB, 3), ("dxt5_rgba8", icb.CODEC_DXT5, icb.RGBA, 4),
+         ("etc1_rgb8", icb.CODEC_ETC1, icb.RGB, 3), ("pvrtc2_rgba8", icb.CODEC_PVRTC2, icb.RGBA, 4))
+for kind in ("random", "smooth_noise", "gradient", "dark", "checker", "constant", "two_colour", "alpha_extremes"):
+    row = {"content": kind}
+    for name, codec, fmt, nc in cases:
+        img = np.tile(imagegen.make(kind, 1024, 1024, nc, seed=3), (4, 4, 1))
+        d = torch.from_numpy(np.ascontiguousarray(img).ravel()).cuda()
+        out = torch.empty(icb.compressed_size(codec, n, n), dtype=torch.uint8, device="cuda")
+        run = (lambda: icb.pvrtc_encode_device(d, n, n, out=out)) if codec == icb.CODEC_PVRTC2 else (lambda: icb.encode_device(codec, fmt, d, n, n, out=out))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        row[name + "_us"] = round(e0.elapsed_time(e1) * 100, 1)
+    print(json.dumps(row))
