@@ -536,7 +536,33 @@ struct HostPipe {  // per host thread, per device: streams, events and grow-only
   // Deliberately no destructor work: at process exit the CUDA context may already be gone.
 };
 
-thread_local HostPipe t_pipe;
+thread_local HostPipe t_pipes[64];  // one per device ordinal this host thread has used
+
+// The calling thread's pipe for the CURRENT device, prepared.
+int current_pipe(HostPipe **out) {
+  int dev = 0;
+  ICB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
+  if (int s = t_pipes[dev].prepare()) return s;
+  *out = &t_pipes[dev];
+  return ICB_OK;
+}
+
+// Devices icb_compress_host spreads one image over: the current device only, unless ICB_HOST_DEVICES=N|all asks for
+// more -- then the current device and the next N-1 ordinals (modulo the device count).
+int host_devices(int *devs, int *count) {
+  int cur = 0, total = 0;
+  ICB_CUDA(cudaGetDevice(&cur));
+  ICB_CUDA(cudaGetDeviceCount(&total));
+  int want = 1;
+  if (const char *e = getenv("ICB_HOST_DEVICES")) want = strcmp(e, "all") == 0 ? total : atoi(e);
+  if (want < 1) want = 1;
+  if (want > total) want = total;
+  if (want > 16) want = 16;
+  for (int i = 0; i < want; ++i) devs[i] = (cur + i) % total;
+  *count = want;
+  return ICB_OK;
+}
 
 // Contiguous host -> device copy on `stream`; pageable sources go through the pinned ring in 16 MiB pieces so that the
 // parallel host copy of one piece overlaps the DMA of the previous one.
@@ -766,8 +792,9 @@ int icb_decompress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t 
   const size_t need_in = static_cast<size_t>((h + 3) / 4) * block_cols * block_bytes, need_out = static_cast<size_t>(h) * w * ncomp;
   if (blocks_size < need_in) return fail(ICB_ERR_SIZE, "block stream is %zu bytes, need %zu", blocks_size, need_in);
   if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
-  if (int s = t_pipe.prepare()) return s;
-  HostPipe &pipe = t_pipe;
+  HostPipe *pipe_ptr = nullptr;
+  if (int s = current_pipe(&pipe_ptr)) return s;
+  HostPipe &pipe = *pipe_ptr;
   if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_in)) return s;     // blocks live in the "dst" buffer
   if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_out)) return s;    // pixels in the "src" buffer
   if (int s = upload_contiguous(pipe, pipe.d_dst, blocks, need_in, pipe.compute)) return s;
@@ -939,8 +966,9 @@ int icb_blockop_host(int op, int codec, int strategy, const uint32_t *args, cons
   }
   if (op != ICB_OP_SOLID && src_size < need_in) return fail(ICB_ERR_SIZE, "source is %zu bytes, need %zu", src_size, need_in);
   if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
-  if (int s = t_pipe.prepare()) return s;
-  HostPipe &pipe = t_pipe;
+  HostPipe *pipe_ptr = nullptr;
+  if (int s = current_pipe(&pipe_ptr)) return s;
+  HostPipe &pipe = *pipe_ptr;
   if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_in > 16 ? need_in : 16)) return s;
   if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_out > 16 ? need_out : 16)) return s;
   cudaStream_t st = pipe.compute;
@@ -1050,8 +1078,9 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   if (codec == ICB_CODEC_ETC1 && format != ICB_RGB) return fail(ICB_ERR_INVALID, "ETC1 supports kRGB only");
   if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_PVRTC2) return fail(ICB_ERR_INVALID, "unknown codec %d", codec);
 
-  if (int s = t_pipe.prepare()) return s;
-  HostPipe &pipe = t_pipe;
+  HostPipe *pipe_ptr = nullptr;
+  if (int s = current_pipe(&pipe_ptr)) return s;
+  HostPipe &pipe = *pipe_ptr;
 
   if (codec == ICB_CODEC_PVRTC2) {
     if ((w & (w - 1)) || (h & (h - 1)) || w != h) return fail(ICB_ERR_UNSUPPORTED, "PVRTC needs a square power-of-two image");
@@ -1076,9 +1105,6 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   const size_t row_bytes = static_cast<size_t>(w) * ncomp;
   const bool keep_pitch = host_pitch % 16 == 0;
   const size_t dev_pitch = keep_pitch ? host_pitch : (row_bytes + 15) / 16 * 16;
-  if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, dev_pitch * h)) return s;
-  if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need)) return s;
-
   const uint32_t grid_rows = (coded_h + 3) / 4, grid_cols = (coded_w + 3) / 4;
   const size_t block_bytes = codec == ICB_CODEC_DXT5 ? 16 : 8;
   // Chunks of whole block rows, about 16 MiB of source each, at most kMaxChunks.
@@ -1088,76 +1114,119 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   if (chunks > grid_rows) chunks = grid_rows;
   // whole tile rows per chunk (4 block rows), so that only the last chunk can leave rows to the generic kernel
   const uint32_t rows_per_chunk = ((grid_rows + chunks - 1) / chunks + 3) / 4 * 4;
-  const uint8_t *hsrc = static_cast<const uint8_t *>(src);
-  uint8_t *hdst = static_cast<uint8_t *>(dst);
-  // Pageable caller memory is staged through pinned rings by the copy pool (both directions independently).
-  const bool stage_src = is_pageable(src), stage_dst = is_pageable(dst);
-  const size_t chunk_out_bytes = static_cast<size_t>(rows_per_chunk) * grid_cols * block_bytes;
-  if (stage_src)
-    if (int s = HostPipe::grow_pinned(pipe.stage_in, &pipe.stage_in_cap, static_cast<size_t>(rows_per_chunk) * 4 * dev_pitch)) return s;
-  if (stage_dst)
-    if (int s = HostPipe::grow_pinned(pipe.stage_out, &pipe.stage_out_cap, chunk_out_bytes)) return s;
-  // Copies chunk c's blocks from its staging buffer to the caller's memory once its D2H has landed.
-  auto drain = [&](uint32_t c) -> int {
-    const uint32_t c_r0 = c * rows_per_chunk, c_r1 = c_r0 + rows_per_chunk < grid_rows ? c_r0 + rows_per_chunk : grid_rows;
-    const size_t bytes = static_cast<size_t>(c_r1 - c_r0) * grid_cols * block_bytes;
-    ICB_CUDA(cudaEventSynchronize(pipe.out_done[c]));
-    CopyPool::get().copy_rows(hdst + static_cast<size_t>(c_r0) * grid_cols * block_bytes, bytes,
-                              static_cast<const uint8_t *>(pipe.stage_out[c % HostPipe::kStageBufs]), bytes, bytes, 1);
-    return ICB_OK;
-  };
-  uint32_t chunk = 0;
-  for (uint32_t r0 = 0; r0 < grid_rows; r0 += rows_per_chunk, ++chunk) {
-    const uint32_t r1 = r0 + rows_per_chunk < grid_rows ? r0 + rows_per_chunk : grid_rows;
-    // Source rows this chunk adds: pixel rows [4*r0, min(4*r1, h)).  Later chunks only ever clamp to row h-1,
-    // which the chunk containing it has already uploaded (chunks run in order on the compute stream).
-    const uint32_t y0 = 4 * r0 < h ? 4 * r0 : h, y1 = 4 * r1 < h ? 4 * r1 : h;
-    if (y1 > y0 && stage_src) {
-      const int b = static_cast<int>(chunk % HostPipe::kStageBufs);
-      if (chunk >= HostPipe::kStageBufs) ICB_CUDA(cudaEventSynchronize(pipe.stage_in_free[b]));  // its last DMA has read it
-      uint8_t *stage = static_cast<uint8_t *>(pipe.stage_in[b]);
-      CopyPool::get().copy_rows(stage, dev_pitch, hsrc + y0 * host_pitch, host_pitch, row_bytes, y1 - y0);
-      ICB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pipe.d_src) + y0 * dev_pitch, stage,
-                               static_cast<size_t>(y1 - y0 - 1) * dev_pitch + row_bytes, cudaMemcpyHostToDevice, pipe.copy_in));
-      ICB_CUDA(cudaEventRecord(pipe.stage_in_free[b], pipe.copy_in));
-    } else if (y1 > y0) {
-      if (keep_pitch) {
-        const size_t bytes = (y1 == h) ? (static_cast<size_t>(y1 - y0 - 1) * host_pitch + row_bytes)
-                                       : static_cast<size_t>(y1 - y0) * host_pitch;
-        ICB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pipe.d_src) + y0 * dev_pitch, hsrc + y0 * host_pitch, bytes,
-                                 cudaMemcpyHostToDevice, pipe.copy_in));
-      } else {
-        ICB_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t *>(pipe.d_src) + y0 * dev_pitch, dev_pitch, hsrc + y0 * host_pitch,
-                                   host_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, pipe.copy_in));
-      }
-    }
-    ICB_CUDA(cudaEventRecord(pipe.in_done[chunk], pipe.copy_in));
-    ICB_CUDA(cudaStreamWaitEvent(pipe.compute, pipe.in_done[chunk], 0));
-    uint8_t *d_out = static_cast<uint8_t *>(pipe.d_dst) + static_cast<size_t>(r0) * grid_cols * block_bytes;
-    if (int s = encode4x4(codec, ncomp, pipe.d_src, h, w, dev_pitch, coded_h, coded_w, swap_rb, strategy, r0, r1, d_out,
-                          pipe.compute))
+  const uint32_t num_chunks = (grid_rows + rows_per_chunk - 1) / rows_per_chunk;
+
+  // Devices: chunk c goes to device c % ndev (ICB_HOST_DEVICES, default one), each over its own PCIe link; every
+  // device writes its chunks' blocks straight to their place in the caller's buffer, so nothing is gathered.  Chunks
+  // below the image (CompressAndPad with coded_h > h) replicate row h-1, which only the device that uploaded it has:
+  // that case stays on one device.
+  int devs[16], ndev = 1, home = 0;
+  ICB_CUDA(cudaGetDevice(&home));
+  if (int s = host_devices(devs, &ndev)) return s;
+  if (static_cast<uint32_t>(ndev) > num_chunks) ndev = static_cast<int>(num_chunks);
+  if (coded_h > (h + 3) / 4 * 4) ndev = 1;
+  HostPipe *pipes[16];
+  pipes[0] = &pipe;
+  for (int k = 1; k < ndev; ++k) {
+    ICB_CUDA(cudaSetDevice(devs[k]));
+    const int s = current_pipe(&pipes[k]);
+    if (s != ICB_OK) {
+      cudaSetDevice(home);
       return s;
-    ICB_CUDA(cudaEventRecord(pipe.enc_done[chunk], pipe.compute));
-    ICB_CUDA(cudaStreamWaitEvent(pipe.copy_out, pipe.enc_done[chunk], 0));
-    const size_t out_off = static_cast<size_t>(r0) * grid_cols * block_bytes;
-    if (stage_dst) {
-      // buffer chunk % 3 was drained two iterations ago (below), so it is free again
-      ICB_CUDA(cudaMemcpyAsync(pipe.stage_out[chunk % HostPipe::kStageBufs], d_out,
-                               static_cast<size_t>(r1 - r0) * grid_cols * block_bytes, cudaMemcpyDeviceToHost, pipe.copy_out));
-      ICB_CUDA(cudaEventRecord(pipe.out_done[chunk], pipe.copy_out));
-      if (chunk >= 2)
-        if (int s = drain(chunk - 2)) return s;
-    } else {
-      ICB_CUDA(cudaMemcpyAsync(hdst + out_off, d_out, static_cast<size_t>(r1 - r0) * grid_cols * block_bytes,
-                               cudaMemcpyDeviceToHost, pipe.copy_out));
     }
   }
-  if (stage_dst)
-    for (uint32_t c = chunk >= 2 ? chunk - 2 : 0; c < chunk; ++c)
-      if (int s = drain(c)) return s;
-  ICB_CUDA(cudaStreamSynchronize(pipe.copy_out));
-  ICB_CUDA(cudaStreamSynchronize(pipe.compute));
-  return ICB_OK;
+  // From here on every exit path has to put the caller's device back.
+  auto run = [&]() -> int {
+    const uint8_t *hsrc = static_cast<const uint8_t *>(src);
+    uint8_t *hdst = static_cast<uint8_t *>(dst);
+    // Pageable caller memory is staged through pinned rings by the copy pool (both directions independently).
+    const bool stage_src = is_pageable(src), stage_dst = is_pageable(dst);
+    const size_t chunk_out_bytes = static_cast<size_t>(rows_per_chunk) * grid_cols * block_bytes;
+    for (int k = 0; k < ndev; ++k) {
+      ICB_CUDA(cudaSetDevice(devs[k]));
+      HostPipe &pk = *pipes[k];
+      if (int s = HostPipe::grow(&pk.d_src, &pk.src_cap, dev_pitch * h)) return s;
+      if (int s = HostPipe::grow(&pk.d_dst, &pk.dst_cap, need)) return s;
+      if (stage_src)
+        if (int s = HostPipe::grow_pinned(pk.stage_in, &pk.stage_in_cap, static_cast<size_t>(rows_per_chunk) * 4 * dev_pitch)) return s;
+      if (stage_dst)
+        if (int s = HostPipe::grow_pinned(pk.stage_out, &pk.stage_out_cap, chunk_out_bytes)) return s;
+    }
+    // Copies chunk c's blocks from its staging buffer to the caller's memory once its D2H has landed.  Chunk c is
+    // the (c / ndev)-th chunk of device c % ndev; rings and events are indexed by that local number.
+    auto drain = [&](uint32_t c) -> int {
+      HostPipe &pk = *pipes[c % ndev];
+      const uint32_t local = c / ndev;
+      const uint32_t c_r0 = c * rows_per_chunk, c_r1 = c_r0 + rows_per_chunk < grid_rows ? c_r0 + rows_per_chunk : grid_rows;
+      const size_t bytes = static_cast<size_t>(c_r1 - c_r0) * grid_cols * block_bytes;
+      ICB_CUDA(cudaEventSynchronize(pk.out_done[local]));
+      CopyPool::get().copy_rows(hdst + static_cast<size_t>(c_r0) * grid_cols * block_bytes, bytes,
+                                static_cast<const uint8_t *>(pk.stage_out[local % HostPipe::kStageBufs]), bytes, bytes, 1);
+      return ICB_OK;
+    };
+    const uint32_t lag = 2u * static_cast<uint32_t>(ndev);  // a chunk is drained two of its own device's chunks later
+    uint32_t chunk = 0;
+    for (uint32_t r0 = 0; r0 < grid_rows; r0 += rows_per_chunk, ++chunk) {
+      const uint32_t r1 = r0 + rows_per_chunk < grid_rows ? r0 + rows_per_chunk : grid_rows;
+      HostPipe &pk = *pipes[chunk % ndev];
+      const uint32_t local = chunk / ndev;
+      if (ndev > 1) ICB_CUDA(cudaSetDevice(devs[chunk % ndev]));
+      // Source rows this chunk adds: pixel rows [4*r0, min(4*r1, h)).  Later chunks only ever clamp to row h-1,
+      // which the chunk containing it has already uploaded (chunks run in order on the compute stream).
+      const uint32_t y0 = 4 * r0 < h ? 4 * r0 : h, y1 = 4 * r1 < h ? 4 * r1 : h;
+      if (y1 > y0 && stage_src) {
+        const int b = static_cast<int>(local % HostPipe::kStageBufs);
+        if (local >= HostPipe::kStageBufs) ICB_CUDA(cudaEventSynchronize(pk.stage_in_free[b]));  // its last DMA has read it
+        uint8_t *stage = static_cast<uint8_t *>(pk.stage_in[b]);
+        CopyPool::get().copy_rows(stage, dev_pitch, hsrc + y0 * host_pitch, host_pitch, row_bytes, y1 - y0);
+        ICB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pk.d_src) + y0 * dev_pitch, stage,
+                                 static_cast<size_t>(y1 - y0 - 1) * dev_pitch + row_bytes, cudaMemcpyHostToDevice, pk.copy_in));
+        ICB_CUDA(cudaEventRecord(pk.stage_in_free[b], pk.copy_in));
+      } else if (y1 > y0) {
+        if (keep_pitch) {
+          const size_t bytes = (y1 == h) ? (static_cast<size_t>(y1 - y0 - 1) * host_pitch + row_bytes)
+                                         : static_cast<size_t>(y1 - y0) * host_pitch;
+          ICB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pk.d_src) + y0 * dev_pitch, hsrc + y0 * host_pitch, bytes,
+                                   cudaMemcpyHostToDevice, pk.copy_in));
+        } else {
+          ICB_CUDA(cudaMemcpy2DAsync(static_cast<uint8_t *>(pk.d_src) + y0 * dev_pitch, dev_pitch, hsrc + y0 * host_pitch,
+                                     host_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, pk.copy_in));
+        }
+      }
+      ICB_CUDA(cudaEventRecord(pk.in_done[local], pk.copy_in));
+      ICB_CUDA(cudaStreamWaitEvent(pk.compute, pk.in_done[local], 0));
+      uint8_t *d_out = static_cast<uint8_t *>(pk.d_dst) + static_cast<size_t>(r0) * grid_cols * block_bytes;
+      if (int s = encode4x4(codec, ncomp, pk.d_src, h, w, dev_pitch, coded_h, coded_w, swap_rb, strategy, r0, r1, d_out,
+                            pk.compute))
+        return s;
+      ICB_CUDA(cudaEventRecord(pk.enc_done[local], pk.compute));
+      ICB_CUDA(cudaStreamWaitEvent(pk.copy_out, pk.enc_done[local], 0));
+      const size_t out_off = static_cast<size_t>(r0) * grid_cols * block_bytes;
+      if (stage_dst) {
+        // this device's buffer local % 3 was drained two of its chunks ago (below), so it is free again
+        ICB_CUDA(cudaMemcpyAsync(pk.stage_out[local % HostPipe::kStageBufs], d_out,
+                                 static_cast<size_t>(r1 - r0) * grid_cols * block_bytes, cudaMemcpyDeviceToHost, pk.copy_out));
+        ICB_CUDA(cudaEventRecord(pk.out_done[local], pk.copy_out));
+        if (chunk >= lag)
+          if (int s = drain(chunk - lag)) return s;
+      } else {
+        ICB_CUDA(cudaMemcpyAsync(hdst + out_off, d_out, static_cast<size_t>(r1 - r0) * grid_cols * block_bytes,
+                                 cudaMemcpyDeviceToHost, pk.copy_out));
+      }
+    }
+    if (stage_dst)
+      for (uint32_t c = chunk >= lag ? chunk - lag : 0; c < chunk; ++c)
+        if (int s = drain(c)) return s;
+    for (int k = 0; k < ndev; ++k) {
+      if (ndev > 1) ICB_CUDA(cudaSetDevice(devs[k]));
+      ICB_CUDA(cudaStreamSynchronize(pipes[k]->copy_out));
+      ICB_CUDA(cudaStreamSynchronize(pipes[k]->compute));
+    }
+    return ICB_OK;
+  };
+  const int status = run();
+  if (ndev > 1) cudaSetDevice(home);
+  return status;
 }
 
 }  // extern "C"

@@ -127,7 +127,10 @@ ICB_API int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pix
  * dst_size must equal the required size exactly (ICB_ERR_SIZE otherwise), mirroring SetUpCompressedImage
  * (internal/compressor4x4_helper.cc:22-43).  Blocking.  Pinned src/dst (icb_host_alloc) are DMA'd directly; ordinary
  * pageable memory is staged through pinned buffers by a small pool of copy threads (ICB_STAGING_THREADS=n overrides
- * their number, 0 leaves pageable copies to the CUDA driver).
+ * their number, 0 leaves pageable copies to the CUDA driver).  ICB_HOST_DEVICES=N|all spreads one call over N GPUs of
+ * the box (the current device and the next ordinals): chunk c is uploaded to, encoded on and downloaded from device
+ * c mod N, each over its own PCIe link, and every device writes its blocks to their place in dst -- no gather.  The
+ * caller's current device is unchanged on return.
  */
 ICB_API int icb_compress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t padded_height,
                       uint32_t padded_width, uint32_t padding_bytes_per_row, int etc_strategy, const void *src,

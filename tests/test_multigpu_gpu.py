@@ -86,3 +86,46 @@ def test_two_gpu_stripes_nccl_gather_and_peer_stores_match_oracle():
         p.join(300)
         assert p.exitcode == 0
     assert results.get(timeout=5) == 1
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_host_path_spread_over_two_gpus(icb):
+    """ICB_HOST_DEVICES=2: one Compress() call uploads alternate chunks to two GPUs, each over its own PCIe link, and
+    every GPU writes its blocks to their place in the caller's buffer.  Same bytes as the oracle, from pageable and
+    from pinned memory, for sizes with several chunks, a ragged bottom edge, and a padded (CompressAndPad) grid."""
+    import ctypes as C
+    import os
+    old = os.environ.get("ICB_HOST_DEVICES")
+    os.environ["ICB_HOST_DEVICES"] = "2"
+    try:
+        L = icb.lib()
+        for codec, fmt, nc, h, w in ((icb.CODEC_DXT1, icb.RGBA, 4, 4096, 4096), (icb.CODEC_DXT5, icb.RGBA, 4, 2050, 4096),
+                                     (icb.CODEC_DXT1, icb.RGB, 3, 3001, 2048), (icb.CODEC_ETC1, icb.RGB, 3, 512, 8192)):
+            img = ck.synthetic(h * w * nc, 9)
+            if codec == icb.CODEC_ETC1:
+                want = ck.oracle_etc1(ck.ETC_SMALLER_ERROR, img, h, w)
+            elif codec == icb.CODEC_DXT1 and nc == 4:
+                want = ck.oracle_dxt1_rgba(img, h, w)
+            else:
+                want = ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, img, h, w)
+            got = icb.compress_host(codec, fmt, img, h, w)
+            assert np.array_equal(got, want), ("pageable", codec, h, w)
+            pin_in, pin_out = L.icb_host_alloc(img.size), L.icb_host_alloc(want.size)
+            a = np.ctypeslib.as_array(C.cast(pin_in, C.POINTER(C.c_uint8)), shape=(img.size,))
+            b = np.ctypeslib.as_array(C.cast(pin_out, C.POINTER(C.c_uint8)), shape=(want.size,))
+            a[:] = img
+            icb.compress_host(codec, fmt, a, h, w, out=b)
+            assert np.array_equal(b, want), ("pinned", codec, h, w)
+            L.icb_host_free(pin_in)
+            L.icb_host_free(pin_out)
+        # CompressAndPad below the image stays on one device (row h-1 replication) and must still be right
+        h, w = 1030, 4096
+        img = ck.synthetic(h * w * 4, 10)
+        got = icb.compress_host(icb.CODEC_DXT5, icb.RGBA, img, h, w, padded=(2048, 4096))
+        assert np.array_equal(got, ck.oracle_dxt(ck.RGBA, img, h, w, coded_h=2048, coded_w=4096))
+        assert torch.cuda.current_device() == 0
+    finally:
+        if old is None:
+            del os.environ["ICB_HOST_DEVICES"]
+        else:
+            os.environ["ICB_HOST_DEVICES"] = old

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """End-to-end icb_compress_host from PINNED vs ordinary PAGEABLE host memory (what a C++ caller that malloc'ed its image
-hands to Compress()).  DXT1 8192x8192 RGBA8.  Prints one JSON line per case."""
+hands to Compress()).  DXT1 8192x8192 RGBA8.  Prints one JSON line per case.  ICB_HOST_DEVICES=N spreads the call
+over N GPUs of the box (each chunk over its own PCIe link)."""
 import ctypes as C
 import json
 import os
@@ -32,5 +33,5 @@ for name, src, dst in (("pinned", pin_in, pin_out), ("pageable", pageable_in, pa
     for _ in range(reps):
         icb.compress_host(icb.CODEC_DXT1, icb.RGBA, src, n, n, out=dst)
     ms = (time.perf_counter() - t0) * 1e3 / reps
-    print(json.dumps({"host_memory": name, "ms": ms, "mpix_s": n * n / ms / 1e3, "h2d_gb_s": in_bytes / ms / 1e6,
+    print(json.dumps({"host_memory": name, "host_devices": os.environ.get("ICB_HOST_DEVICES", "1"), "ms": ms, "mpix_s": n * n / ms / 1e3, "h2d_gb_s": in_bytes / ms / 1e6,
                       "same_output": bool(np.array_equal(dst, pin_out))}))
