@@ -5,7 +5,10 @@
 // block in raster order, window gather with clamp-to-edge replication as in Pixel4x4
 // (internal/pixel4x4.h:45-67, internal/pixel4x4.cc:24-59).
 //
-// Two drivers:
+// Three drivers:
+//   encode4x4_ring_kernel     same tiles, ring and consumers as encode4x4_tma_kernel but without a producer warp: the
+//                             consumer warps count themselves off a slot and the last one refills it (DXT5's default;
+//                             see the comment above that kernel for the measured trade-off).
 //   encode4x4_tma_kernel      the fast path, for every 64 x 4-block tile that lies entirely inside the image.
 //                             Persistent CTAs; one elected producer thread streams 2-D pixel tiles HBM -> shared
 //                             memory with TMA (cp.async.bulk.tensor) through a ring of mbarrier-guarded stages;
