@@ -25,7 +25,7 @@ namespace icb {
 
 // Table of optimal endpoint pairs for a constant channel value; regenerated, not copied
 // (tools/gen_dxt_const_table.py re-runs the published search and checks it against the reference).
-__device__ const uint8_t g_dxt_const_endpoints[256][8] = {
+__device__ __align__(8) const uint8_t g_dxt_const_endpoints[256][8] = {
 #include "dxt_const_table.inc"
 };
 
@@ -61,11 +61,14 @@ __device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
   const uint32_t qr = quant_round(tr, 31u), qg = quant_round(tg, 63u), qb = quant_round(tb, 31u);
   uint32_t c0 = (qr << 11) | (qg << 5) | qb, c1 = c0, which = 0;
   uint32_t best = lum_of_diff_sq(tr, tg, tb, expand5(qr), expand6(qg), expand5(qb));
-  const uint8_t *row_r = g_dxt_const_endpoints[tr];
-  const uint8_t *row_g = g_dxt_const_endpoints[tg];
-  const uint8_t *row_b = g_dxt_const_endpoints[tb];
-  if (!always4) {  // 1/2 blend of a three-colour block (DXT1 only)
-    const uint32_t e0r = row_r[2], e1r = row_r[3], e0g = row_g[6], e1g = row_g[7], e0b = row_b[2], e1b = row_b[3];
+  // one 8-byte load per channel row (the table rows are 8-byte aligned), bytes picked out of the two words
+  const uint2 row_r = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tr]);
+  const uint2 row_g = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tg]);
+  const uint2 row_b = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tb]);
+  auto byte_of = [](uint32_t word, int k) { return (word >> (8 * k)) & 255u; };
+  if (!always4) {  // 1/2 blend of a three-colour block (DXT1 only): columns 2,3 (r, b) and 6,7 (g)
+    const uint32_t e0r = byte_of(row_r.x, 2), e1r = byte_of(row_r.x, 3), e0g = byte_of(row_g.y, 2), e1g = byte_of(row_g.y, 3),
+                   e0b = byte_of(row_b.x, 2), e1b = byte_of(row_b.x, 3);
     const uint32_t err = lum_of_diff_sq(tr, tg, tb, (expand5(e0r) + expand5(e1r)) >> 1,
                                         (expand6(e0g) + expand6(e1g)) >> 1, (expand5(e0b) + expand5(e1b)) >> 1);
     if (err < best) {
@@ -76,8 +79,9 @@ __device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
       best = err;
     }
   }
-  {  // 1/3 blend of a four-colour block
-    const uint32_t e0r = row_r[0], e1r = row_r[1], e0g = row_g[4], e1g = row_g[5], e0b = row_b[0], e1b = row_b[1];
+  {  // 1/3 blend of a four-colour block: columns 0,1 (r, b) and 4,5 (g)
+    const uint32_t e0r = byte_of(row_r.x, 0), e1r = byte_of(row_r.x, 1), e0g = byte_of(row_g.y, 0), e1g = byte_of(row_g.y, 1),
+                   e0b = byte_of(row_b.x, 0), e1b = byte_of(row_b.x, 1);
     const uint32_t err = lum_of_diff_sq(tr, tg, tb, div3_small(2u * expand5(e0r) + expand5(e1r)),
                                         div3_small(2u * expand6(e0g) + expand6(e1g)),
                                         div3_small(2u * expand5(e0b) + expand5(e1b)));
@@ -184,11 +188,11 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
   // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
   // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
-  // midpoints have to be computed.  (Constant blocks vote too; whatever they say only selects which path the
-  // other lanes take, and both paths are exact.)
+  // midpoints have to be computed.  (Constant blocks vote yes: they take neither path, and a no would send the
+  // warp's other blocks down the slower general path -- flat image regions would pay for it.)
   const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
   const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
-  const bool all_regular = __all_sync(kFullWarp ? 0xffffffffu : __activemask(), rising || falling);
+  const bool all_regular = __all_sync(kFullWarp ? 0xffffffffu : __activemask(), constant || rising || falling);
   uint32_t bits;
   if (constant) {
     // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
