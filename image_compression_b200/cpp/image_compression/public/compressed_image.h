@@ -42,41 +42,17 @@ class CompressedImage {
     uint32 padding_bytes_per_row;  // of the source rows
   };
 
-  CompressedImage() : metadata_(kRGB, "", 0, 0, 0, 0, 0), data_size_(0), data_(NULL), owns_data_(true) {}
-
-  CompressedImage(size_t data_size, uint8 *external_data)
-      : metadata_(kRGB, "", 0, 0, 0, 0, 0), data_size_(data_size), data_(external_data), owns_data_(false) {
-    DCHECK(external_data);
-  }
-
-  ~CompressedImage() {
-    if (owns_data_) delete[] data_;
-  }
+  // Empty image that will own whatever a compressor allocates for it.
+  CompressedImage();
+  // Image over caller-owned storage of exactly the size the compressor will need.
+  CompressedImage(size_t data_size, uint8 *external_data);
+  ~CompressedImage() { ReleaseOwned(); }
 
   // Deep copy; this instance owns the copy whatever `from` did.
-  void Duplicate(const CompressedImage &from) {
-    if (&from == this && owns_data_) return;
-    const uint8 *bytes = from.data_;
-    const size_t size = from.data_size_;
-    DCHECK(bytes);
-    uint8 *fresh = new uint8[size];
-    std::memcpy(fresh, bytes, size);
-    const Metadata meta = from.metadata_;
-    if (owns_data_) delete[] data_;
-    metadata_ = meta;
-    data_size_ = size;
-    data_ = fresh;
-    owns_data_ = true;
-  }
-
-  void CreateOwnedData(const Metadata &metadata, size_t data_size) {
-    if (owns_data_) delete[] data_;
-    metadata_ = metadata;
-    data_size_ = data_size;
-    data_ = new uint8[data_size];
-    owns_data_ = true;
-  }
-
+  void Duplicate(const CompressedImage &from);
+  // Replaces the contents by a fresh, owned, uninitialised buffer of data_size bytes.
+  void CreateOwnedData(const Metadata &metadata, size_t data_size) { Adopt(metadata, data_size, new uint8[data_size]); }
+  // Only for images over external storage: the bytes are the caller's, the description is ours.
   void SetMetadata(const Metadata &metadata) {
     DCHECK(!owns_data_);
     metadata_ = metadata;
@@ -89,26 +65,47 @@ class CompressedImage {
   uint8 *GetMutableData() { return data_; }
 
  private:
+  void ReleaseOwned() {
+    if (owns_data_) delete[] data_;
+  }
+  void Adopt(const Metadata &metadata, size_t data_size, uint8 *owned_bytes) {
+    ReleaseOwned();
+    metadata_ = metadata;
+    data_size_ = data_size;
+    data_ = owned_bytes;
+    owns_data_ = true;
+  }
+
   Metadata metadata_;
   size_t data_size_;
   uint8 *data_;
   bool owns_data_;
 
-  CompressedImage(const CompressedImage &);
+  CompressedImage(const CompressedImage &);  // not copyable: use Duplicate
   void operator=(const CompressedImage &);
 };
 
+inline CompressedImage::CompressedImage() : metadata_(kRGB, "", 0, 0, 0, 0, 0), data_size_(0), data_(NULL), owns_data_(true) {}
+
+inline CompressedImage::CompressedImage(size_t data_size, uint8 *external_data)
+    : metadata_(kRGB, "", 0, 0, 0, 0, 0), data_size_(data_size), data_(external_data), owns_data_(false) {
+  DCHECK(external_data);
+}
+
+inline void CompressedImage::Duplicate(const CompressedImage &from) {
+  if (&from == this && owns_data_) return;  // already an owned copy of itself
+  DCHECK(from.data_);
+  // copy first, release afterwards: `from` may be this very image over external storage
+  uint8 *fresh = new uint8[from.data_size_];
+  std::memcpy(fresh, from.data_, from.data_size_);
+  const Metadata meta = from.metadata_;
+  Adopt(meta, from.data_size_, fresh);
+}
+
+// 3 for kRGB / kBGR, 4 for kRGBA / kBGRA, 0 for anything else.
 inline int GetNumFormatComponents(CompressedImage::Format format) {
-  switch (format) {
-    case CompressedImage::kRGB:
-    case CompressedImage::kBGR:
-      return 3;
-    case CompressedImage::kRGBA:
-    case CompressedImage::kBGRA:
-      return 4;
-    default:
-      return 0;
-  }
+  const unsigned f = static_cast<unsigned>(format);
+  return f < 2u ? 3 : (f < 4u ? 4 : 0);
 }
 
 inline bool NeedsRedAndBlueSwapped(CompressedImage::Format format) {

@@ -6,8 +6,8 @@
 // returning a CompressedImage through an out-parameter allocate into a default-constructed instance or fill
 // caller storage of exactly ComputeCompressedDataSize() bytes.  Errors are reported as `false`.
 //
-// In this build Compress() and CompressAndPad() run on the GPU (CUDA, sm_100a) through the C ABI in
-// include/icb200.h; see INTEGRATION.md.
+// In this build every method runs on the GPU (CUDA, sm_100a) through the C ABI in include/icb200.h; see
+// INTEGRATION.md.
 #ifndef IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_
 #define IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_
 
@@ -46,5 +46,25 @@ class Compressor {
 };
 
 }  // namespace image_codec_compression
+
+// The concrete compressors override the whole interface with identical signatures; they declare it through this
+// list instead of repeating it three times.
+#define IMAGE_CODEC_COMPRESSION_OVERRIDE_ALL()                                                                          \
+  bool SupportsFormat(CompressedImage::Format format) const override;                                                   \
+  bool IsValidCompressedImage(const CompressedImage &image) override;                                                   \
+  size_t ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) override;               \
+  bool Compress(CompressedImage::Format format, uint32 height, uint32 width, uint32 padding_bytes_per_row,              \
+                const uint8 *buffer, CompressedImage *image) override;                                                  \
+  bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,                \
+                      uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,                           \
+                      CompressedImage *padded_image) override;                                                          \
+  bool Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) override;                      \
+  bool Downsample(const CompressedImage &image, CompressedImage *downsampled_image) override;                           \
+  bool Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width, CompressedImage *padded_image)      \
+      override;                                                                                                         \
+  bool CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,                \
+                        CompressedImage *image) override;                                                               \
+  bool CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height, uint32 width,   \
+                    CompressedImage *subimage) override
 
 #endif  // IMAGE_COMPRESSION_PUBLIC_COMPRESSOR_H_

@@ -1,9 +1,9 @@
 // PvrtcCompressor: PVRTC1 2 bits-per-pixel RGBA; square power-of-two images only, no row
 // padding.  Only Compress() is provided (as in the reference); everything else returns false.
 //
-// Interface-compatible with the reference's image_compression/public/pvrtc_compressor.h.  Compress() and
-// CompressAndPad() run on the GPU (sm_100a CUDA kernels behind include/icb200.h) and produce byte-identical
-// blocks; see DESIGN.md for which of the remaining methods are implemented in this round.
+// Interface-compatible with the reference's image_compression/public/pvrtc_compressor.h.  Compress() runs on the GPU
+// (sm_100a CUDA kernels behind include/icb200.h) and produces byte-identical blocks; the other methods return false,
+// as the reference's do (internal/pvrtc_compressor.cc:669-704).
 #ifndef IMAGE_COMPRESSION_PUBLIC_PVRTC_COMPRESSOR_H_
 #define IMAGE_COMPRESSION_PUBLIC_PVRTC_COMPRESSOR_H_
 
@@ -20,24 +20,9 @@ namespace image_codec_compression {
 class PvrtcCompressor : public Compressor {
  public:
   PvrtcCompressor();
-  virtual ~PvrtcCompressor();
+  ~PvrtcCompressor() override;
 
-  virtual bool SupportsFormat(CompressedImage::Format format) const;
-  virtual bool IsValidCompressedImage(const CompressedImage &image);
-  virtual size_t ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width);
-  virtual bool Compress(CompressedImage::Format format, uint32 height, uint32 width, uint32 padding_bytes_per_row,
-                        const uint8 *buffer, CompressedImage *image);
-  virtual bool Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer);
-  virtual bool Downsample(const CompressedImage &image, CompressedImage *downsampled_image);
-  virtual bool Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width,
-                   CompressedImage *padded_image);
-  virtual bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,
-                              uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,
-                              CompressedImage *padded_image);
-  virtual bool CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,
-                                CompressedImage *image);
-  virtual bool CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height,
-                            uint32 width, CompressedImage *subimage);
+  IMAGE_CODEC_COMPRESSION_OVERRIDE_ALL();
 };
 
 }  // namespace image_codec_compression
