@@ -18,7 +18,7 @@
 #include <cstdint>
 #include <type_traits>
 
-#include "block4x4_kernels.cuh"
+#include "block4x4_generic.cuh"
 #include "decode4x4_kernels.cuh"
 
 namespace icb {

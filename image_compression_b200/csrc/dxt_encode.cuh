@@ -310,6 +310,14 @@ __device__ __align__(16) const uint8_t g_dxt5_alpha_table[512 * 16] = {
 constexpr int kDxt5AlphaTableBytes = 512 * 16;
 
 // Packed fp16 helpers on raw 32-bit registers (two lanes per instruction; HFMA2 / HADD2 in SASS).
+// ICB_HOST_EMULATION is defined only by tests/hostemu (the encoders compiled for the CPU to be checked against the
+// oracle without a GPU); the library itself is never built that way.
+#ifdef ICB_HOST_EMULATION
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return icb_emu::fma_f16x2(a, b, c, false); }
+__device__ __forceinline__ uint32_t h2_fma_sat(uint32_t a, uint32_t b, uint32_t c) { return icb_emu::fma_f16x2(a, b, c, true); }
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { return icb_emu::add_f16x2(a, b, false); }
+__device__ __forceinline__ uint32_t h2_add_sat(uint32_t a, uint32_t b) { return icb_emu::add_f16x2(a, b, true); }
+#else
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -330,6 +338,7 @@ __device__ __forceinline__ uint32_t h2_add_sat(uint32_t a, uint32_t b) {
   asm("add.rn.sat.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
+#endif
 
 // Encodes the DXT5 alpha half from the top byte of each pixel (ComputeBaseAlphas, dxtc_compressor.cc:374-424;
 // ComputeAlphaBits :427-479; bit layout Dxt5AlphaBits :103-158).  Returns the 8 output bytes as two words.

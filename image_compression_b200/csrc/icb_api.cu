@@ -691,28 +691,23 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
     if (int s = scratch_pool(&pool)) return s;
     ICB_CUDA(cudaMallocFromPoolAsync(&scratch, icb_pvrtc2_scratch_size(h, w), pool, st));
   }
-  icb::PvrtcParams p;
-  const uint32_t lw = w / 8, lh = h / 4, nblocks = lw * lh;
-  p.src = static_cast<const uint32_t *>(d_src);
-  p.first_pixel = static_cast<const uint32_t *>(d_first_pixel);
-  p.low_a = static_cast<uint32_t *>(scratch);
-  p.low_b = p.low_a + nblocks;
-  p.mod = reinterpret_cast<uint16_t *>(p.low_b + nblocks);
-  p.dst = static_cast<uint2 *>(d_dst);
-  p.width = w;
-  p.height = h;
-  p.src_row0 = src_row0;
-  if (whole) {
-    p.morph_row0 = 0; p.morph_rows = lh;
-    p.mod_row0 = 0; p.mod_rows = h;
-  } else {
-    p.morph_row0 = (r0 + lh - 1) & (lh - 1); p.morph_rows = r1 - r0 + 2;
-    p.mod_row0 = 4 * r0; p.mod_rows = 4 * (r1 - r0) + 1;
-  }
-  p.pack_row0 = r0; p.pack_rows = r1 - r0;
+  const icb::PvrtcParams p = icb::pvrtc_make_params(d_src, d_first_pixel, scratch, d_dst, h, w, src_row0, r0, r1, whole);
+  const uint32_t lw = w / 8;
   icb::pvrtc_morph_kernel<<<(lw * p.morph_rows + 127) / 128, 128, 0, st>>>(p);
-  icb::pvrtc_modulate_kernel<<<(lw * p.mod_rows + 255) / 256, 256, 0, st>>>(p);
-  icb::pvrtc_pack_kernel<<<(lw * p.pack_rows + 127) / 128, 128, 0, st>>>(p);
+  // Modulate and Pack: programmatic dependent launch (see pvrtc_kernels.cuh); ICB_NO_PDL=1 launches them plainly.
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("ICB_NO_PDL") ? 0 : 1;
+  cfg.gridDim = dim3((lw * p.mod_rows + 255) / 256);
+  cfg.blockDim = dim3(256);
+  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p));
+  cfg.gridDim = dim3((lw * p.pack_rows + 127) / 128);
+  cfg.blockDim = dim3(128);
+  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_pack_kernel, p));
   g_launches.fetch_add(3, std::memory_order_relaxed);
   ICB_CUDA(cudaGetLastError());
   if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));

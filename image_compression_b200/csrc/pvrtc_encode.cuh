@@ -20,9 +20,13 @@ __device__ __forceinline__ uint32_t pv_l1(uint32_t p, uint32_t q) { return __vsa
 // a*32 + c as ONE multiply-add on the FMA pipe.  Written in PTX because the compiler otherwise rewrites
 // (x & mask)*32 + c into shift/and/or -- three instructions on the integer pipe that bounds these kernels.
 __device__ __forceinline__ uint32_t pv_mad32(uint32_t a, uint32_t c) {
+#ifdef ICB_HOST_EMULATION  // tests/hostemu only (device code stepped through on the CPU); never in the library
+  return a * 32u + c;
+#else
   uint32_t d;
   asm("mad.lo.u32 %0, %1, 32, %2;" : "=r"(d) : "r"(a), "r"(c));
   return d;
+#endif
 }
 
 // Keep the top n bits of an 8-bit value and replicate them downwards (ApplyBitDepthReduction).

@@ -36,12 +36,53 @@ struct PvrtcParams {
   uint32_t pack_row0, pack_rows;    // block rows Pack covers
 };
 
+// Host side: the parameter block for block rows [r0, r1) of an h x w image.  `whole`: src holds the whole image
+// (src_row0 = 0) and every kernel covers everything; otherwise src holds the stripe and its two halo block rows.
+// scratch: icb_pvrtc2_scratch_size(h, w) bytes -- the A image, the B image, then the 2-bit modulation words.
+inline PvrtcParams pvrtc_make_params(const void *src, const void *first_pixel, void *scratch, void *dst, uint32_t h,
+                                     uint32_t w, uint32_t src_row0, uint32_t r0, uint32_t r1, bool whole) {
+  PvrtcParams p;
+  const uint32_t lw = w / 8, lh = h / 4, nblocks = lw * lh;
+  p.src = static_cast<const uint32_t *>(src);
+  p.first_pixel = static_cast<const uint32_t *>(first_pixel);
+  p.low_a = static_cast<uint32_t *>(scratch);
+  p.low_b = p.low_a + nblocks;
+  p.mod = reinterpret_cast<uint16_t *>(p.low_b + nblocks);
+  p.dst = static_cast<uint2 *>(dst);
+  p.width = w;
+  p.height = h;
+  p.src_row0 = src_row0;
+  if (whole) {
+    p.morph_row0 = 0; p.morph_rows = lh;
+    p.mod_row0 = 0; p.mod_rows = h;
+  } else {
+    p.morph_row0 = (r0 + lh - 1) & (lh - 1); p.morph_rows = r1 - r0 + 2;
+    p.mod_row0 = 4 * r0; p.mod_rows = 4 * (r1 - r0) + 1;
+  }
+  p.pack_row0 = r0; p.pack_rows = r1 - r0;
+  return p;
+}
+
 // Address of image row y (absolute, < height) in the resident rows.
 __device__ __forceinline__ const uint32_t *pv_src_row(const PvrtcParams &p, uint32_t y) {
   return p.src + static_cast<size_t>((y - p.src_row0) & (p.height - 1u)) * p.width;
 }
 
+// The three kernels of one encode are chained with programmatic dependent launch: each lets the next one start its
+// launch and prologue at once (launch_dependents) and the next one waits for this one's memory to be complete before
+// its first global access (griddepcontrol.wait) -- only the launch latency overlaps, which is what separates three
+// 10-35 us kernels.  Morph itself is launched plainly, so it never overlaps the previous encode's Pack, whose inputs
+// it overwrites.
+#ifdef ICB_HOST_EMULATION  // tests/hostemu only: kernels run one after another on the CPU, nothing to order
+__device__ __forceinline__ void pv_launch_dependents() {}
+__device__ __forceinline__ void pv_wait_for_previous() {}
+#else
+__device__ __forceinline__ void pv_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pv_wait_for_previous() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
+  pv_launch_dependents();
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.morph_rows) return;
@@ -63,6 +104,8 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
 }
 
 __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p) {
+  pv_launch_dependents();
+  pv_wait_for_previous();  // Morph's A/B colours
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.mod_rows) return;
@@ -98,6 +141,7 @@ __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p
 }
 
 __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
+  pv_wait_for_previous();  // Modulate's 2-bit values (and, transitively, Morph's colours)
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.pack_rows) return;

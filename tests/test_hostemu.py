@@ -1,0 +1,243 @@
+"""CPU-only parity tests of the DEVICE arithmetic: the CUDA headers of image_compression_b200/csrc compiled for the
+host with the intrinsics emulated (tests/hostemu/ -- test infrastructure, never part of the product) and stepped
+through one emulated thread at a time, against the CPU oracle and the reference-generated golden fixtures.
+Bit-exact: every comparison is array_equal.
+
+What this covers that the GPU suite cannot cover here (the container has no GPU): the block encoders, decoders,
+PVRTC kernels and compressed-domain operations themselves.  What it does not cover: the TMA ring drivers, launch
+configuration and the memory system (tests/*_gpu.py, run on the B200 box)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import checkers as ck
+import imagegen
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
+CSRC = os.path.join(ck.ROOT, "image_compression_b200", "csrc")
+_u8p = C.POINTER(C.c_uint8)
+VOTES = (0, 1)  # what the other lanes of the warp answer to a warp vote: like this lane / "no" (cuda_emulation.h)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_u8p)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "libhostemu.so")
+    sources = [os.path.join(HERE, f) for f in ("hostemu.cc", "cuda_emulation.h")]
+    sources += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in sources):
+        # -ffp-contract=off: every float operation rounds on its own, as the SASS does (FADD / FFMA as written)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                        "-Wno-unused-function", "-o", so, os.path.join(HERE, "hostemu.cc")], check=True)
+    lib = C.CDLL(so)
+    lib.emu_encode4x4.argtypes = [C.c_int, C.c_int, _u8p] + [C.c_uint32] * 5 + [C.c_int, C.c_int, _u8p]
+    lib.emu_dxt1_rgb888_rows.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _u8p]
+    lib.emu_pvrtc2.argtypes = [_u8p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p]
+    lib.emu_decode4x4.argtypes = [C.c_int, _u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _u8p, C.c_uint32]
+    lib.emu_downsample4x4.argtypes = [C.c_int, C.c_int, _u8p, C.c_uint32, C.c_uint32, _u8p]
+    lib.emu_pad4x4.argtypes = [C.c_int, C.c_int, _u8p] + [C.c_uint32] * 4 + [_u8p]
+    lib.emu_fill_solid4x4.argtypes = [C.c_int, C.c_uint32, C.c_uint64, _u8p]
+    lib.emu_transcode_dxt1_to_etc1.argtypes = [_u8p, C.c_uint64]
+    yield lib
+    lib.emu_set_vote(0)
+
+
+def encode(emu, codec, nc, buf, h, w, pitch=None, coded=None, swap=0, strategy=2, vote=0):
+    ch, cw = coded if coded else (h, w)
+    ch, cw = max(h, ch), max(w, cw)
+    out = np.zeros(ck.nblocks(ch) * ck.nblocks(cw) * ck.block_bytes(codec), np.uint8)
+    buf = np.ascontiguousarray(buf)
+    emu.emu_set_vote(vote)
+    assert emu.emu_encode4x4(codec, nc, _ptr(buf), h, w, pitch or w * nc, ch, cw, swap, strategy, _ptr(out)) == 0
+    return out
+
+
+def pvrtc(emu, img, n, stripes=1):
+    out = np.zeros(n * n // 4, np.uint8)
+    img = np.ascontiguousarray(img)
+    assert emu.emu_pvrtc2(_ptr(img), n, n, stripes, _ptr(out)) == 0
+    return out
+
+
+def test_emulated_instructions(emu):
+    """The emulation layer itself: byte permutes, dp4a, SIMD min/max/add-clamp, packed-half rounding and saturation."""
+    assert emu.emu_self_check() == 0
+
+
+def test_golden_fixtures(emu, golden):
+    """Every reference-generated fixture (tests/golden/golden_v1.npz) through the device code."""
+    for meta, buf, want in golden:
+        h, w, nc = meta["h"], meta["w"], meta["ncomp"]
+        if meta["codec"] == "pvrtc":
+            got = pvrtc(emu, buf, h)
+        else:
+            codec = 2 if meta["codec"] == "etc" else (0 if nc == 3 else 1)
+            swap = 1 if meta["format"] in (ck.BGR, ck.BGRA) else 0
+            for vote in VOTES:
+                got = encode(emu, codec, nc, buf, h, w, pitch=w * nc + meta["padding"], coded=meta["padded"], swap=swap,
+                             strategy=meta["strategy"], vote=vote)
+                assert np.array_equal(got, want), (meta, vote)
+        assert np.array_equal(got, want), meta
+
+
+@pytest.mark.parametrize("fmt", [ck.RGB, ck.BGR, ck.RGBA, ck.BGRA])
+def test_dxt_vs_oracle(emu, fmt):
+    """DXT1 (3 components) / DXT5 (4), every image kind, ragged sizes; the warp-uniform fast path of the colour index
+    search and the general path must both give the oracle's bytes (the vote only picks which one runs)."""
+    nc = ck.ncomp(fmt)
+    codec, swap = (0 if nc == 3 else 1), (1 if fmt in (ck.BGR, ck.BGRA) else 0)
+    for kind in imagegen.KINDS:
+        for (h, w) in ((32, 64), (13, 30), (1, 1), (5, 3)):
+            img = imagegen.make(kind, h, w, nc, seed=21)
+            want = ck.oracle_dxt(fmt, img.ravel(), h, w)
+            for vote in VOTES:
+                assert np.array_equal(encode(emu, codec, nc, img.ravel(), h, w, swap=swap, vote=vote), want), (kind, h, w, vote)
+
+
+def test_dxt_padding_and_compress_and_pad(emu):
+    for fmt in (ck.RGB, ck.BGRA):
+        nc = ck.ncomp(fmt)
+        codec, swap = (0 if nc == 3 else 1), (1 if fmt == ck.BGRA else 0)
+        for (h, w, padding, coded) in ((3, 3, 1, None), (9, 13, 7, None), (8, 8, 0, (8, 40)), (8, 8, 0, (40, 8)), (33, 67, 5, (64, 128))):
+            img = imagegen.make("smooth_noise", h, w, nc, seed=14)
+            buf, pitch = imagegen.with_row_padding(img, padding)
+            ch, cw = coded if coded else (None, None)
+            got = encode(emu, codec, nc, buf, h, w, pitch=pitch, coded=coded, swap=swap)
+            assert np.array_equal(got, ck.oracle_dxt(fmt, buf, h, w, ch, cw, padding)), (fmt, h, w, padding, coded)
+
+
+@pytest.mark.parametrize("swap", [0, 1])
+def test_dxt1_from_rgba_extension(emu, swap):
+    for kind in imagegen.KINDS:
+        img = imagegen.make(kind, 24, 36, 4, seed=22)
+        want = ck.oracle_dxt1_rgba(img.ravel(), 24, 36, swap_rb=swap)
+        for vote in VOTES:
+            assert np.array_equal(encode(emu, 0, 4, img.ravel(), 24, 36, swap=swap, vote=vote), want), (kind, vote)
+
+
+@pytest.mark.parametrize("swap", [0, 1])
+def test_dxt1_rgb888_row_word_form(emu, swap):
+    """The form the TMA consumers use for RGB888: luminance keys straight from the three 32-bit words of a block row."""
+    for kind in imagegen.KINDS:
+        for padding in (0, 4):
+            img = imagegen.make(kind, 16, 48, 3, seed=23)
+            buf, pitch = imagegen.with_row_padding(img, padding)
+            want = ck.oracle_dxt(ck.BGR if swap else ck.RGB, buf, 16, 48, None, None, padding)
+            for vote in VOTES:
+                emu.emu_set_vote(vote)
+                got = np.zeros(want.size, np.uint8)
+                assert emu.emu_dxt1_rgb888_rows(_ptr(buf), 16, 48, pitch, swap, _ptr(got)) == 0
+                assert np.array_equal(got, want), (kind, padding, vote)
+
+
+def test_dxt5_alpha_statistics_corner_cases(emu):
+    """ComputeBaseAlphas' rules (dxtc_compressor.cc:374-424): counts of 0 / 255 around the '> 1' threshold, all-extreme
+    blocks, equal endpoints -- one block per case, colour held constant."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for n0 in (0, 1, 2, 15, 16):
+        for n255 in (0, 1, 2, 16 - n0):
+            if n0 + n255 > 16:
+                continue
+            for _ in range(6):
+                a = rng.integers(1, 255, 16)
+                a[:n0] = 0
+                a[n0:n0 + n255] = 255
+                cases.append(rng.permutation(a))
+    for v in (0, 1, 127, 254, 255):
+        cases.append(np.full(16, v))
+    for lo, hi in ((1, 2), (100, 101), (253, 254), (1, 254), (7, 9)):
+        cases.append(rng.choice([lo, hi], 16))
+        cases.append(np.concatenate([[0], rng.choice([lo, hi], 15)]))
+        cases.append(np.concatenate([[255], rng.choice([lo, hi], 15)]))
+    img = np.zeros((4, 4 * len(cases), 4), np.uint8)
+    img[..., :3] = (90, 160, 30)
+    for k, a in enumerate(cases):
+        img[:, 4 * k:4 * k + 4, 3] = np.asarray(a, np.uint8).reshape(4, 4)
+    h, w = img.shape[:2]
+    assert np.array_equal(encode(emu, 1, 4, img.ravel(), h, w), ck.oracle_dxt(ck.RGBA, img.ravel(), h, w))
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3])
+def test_etc1_vs_oracle(emu, strategy):
+    for kind in imagegen.KINDS:
+        for (h, w) in ((16, 32), (9, 14)):
+            img = imagegen.make(kind, h, w, 3, seed=24)
+            got = encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy)
+            assert np.array_equal(got, ck.oracle_etc1(strategy, img.ravel(), h, w)), (kind, h, w)
+
+
+def test_pvrtc_vs_oracle_whole_and_striped(emu):
+    """Morph / Modulate / Pack over whole images, and the halo-stripe form (each stripe from a private copy of its rows
+    plus wrapped halo rows, scratch poisoned in between): any number of stripes assembles the whole image."""
+    for n in (8, 16, 32, 64):
+        for kind in imagegen.KINDS:
+            img = imagegen.make(kind, n, n, 4, seed=n + 1)
+            want = ck.oracle_pvrtc(img.ravel(), n, n)
+            assert np.array_equal(pvrtc(emu, img.ravel(), n), want), (n, kind)
+            for parts in (2, 3, 4):
+                if n // 4 // parts + 2 <= n // 4 and parts <= n // 4:
+                    assert np.array_equal(pvrtc(emu, img.ravel(), n, parts), want), (n, kind, parts)
+
+
+def test_decoders_every_kind_of_block(emu):
+    """Random bit patterns (blocks no encoder produces included) and encoder output, whole and cropped images."""
+    rng = np.random.default_rng(9)
+    for codec in (0, 1, 2):
+        nc = 4 if codec == 1 else 3
+        for (h, w) in ((16, 64), (7, 10), (4, 4), (1, 1), (33, 130)):
+            blocks = rng.integers(0, 256, ck.nblocks(h) * ck.nblocks(w) * ck.block_bytes(codec), dtype=np.uint8)
+            for swap in ((0, 1) if codec != 2 else (0,)):
+                got = np.zeros(h * w * nc, np.uint8)
+                assert emu.emu_decode4x4(codec, _ptr(blocks), h, w, ck.nblocks(w), swap, _ptr(got), w * nc) == 0
+                assert np.array_equal(got, ck.oracle_decode(codec, blocks, h, w, swap_rb=swap)), (codec, h, w, swap)
+
+
+def test_block_operations_golden_and_oracle(emu, golden_ops):
+    """Downsample / Pad / CreateSolidImage / TranscodeDxt1ToEtc1 kernels against the reference-generated fixtures."""
+    for meta, src, want in golden_ops:
+        op, codec = meta["op"], meta["codec"]
+        src = np.ascontiguousarray(src)
+        st = meta.get("strategy", 2)
+        got = np.zeros(want.size, np.uint8)
+        if op == "downsample":
+            status = emu.emu_downsample4x4(codec, st, _ptr(src), meta["h"], meta["w"], _ptr(got))
+            if meta["refused"]:
+                assert status == -4, meta
+                continue
+            assert status == 0
+        elif op == "pad":
+            ch, cw = 4 * ck.nblocks(meta["h"]), 4 * ck.nblocks(meta["w"])
+            assert emu.emu_pad4x4(codec, st, _ptr(src), ch, cw, meta["ph"], meta["pw"], _ptr(got)) == 0
+        elif op == "solid":
+            packed = int(src[0]) | int(src[1]) << 8 | int(src[2]) << 16 | int(src[3]) << 24
+            assert emu.emu_fill_solid4x4(codec, packed, want.size // ck.block_bytes(codec), _ptr(got)) == 0
+        elif op == "transcode":
+            got = src.copy()
+            assert emu.emu_transcode_dxt1_to_etc1(_ptr(got), got.size // 8) == 0
+        else:
+            continue  # copy_subimage is a strided memcpy on the device, no kernel to emulate
+        assert np.array_equal(got, want), meta
+
+
+@pytest.mark.parametrize("codec,fmt", [(0, ck.RGB), (1, ck.RGBA), (2, ck.RGB)])
+def test_mip_chain(emu, codec, fmt):
+    """Compress, then halve down to one block: every level equals the oracle's (decode + average + re-encode)."""
+    n, nc = 64, ck.ncomp(fmt)
+    img = imagegen.make("smooth_noise", n, n, nc, seed=5)
+    level = encode(emu, codec, nc, img.ravel(), n, n)
+    want = ck.oracle_etc1(2, img.ravel(), n, n) if codec == 2 else ck.oracle_dxt(fmt, img.ravel(), n, n)
+    size = n
+    while size > 4:
+        assert np.array_equal(level, want), size
+        out = np.zeros(want.size // 4 if size > 4 else want.size, np.uint8)
+        assert emu.emu_downsample4x4(codec, 2, _ptr(level), size, size, _ptr(out)) == 0
+        level, want = out, ck.oracle_downsample(codec, want, size, size)
+        size //= 2
+    assert np.array_equal(level, want)
