@@ -693,8 +693,7 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   }
   const icb::PvrtcParams p = icb::pvrtc_make_params(d_src, d_first_pixel, scratch, d_dst, h, w, src_row0, r0, r1, whole);
   const uint32_t lw = w / 8;
-  icb::pvrtc_morph_kernel<<<(lw * p.morph_rows + 127) / 128, 128, 0, st>>>(p);
-  // Modulate and Pack: programmatic dependent launch (see pvrtc_kernels.cuh); ICB_NO_PDL=1 launches them plainly.
+  // Programmatic dependent launch for all three (see pvrtc_kernels.cuh); ICB_NO_PDL=1 launches them plainly.
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -702,6 +701,9 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   cfg.stream = st;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("ICB_NO_PDL") ? 0 : 1;
+  cfg.gridDim = dim3((lw * p.morph_rows + 127) / 128);
+  cfg.blockDim = dim3(128);
+  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p));
   cfg.gridDim = dim3((lw * p.mod_rows + 255) / 256);
   cfg.blockDim = dim3(256);
   ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p));

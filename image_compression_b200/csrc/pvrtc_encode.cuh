@@ -17,17 +17,11 @@ namespace icb {
 
 __device__ __forceinline__ uint32_t pv_l1(uint32_t p, uint32_t q) { return __vsadu4(p, q); }
 
-// a*32 + c as ONE multiply-add on the FMA pipe.  Written in PTX because the compiler otherwise rewrites
-// (x & mask)*32 + c into shift/and/or -- three instructions on the integer pipe that bounds these kernels.
-__device__ __forceinline__ uint32_t pv_mad32(uint32_t a, uint32_t c) {
-#ifdef ICB_HOST_EMULATION  // tests/hostemu only (device code stepped through on the CPU); never in the library
-  return a * 32u + c;
-#else
-  uint32_t d;
-  asm("mad.lo.u32 %0, %1, 32, %2;" : "=r"(d) : "r"(a), "r"(c));
-  return d;
-#endif
-}
+// value * 32 + index as ONE multiply-add on the FMA pipe (IMAD).  The multiplier arrives as a kernel parameter
+// (PvrtcParams::key_scale, always 32): with a literal 32 -- in C or in PTX -- ptxas strength-reduces the multiply-add to
+// LEA, which issues on the integer pipe that bounds Morph (measured: 130 LEA per block, integer pipe 82 % busy, FMA
+// pipe 10 %); a multiplier it cannot see stays an IMAD with a constant-bank operand.
+__device__ __forceinline__ uint32_t pv_key(uint32_t value, uint32_t key_scale, uint32_t index) { return value * key_scale + index; }
 
 // Keep the top n bits of an 8-bit value and replicate them downwards (ApplyBitDepthReduction).
 __device__ __forceinline__ uint32_t pv_keep_bits(uint32_t v, uint32_t n) {
@@ -56,31 +50,38 @@ __device__ __forceinline__ uint32_t pv_reduce_colour(uint32_t c, bool is_b) {
 // The block's two extreme colours (GetExtremesFast + ApplyColorChannelReduction).  px[j], j = 8*y + x, are the
 // block's 32 pixels; fetch(j) must return px[j] (callers re-read memory by index: a register-indexed lookup would
 // be a 31-deep select chain per colour); first_pixel is the image's pixel (0,0), which the reference uses whenever
-// an axis is all zero in the block (its "max" slot never moves off index 0).
-// Keys: value*32 + j for "first minimum", the same with the index field reversed (^31) for "first maximum".
-// A key needs 13 bits, so the four channel axes ride two to a register -- (r,b) and (g,a) in 16-bit lanes: one
-// mask or byte permute plus one IMAD builds two keys, VIMNMX3.U16x2 folds two pixels of two axes per instruction.
+// an axis is all zero in the block (its "max" slot never moves off index 0); key_scale is 32 (see pv_key).
+// Keys: value*32 + j for "first minimum", value*32 + (31 - j) for "first maximum" (ties resolve to the lowest j under
+// max) -- each key its own IMAD rather than one key and an XOR, because the FMA pipe is idle here and the integer
+// pipe is not.  A key needs 13 bits, so the four channel axes ride two to a register -- (r,b) and (g,a) in 16-bit
+// lanes: one mask or byte permute plus two IMADs build four keys, VIMNMX3.U16x2 folds two pixels of two axes per
+// instruction.
 template <typename Fetch>
-__device__ __forceinline__ void pv_block_extremes(const uint32_t (&px)[32], uint32_t first_pixel, Fetch fetch,
-                                                  uint32_t *colour_a, uint32_t *colour_b) {
+__device__ __forceinline__ void pv_block_extremes(const uint32_t (&px)[32], uint32_t first_pixel, uint32_t key_scale,
+                                                  Fetch fetch, uint32_t *colour_a, uint32_t *colour_b) {
   uint32_t min_l = 0xffffffffu, max_l = 0u;              // lightness axis, scalar keys
   uint32_t min_rb = 0xffffffffu, max_rb = 0u, min_ga = 0xffffffffu, max_ga = 0u;  // packed channel keys
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    uint32_t kl[2], krb[2], kga[2];
+    uint32_t nl[2], xl[2], nrb[2], xrb[2], nga[2], xga[2];  // n.. = key for the minimum, x.. = key for the maximum
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      const uint32_t p = px[j + t], idx = static_cast<uint32_t>(j + t);
-      kl[t] = pv_mad32(__dp4a(p, 0x001c964du, 0u) >> 8, idx);  // lightness (77r + 150g + 28b) / 256
-      krb[t] = pv_mad32(p & 0x00ff00ffu, idx * 0x10001u);
-      kga[t] = pv_mad32(__byte_perm(p, 0u, 0x4341), idx * 0x10001u);
+      const uint32_t p = px[j + t], idx = static_cast<uint32_t>(j + t), rev = 31u - idx;
+      const uint32_t light = __dp4a(p, 0x001c964du, 0u) >> 8;  // lightness (77r + 150g + 28b) / 256
+      const uint32_t rb = p & 0x00ff00ffu, ga = __byte_perm(p, 0u, 0x4341);
+      nl[t] = pv_key(light, key_scale, idx);
+      xl[t] = pv_key(light, key_scale, rev);
+      nrb[t] = pv_key(rb, key_scale, idx * 0x10001u);
+      xrb[t] = pv_key(rb, key_scale, rev * 0x10001u);
+      nga[t] = pv_key(ga, key_scale, idx * 0x10001u);
+      xga[t] = pv_key(ga, key_scale, rev * 0x10001u);
     }
-    min_l = __vimin3_u32(min_l, kl[0], kl[1]);
-    max_l = __vimax3_u32(max_l, kl[0] ^ 31u, kl[1] ^ 31u);
-    min_rb = __vimin3_u16x2(min_rb, krb[0], krb[1]);
-    max_rb = __vimax3_u16x2(max_rb, krb[0] ^ 0x001f001fu, krb[1] ^ 0x001f001fu);
-    min_ga = __vimin3_u16x2(min_ga, kga[0], kga[1]);
-    max_ga = __vimax3_u16x2(max_ga, kga[0] ^ 0x001f001fu, kga[1] ^ 0x001f001fu);
+    min_l = __vimin3_u32(min_l, nl[0], nl[1]);
+    max_l = __vimax3_u32(max_l, xl[0], xl[1]);
+    min_rb = __vimin3_u16x2(min_rb, nrb[0], nrb[1]);
+    max_rb = __vimax3_u16x2(max_rb, xrb[0], xrb[1]);
+    min_ga = __vimin3_u16x2(min_ga, nga[0], nga[1]);
+    max_ga = __vimax3_u16x2(max_ga, xga[0], xga[1]);
   }
   // axis order of the reference: lightness, r, g, b, a
   const uint32_t kmin[5] = {min_l, min_rb & 0xffffu, min_ga & 0xffffu, min_rb >> 16, min_ga >> 16};

@@ -34,6 +34,7 @@ struct PvrtcParams {
   uint32_t morph_row0, morph_rows;  // block rows Morph covers: morph_row0 .. +morph_rows (mod h/4)
   uint32_t mod_row0, mod_rows;      // pixel rows Modulate covers (mod h)
   uint32_t pack_row0, pack_rows;    // block rows Pack covers
+  uint32_t key_scale;               // the constant 32, kept out of the compiler's sight (pvrtc_encode.cuh:pv_key)
 };
 
 // Host side: the parameter block for block rows [r0, r1) of an h x w image.  `whole`: src holds the whole image
@@ -60,6 +61,7 @@ inline PvrtcParams pvrtc_make_params(const void *src, const void *first_pixel, v
     p.mod_row0 = 4 * r0; p.mod_rows = 4 * (r1 - r0) + 1;
   }
   p.pack_row0 = r0; p.pack_rows = r1 - r0;
+  p.key_scale = 32;
   return p;
 }
 
@@ -68,11 +70,11 @@ __device__ __forceinline__ const uint32_t *pv_src_row(const PvrtcParams &p, uint
   return p.src + static_cast<size_t>((y - p.src_row0) & (p.height - 1u)) * p.width;
 }
 
-// The three kernels of one encode are chained with programmatic dependent launch: each lets the next one start its
-// launch and prologue at once (launch_dependents) and the next one waits for this one's memory to be complete before
-// its first global access (griddepcontrol.wait) -- only the launch latency overlaps, which is what separates three
-// 10-35 us kernels.  Morph itself is launched plainly, so it never overlaps the previous encode's Pack, whose inputs
-// it overwrites.
+// All three kernels are launched with programmatic dependent launch: each lets the next kernel in the stream start
+// its launch and prologue at once (launch_dependents) and waits for the kernel before it to be complete, its memory
+// flushed, before its own first global access (griddepcontrol.wait) -- only the launch latency overlaps, which is what
+// separates three 10-35 us kernels.  Morph waits too: it may follow the kernel that produced the image, and it
+// overwrites the A/B colours the previous encode's Pack is still reading.
 #ifdef ICB_HOST_EMULATION  // tests/hostemu only: kernels run one after another on the CPU, nothing to order
 __device__ __forceinline__ void pv_launch_dependents() {}
 __device__ __forceinline__ void pv_wait_for_previous() {}
@@ -83,6 +85,7 @@ __device__ __forceinline__ void pv_wait_for_previous() { asm volatile("griddepco
 
 __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   pv_launch_dependents();
+  pv_wait_for_previous();  // whatever wrote the image; the previous encode's Pack (reads the colours written below)
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.morph_rows) return;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   }
   auto fetch = [&](uint32_t j) { return __ldg(origin + static_cast<size_t>(j >> 3) * p.width + (j & 7u)); };
   uint32_t ca, cb;
-  pv_block_extremes(px, __ldg(p.first_pixel), fetch, &ca, &cb);
+  pv_block_extremes(px, __ldg(p.first_pixel), p.key_scale, fetch, &ca, &cb);
   p.low_a[by * lw + bx] = ca;
   p.low_b[by * lw + bx] = cb;
 }
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p
 }
 
 __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
+  pv_launch_dependents();
   pv_wait_for_previous();  // Modulate's 2-bit values (and, transitively, Morph's colours)
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
