@@ -55,34 +55,43 @@ __device__ __forceinline__ uint32_t pv_reduce_colour(uint32_t c, bool is_b) {
 // max) -- each key its own IMAD rather than one key and an XOR, because the FMA pipe is idle here and the integer
 // pipe is not.  A key needs 13 bits, so the four channel axes ride two to a register -- (r,b) and (g,a) in 16-bit
 // lanes: one mask or byte permute plus two IMADs build four keys, VIMNMX3.U16x2 folds two pixels of two axes per
-// instruction.
+// instruction -- and so do the lightness keys of two neighbouring pixels.
 template <typename Fetch>
 __device__ __forceinline__ void pv_block_extremes(const uint32_t (&px)[32], uint32_t first_pixel, uint32_t key_scale,
                                                   Fetch fetch, uint32_t *colour_a, uint32_t *colour_b) {
-  uint32_t min_l = 0xffffffffu, max_l = 0u;              // lightness axis, scalar keys
+  uint32_t min_l = 0xffffffffu, max_l = 0u;              // lightness axis: pixels j, j+1 in the two 16-bit lanes
   uint32_t min_rb = 0xffffffffu, max_rb = 0u, min_ga = 0xffffffffu, max_ga = 0u;  // packed channel keys
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    uint32_t nl[2], xl[2], nrb[2], xrb[2], nga[2], xga[2];  // n.. = key for the minimum, x.. = key for the maximum
+  for (int j = 0; j < 32; j += 4) {
+    uint32_t nl[2], xl[2];  // n.. = key for the minimum, x.. = key for the maximum
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const uint32_t p = px[j + t], idx = static_cast<uint32_t>(j + t), rev = 31u - idx;
-      const uint32_t light = __dp4a(p, 0x001c964du, 0u) >> 8;  // lightness (77r + 150g + 28b) / 256
-      const uint32_t rb = p & 0x00ff00ffu, ga = __byte_perm(p, 0u, 0x4341);
-      nl[t] = pv_key(light, key_scale, idx);
-      xl[t] = pv_key(light, key_scale, rev);
-      nrb[t] = pv_key(rb, key_scale, idx * 0x10001u);
-      xrb[t] = pv_key(rb, key_scale, rev * 0x10001u);
-      nga[t] = pv_key(ga, key_scale, idx * 0x10001u);
-      xga[t] = pv_key(ga, key_scale, rev * 0x10001u);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t nrb[2], xrb[2], nga[2], xga[2], dot[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t p = px[j + 2 * h + t], idx = static_cast<uint32_t>(j + 2 * h + t), rev = 31u - idx;
+        dot[t] = __dp4a(p, 0x001c964du, 0u);  // 77r + 150g + 28b <= 65025: lightness is byte 1, bytes 2 and 3 are zero
+        const uint32_t rb = p & 0x00ff00ffu, ga = __byte_perm(p, 0u, 0x4341);
+        nrb[t] = pv_key(rb, key_scale, idx * 0x10001u);
+        xrb[t] = pv_key(rb, key_scale, rev * 0x10001u);
+        nga[t] = pv_key(ga, key_scale, idx * 0x10001u);
+        xga[t] = pv_key(ga, key_scale, rev * 0x10001u);
+      }
+      min_rb = __vimin3_u16x2(min_rb, nrb[0], nrb[1]);
+      max_rb = __vimax3_u16x2(max_rb, xrb[0], xrb[1]);
+      min_ga = __vimin3_u16x2(min_ga, nga[0], nga[1]);
+      max_ga = __vimax3_u16x2(max_ga, xga[0], xga[1]);
+      // one byte permute divides both lightness sums by 256 and puts them side by side; one IMAD keys both pixels
+      const uint32_t light2 = __byte_perm(dot[0], dot[1], 0x7531);
+      const uint32_t i0 = static_cast<uint32_t>(j + 2 * h), i1 = i0 + 1u;
+      nl[h] = pv_key(light2, key_scale, i0 | (i1 << 16));
+      xl[h] = pv_key(light2, key_scale, (31u - i0) | ((31u - i1) << 16));
     }
-    min_l = __vimin3_u32(min_l, nl[0], nl[1]);
-    max_l = __vimax3_u32(max_l, xl[0], xl[1]);
-    min_rb = __vimin3_u16x2(min_rb, nrb[0], nrb[1]);
-    max_rb = __vimax3_u16x2(max_rb, xrb[0], xrb[1]);
-    min_ga = __vimin3_u16x2(min_ga, nga[0], nga[1]);
-    max_ga = __vimax3_u16x2(max_ga, xga[0], xga[1]);
+    min_l = __vimin3_u16x2(min_l, nl[0], nl[1]);
+    max_l = __vimax3_u16x2(max_l, xl[0], xl[1]);
   }
+  min_l = min(min_l & 0xffffu, min_l >> 16);
+  max_l = max(max_l & 0xffffu, max_l >> 16);
   // axis order of the reference: lightness, r, g, b, a
   const uint32_t kmin[5] = {min_l, min_rb & 0xffffu, min_ga & 0xffffu, min_rb >> 16, min_ga >> 16};
   const uint32_t kmax[5] = {max_l, max_rb & 0xffffu, max_ga & 0xffffu, max_rb >> 16, max_ga >> 16};

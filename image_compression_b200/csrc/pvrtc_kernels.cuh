@@ -35,6 +35,8 @@ struct PvrtcParams {
   uint32_t mod_row0, mod_rows;      // pixel rows Modulate covers (mod h)
   uint32_t pack_row0, pack_rows;    // block rows Pack covers
   uint32_t key_scale;               // the constant 32, kept out of the compiler's sight (pvrtc_encode.cuh:pv_key)
+  uint32_t lw_shift;                // log2(width / 8): images are powers of two, so thread -> (block column, row) is
+                                    // a mask and a shift instead of a 20-instruction division by a run-time value
 };
 
 // Host side: the parameter block for block rows [r0, r1) of an h x w image.  `whole`: src holds the whole image
@@ -62,6 +64,8 @@ inline PvrtcParams pvrtc_make_params(const void *src, const void *first_pixel, v
   }
   p.pack_row0 = r0; p.pack_rows = r1 - r0;
   p.key_scale = 32;
+  p.lw_shift = 0;
+  while ((1u << p.lw_shift) < lw) ++p.lw_shift;
   return p;
 }
 
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.morph_rows) return;
-  const uint32_t bx = t % lw, by = (p.morph_row0 + t / lw) & (lh - 1u);
+  const uint32_t bx = t & (lw - 1u), by = (p.morph_row0 + (t >> p.lw_shift)) & (lh - 1u);
   const uint32_t *origin = pv_src_row(p, by * 4u) + bx * 8;  // a block's four rows are contiguous in the buffer
   uint32_t px[32];
 #pragma unroll
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.mod_rows) return;
-  const uint32_t bx = t % lw, y = (p.mod_row0 + t / lw) & (p.height - 1u);
+  const uint32_t bx = t & (lw - 1u), y = (p.mod_row0 + (t >> p.lw_shift)) & (p.height - 1u);
   // Low-resolution rows/columns this pixel row interpolates between, wrapped (pvrtc_compressor.cc:216-223).
   const uint32_t top = ((y - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
   const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lw * p.pack_rows) return;
-  const uint32_t bx = t % lw, by = (p.pack_row0 + t / lw) & (lh - 1u);
+  const uint32_t bx = t & (lw - 1u), by = (p.pack_row0 + (t >> p.lw_shift)) & (lh - 1u);
   const uint32_t right_bx = (bx + 1u) & (lw - 1u);
   uint32_t row[5], right[4];
 #pragma unroll
