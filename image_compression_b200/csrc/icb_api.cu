@@ -673,7 +673,7 @@ int icb_encode4x4_stripe(int codec, int ncomp, const void *d_src, uint32_t h, ui
   return encode4x4(codec, ncomp, d_src, h, w, pitch, ch, cw, swap_rb, strategy, r0, r1, d_dst, stream);
 }
 
-// two low-resolution colour images (4 B per block each) + 2-bit modulation per pixel (2 B per 8 pixels)
+// low-resolution A/B colour pairs (8 B per block) + 2-bit modulation per pixel (2 B per 8 pixels)
 size_t icb_pvrtc2_scratch_size(uint32_t h, uint32_t w) {
   return static_cast<size_t>(w / 8) * (h / 4) * 4 * 2 + static_cast<size_t>(w / 8) * h * 2;
 }
@@ -686,6 +686,7 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   DeviceInfo info;
   if (int s = device_info(&info)) return s;
   void *scratch = d_scratch;
+  if (reinterpret_cast<uintptr_t>(scratch) % 8 != 0) return fail(ICB_ERR_INVALID, "PVRTC scratch must be 8-byte aligned");
   if (!scratch) {
     cudaMemPool_t pool;
     if (int s = scratch_pool(&pool)) return s;
@@ -704,8 +705,8 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   cfg.gridDim = dim3((lw * p.morph_rows + 127) / 128);
   cfg.blockDim = dim3(128);
   ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p));
-  cfg.gridDim = dim3((lw * p.mod_rows + 255) / 256);
-  cfg.blockDim = dim3(256);
+  cfg.gridDim = dim3((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads);
+  cfg.blockDim = dim3(icb::kModThreads);
   ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p));
   cfg.gridDim = dim3((lw * p.pack_rows + 127) / 128);
   cfg.blockDim = dim3(128);

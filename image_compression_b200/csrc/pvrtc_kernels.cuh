@@ -16,23 +16,34 @@
 
 namespace icb {
 
+// Pixel rows per Modulate thread: kModRows consecutive rows that interpolate between the same two rows of the
+// low-resolution images (rows 4g+2 .. 4g+5 lie between block rows g and g+1), so the six colour-pair loads and their
+// lane splits are done once per thread.  Must divide 4.
+#ifndef ICB_PVRTC_MOD_ROWS
+#define ICB_PVRTC_MOD_ROWS 4
+#endif
+constexpr uint32_t kModRows = ICB_PVRTC_MOD_ROWS;
+static_assert(kModRows == 1 || kModRows == 2 || kModRows == 4, "a thread's rows must share their low-resolution rows");
+constexpr uint32_t kModThreads = 128;
+
 // Whole image: src holds all rows, src_row0 = 0, every range covers the image.  Row stripe (one rank of a sharded
 // image): src holds only the pixel rows of block rows [r0 - 1, r1 + 1) -- the stripe plus one
 // block row of halo above and below, wrapped round the torus -- starting at image row src_row0 = 4 * (r0 - 1) mod h;
 // Morph runs over those r1 - r0 + 2 block rows (the halo blocks are recomputed, not exchanged), Modulate over pixel
-// rows [4 r0, 4 r1] (the extra row is the one the last block row's mode decision looks at), Pack over [r0, r1).
+// rows [4 r0, 4 r1] (the extra row is the one the last block row's mode decision looks at) rounded outwards to whole
+// thread units, Pack over [r0, r1).
 // Scratch images are indexed by absolute position in both cases, and so is the Z-ordered output.
 struct PvrtcParams {
   const uint32_t *src;          // RGBA8 pixels, row-major, no padding; row 0 of this buffer is image row src_row0
   const uint32_t *first_pixel;  // image pixel (0,0): quirk P1 (pvrtc_compressor.cc:255-329) needs it in every block
-  uint32_t *low_a;              // (w/8) x (h/4) A colours
-  uint32_t *low_b;              // (w/8) x (h/4) B colours
+  uint2 *low;                   // (w/8) x (h/4) colour pairs: .x = the block's A colour, .y = its B colour (one 8-byte
+                                // load/store per block; the two low-resolution images of the reference, interleaved)
   uint16_t *mod;                // h x (w/8) words: 2-bit modulation of pixels 8*bx .. 8*bx+7 of row y
   uint2 *dst;                   // w*h/32 blocks in Z-order
   uint32_t width, height;
   uint32_t src_row0;            // image row held in row 0 of src
   uint32_t morph_row0, morph_rows;  // block rows Morph covers: morph_row0 .. +morph_rows (mod h/4)
-  uint32_t mod_row0, mod_rows;      // pixel rows Modulate covers (mod h)
+  uint32_t mod_unit0, mod_units;    // Modulate covers pixel rows 2 + kModRows * [mod_unit0, mod_unit0 + mod_units) (mod h)
   uint32_t pack_row0, pack_rows;    // block rows Pack covers
   uint32_t key_scale;               // the constant 32, kept out of the compiler's sight (pvrtc_encode.cuh:pv_key)
   uint32_t lw_shift;                // log2(width / 8): images are powers of two, so thread -> (block column, row) is
@@ -41,26 +52,29 @@ struct PvrtcParams {
 
 // Host side: the parameter block for block rows [r0, r1) of an h x w image.  `whole`: src holds the whole image
 // (src_row0 = 0) and every kernel covers everything; otherwise src holds the stripe and its two halo block rows.
-// scratch: icb_pvrtc2_scratch_size(h, w) bytes -- the A image, the B image, then the 2-bit modulation words.
+// scratch: icb_pvrtc2_scratch_size(h, w) bytes (8-byte aligned) -- the A/B colour pairs, then the 2-bit modulation words.
 inline PvrtcParams pvrtc_make_params(const void *src, const void *first_pixel, void *scratch, void *dst, uint32_t h,
                                      uint32_t w, uint32_t src_row0, uint32_t r0, uint32_t r1, bool whole) {
   PvrtcParams p;
   const uint32_t lw = w / 8, lh = h / 4, nblocks = lw * lh;
   p.src = static_cast<const uint32_t *>(src);
   p.first_pixel = static_cast<const uint32_t *>(first_pixel);
-  p.low_a = static_cast<uint32_t *>(scratch);
-  p.low_b = p.low_a + nblocks;
-  p.mod = reinterpret_cast<uint16_t *>(p.low_b + nblocks);
+  p.low = static_cast<uint2 *>(scratch);
+  p.mod = reinterpret_cast<uint16_t *>(p.low + nblocks);
   p.dst = static_cast<uint2 *>(dst);
   p.width = w;
   p.height = h;
   p.src_row0 = src_row0;
   if (whole) {
     p.morph_row0 = 0; p.morph_rows = lh;
-    p.mod_row0 = 0; p.mod_rows = h;
+    p.mod_unit0 = 0; p.mod_units = h / kModRows;
   } else {
     p.morph_row0 = (r0 + lh - 1) & (lh - 1); p.morph_rows = r1 - r0 + 2;
-    p.mod_row0 = 4 * r0; p.mod_rows = 4 * (r1 - r0) + 1;
+    // pixel rows 4 r0 .. 4 r1 inclusive, in units of kModRows rows that start at row 2 (the first unit may begin up to
+    // two rows early and the last one end a row late: those rows lie in the resident halo block rows)
+    const uint32_t units = h / kModRows;
+    const uint32_t first = ((4 * r0 + h - 2) & (h - 1)) / kModRows, last = ((4 * r1 + h - 2) & (h - 1)) / kModRows;
+    p.mod_unit0 = first; p.mod_units = ((last + units - first) & (units - 1)) + 1;
   }
   p.pack_row0 = r0; p.pack_rows = r1 - r0;
   p.key_scale = 32;
@@ -106,45 +120,53 @@ __global__ void __launch_bounds__(128) pvrtc_morph_kernel(const PvrtcParams p) {
   auto fetch = [&](uint32_t j) { return __ldg(origin + static_cast<size_t>(j >> 3) * p.width + (j & 7u)); };
   uint32_t ca, cb;
   pv_block_extremes(px, __ldg(p.first_pixel), p.key_scale, fetch, &ca, &cb);
-  p.low_a[by * lw + bx] = ca;
-  p.low_b[by * lw + bx] = cb;
+  p.low[by * lw + bx] = make_uint2(ca, cb);
 }
 
-__global__ void __launch_bounds__(256) pvrtc_modulate_kernel(const PvrtcParams p) {
+// Thread t handles pixels 8*bx .. 8*bx+7 of rows y0 .. y0+kModRows-1, y0 = 2 + kModRows * (mod_unit0 + t / lw) mod h.
+__global__ void __launch_bounds__(kModThreads) pvrtc_modulate_kernel(const PvrtcParams p) {
   pv_launch_dependents();
   pv_wait_for_previous();  // Morph's A/B colours
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= lw * p.mod_rows) return;
-  const uint32_t bx = t & (lw - 1u), y = (p.mod_row0 + (t >> p.lw_shift)) & (p.height - 1u);
-  // Low-resolution rows/columns this pixel row interpolates between, wrapped (pvrtc_compressor.cc:216-223).
-  const uint32_t top = ((y - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
+  if (t >= lw * p.mod_units) return;
+  const uint32_t bx = t & (lw - 1u), y0 = (2u + kModRows * (p.mod_unit0 + (t >> p.lw_shift))) & (p.height - 1u);
+  // Low-resolution rows/columns these pixel rows interpolate between, wrapped (pvrtc_compressor.cc:216-223).
+  const uint32_t top = ((y0 - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
   const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
-  const uint32_t fy = (y + 2u) & 3u;
-  PvLanes va[3], vb[3];  // vertical blend, shared by the whole row: (4-fy)*top + fy*bottom, not yet divided
+  PvLanes at[3], ab[3], bt[3], bb[3];  // A and B colours of the top / bottom low-resolution row, three columns
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const PvLanes at = pv_split(__ldg(p.low_a + top * lw + col[i])), ab = pv_split(__ldg(p.low_a + bottom * lw + col[i]));
-    const PvLanes bt = pv_split(__ldg(p.low_b + top * lw + col[i])), bb = pv_split(__ldg(p.low_b + bottom * lw + col[i]));
-    va[i].rb = at.rb * (4u - fy) + ab.rb * fy;
-    va[i].ga = at.ga * (4u - fy) + ab.ga * fy;
-    vb[i].rb = bt.rb * (4u - fy) + bb.rb * fy;
-    vb[i].ga = bt.ga * (4u - fy) + bb.ga * fy;
+    const uint2 ct = __ldg(p.low + top * lw + col[i]), cb = __ldg(p.low + bottom * lw + col[i]);
+    at[i] = pv_split(ct.x); ab[i] = pv_split(cb.x); bt[i] = pv_split(ct.y); bb[i] = pv_split(cb.y);
   }
-  const uint4 *row = reinterpret_cast<const uint4 *>(pv_src_row(p, y) + bx * 8);
-  const uint4 u = __ldg(row), v = __ldg(row + 1);
-  const uint32_t px[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
-  uint32_t bits = 0;
 #pragma unroll
-  for (int x = 0; x < 8; ++x) {
-    const int left = x < 4 ? 0 : 1;       // pixels 0..3 sit between columns (bx-1, bx), 4..7 between (bx, bx+1)
-    const uint32_t fx = (x + 4) & 7;
-    // ((8-fx)*V_left + fx*V_right) / 32, V <= 4*255: weights scaled by 8 so the divisor is 256 (lanes < 2^16)
-    const uint32_t ca = pv_blend256(va[left], 64u - 8u * fx, va[left + 1], 8u * fx);
-    const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
-    bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
+  for (uint32_t r = 0; r < kModRows; ++r) {
+    const uint32_t y = (y0 + r) & (p.height - 1u);  // (only the unit that straddles the bottom edge wraps)
+    const uint32_t fy = (y + 2u) & 3u;
+    PvLanes va[3], vb[3];  // vertical blend, shared by the whole row: (4-fy)*top + fy*bottom, not yet divided
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      va[i].rb = at[i].rb * (4u - fy) + ab[i].rb * fy;
+      va[i].ga = at[i].ga * (4u - fy) + ab[i].ga * fy;
+      vb[i].rb = bt[i].rb * (4u - fy) + bb[i].rb * fy;
+      vb[i].ga = bt[i].ga * (4u - fy) + bb[i].ga * fy;
+    }
+    const uint4 *row = reinterpret_cast<const uint4 *>(pv_src_row(p, y) + bx * 8);
+    const uint4 u = __ldg(row), v = __ldg(row + 1);
+    const uint32_t px[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int left = x < 4 ? 0 : 1;       // pixels 0..3 sit between columns (bx-1, bx), 4..7 between (bx, bx+1)
+      const uint32_t fx = (x + 4) & 7;
+      // ((8-fx)*V_left + fx*V_right) / 32, V <= 4*255: weights scaled by 8 so the divisor is 256 (lanes < 2^16)
+      const uint32_t ca = pv_blend256(va[left], 64u - 8u * fx, va[left + 1], 8u * fx);
+      const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
+      bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
+    }
+    p.mod[y * lw + bx] = static_cast<uint16_t>(bits);
   }
-  p.mod[y * lw + bx] = static_cast<uint16_t>(bits);
 }
 
 __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
@@ -164,7 +186,8 @@ __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   }
   bool one_bpp;
   const uint32_t mod_bits = pv_pack_modulation(row, right, &one_bpp);
-  const uint32_t colours = pv_pack_colours(p.low_a[by * lw + bx], p.low_b[by * lw + bx], one_bpp);
+  const uint2 ab = p.low[by * lw + bx];
+  const uint32_t colours = pv_pack_colours(ab.x, ab.y, one_bpp);
   p.dst[pv_z_index(bx, by)] = make_uint2(mod_bits, colours);
 }
 

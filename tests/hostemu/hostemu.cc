@@ -145,7 +145,7 @@ int emu_pvrtc2(const uint8_t *src, uint32_t h, uint32_t w, uint32_t nstripes, ui
   std::vector<uint8_t> scratch(static_cast<size_t>(lw) * lh * 8 + static_cast<size_t>(lw) * h * 2);
   auto run = [&](const icb::PvrtcParams &p) {
     launch((lw * p.morph_rows + 127) / 128, 1, 128, [&] { icb::pvrtc_morph_kernel(p); });
-    launch((lw * p.mod_rows + 255) / 256, 1, 256, [&] { icb::pvrtc_modulate_kernel(p); });
+    launch((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads, 1, icb::kModThreads, [&] { icb::pvrtc_modulate_kernel(p); });
     launch((lw * p.pack_rows + 127) / 128, 1, 128, [&] { icb::pvrtc_pack_kernel(p); });
   };
   if (nstripes <= 1) {

@@ -9,6 +9,7 @@ configuration and the memory system (tests/*_gpu.py, run on the B200 box)."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -241,3 +242,50 @@ def test_mip_chain(emu, codec, fmt):
         level, want = out, ck.oracle_downsample(codec, want, size, size)
         size //= 2
     assert np.array_equal(level, want)
+
+
+def test_device_code_addressing_under_sanitizers():
+    """The same device code built with AddressSanitizer + UBSan and driven through the encoders that index memory in
+    interesting ways: clamp-to-edge windows on ragged images with row padding, CompressAndPad grids, and PVRTC halo
+    stripes that see nothing but a private copy of their own rows (an out-of-stripe read would leave that buffer)."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    ubsan = subprocess.run(["gcc", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+    if not (os.path.isabs(asan) and os.path.isabs(ubsan)):
+        pytest.skip("no sanitizer runtimes in this toolchain")
+    so = os.path.join(HERE, "libhostemu_asan.so")
+    sources = [os.path.join(HERE, f) for f in ("hostemu.cc", "cuda_emulation.h")]
+    sources += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in sources):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize=alignment",
+                        "-fno-sanitize-recover=undefined", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-o", so, os.path.join(HERE, "hostemu.cc")], check=True)
+    script = r"""
+import ctypes as C, sys
+import numpy as np
+lib = C.CDLL(sys.argv[1])
+u8p = C.POINTER(C.c_uint8)
+ptr = lambda a: a.ctypes.data_as(u8p)
+lib.emu_encode4x4.argtypes = [C.c_int, C.c_int, u8p] + [C.c_uint32] * 5 + [C.c_int, C.c_int, u8p]
+lib.emu_pvrtc2.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, u8p]
+lib.emu_decode4x4.argtypes = [C.c_int, u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, C.c_uint32]
+rng = np.random.default_rng(3)
+for codec, nc in ((0, 3), (0, 4), (1, 4), (2, 3)):
+    for h, w, padding, ch, cw in ((1, 1, 0, 1, 1), (5, 7, 3, 5, 7), (9, 13, 0, 16, 20), (33, 67, 5, 64, 128)):
+        pitch = w * nc + padding
+        src = rng.integers(0, 256, h * pitch - padding, dtype=np.uint8)   # the last row carries no padding
+        out = np.zeros(((ch + 3) // 4) * ((cw + 3) // 4) * (16 if codec == 1 else 8), np.uint8)
+        assert lib.emu_encode4x4(codec, nc, ptr(src), h, w, pitch, ch, cw, 0, 2, ptr(out)) == 0
+        if (ch, cw) == (h, w):
+            dec = np.zeros(h * w * (4 if codec == 1 else 3), np.uint8)
+            assert lib.emu_decode4x4(codec, ptr(out), h, w, (w + 3) // 4, 0, ptr(dec), w * (4 if codec == 1 else 3)) == 0
+for n in (8, 16, 64):
+    img = rng.integers(0, 256, n * n * 4, dtype=np.uint8)
+    for stripes in (1, 2, 3, 4, 5):
+        out = np.zeros(n * n // 4, np.uint8)
+        status = lib.emu_pvrtc2(ptr(img), n, n, stripes, ptr(out))
+        assert status in (0, -1), status
+print("clean")
+"""
+    env = dict(os.environ, LD_PRELOAD=asan + ":" + ubsan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0")
+    run = subprocess.run([sys.executable, "-c", script, so], capture_output=True, text=True, env=env, timeout=600)
+    assert run.returncode == 0 and run.stdout.strip().endswith("clean"), run.stderr[-3000:]
