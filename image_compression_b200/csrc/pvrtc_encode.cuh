@@ -194,9 +194,9 @@ __device__ __forceinline__ uint32_t pv_pack_modulation(const uint32_t (&row)[5],
     inter += __popc((row[y] ^ (row[y] >> 1)) & 0x5555u);  // values 1 and 2 have unequal bits
     // (sic) the reference's "horizontal" count compares with the row BELOW, "vertical" with the pixel to the RIGHT
     horizontal = __vsadu4(lo_bytes[y], lo_bytes[y + 1]) + __vsadu4(hi_bytes[y], hi_bytes[y + 1]) + horizontal;
-    const uint32_t shifted = (row[y] >> 2) | (right[y] << 14);  // pixel x+1 in the place of pixel x
-    vertical = __vsadu4(lo_bytes[y], pv_fields_to_bytes(shifted & 0xffu)) +
-               __vsadu4(hi_bytes[y], pv_fields_to_bytes(shifted >> 8)) + vertical;
+    // pixel x+1 in the place of pixel x: the byte-expanded row moved down one byte, the right neighbour's value on top
+    const uint32_t next_lo = __byte_perm(lo_bytes[y], hi_bytes[y], 0x4321), next_hi = __byte_perm(hi_bytes[y], right[y], 0x4321);
+    vertical = __vsadu4(lo_bytes[y], next_lo) + __vsadu4(hi_bytes[y], next_hi) + vertical;
   }
   enum { k1Bpp, kAverage4, kVertical, kHorizontal } mode;
   if (inter <= 4u)
