@@ -244,6 +244,112 @@ def test_mip_chain(emu, codec, fmt):
     assert np.array_equal(level, want)
 
 
+# ---- exhaustive and large sweeps: the emulated device code is fast enough to leave random sampling behind ----------
+
+def _blocks_to_plane(blocks16, cols=1024):
+    """(n, 16) block rows -> a (4*rows, 4*cols) plane whose 4x4 block (br, bc) is blocks16[br * cols + bc]."""
+    n = len(blocks16)
+    rows = (n + cols - 1) // cols
+    padded = np.concatenate([blocks16, np.tile(blocks16[:1], (rows * cols - n, 1))])
+    return np.ascontiguousarray(padded.reshape(rows, cols, 4, 4).transpose(0, 2, 1, 3).reshape(rows * 4, cols * 4))
+
+
+def _families(make):
+    out = []
+
+    def family(prefix, vals, prefix_last=False):
+        k = 16 - len(prefix)
+        vals = np.asarray(vals, np.uint8)
+        vals = np.concatenate([vals, np.full((-len(vals)) % k, vals[0], np.uint8)]).reshape(-1, k)
+        pre = np.tile(np.asarray(prefix, np.uint8), (len(vals), 1))
+        out.append(np.concatenate([vals, pre] if prefix_last else [pre, vals], axis=1))
+
+    make(family)
+    return np.concatenate(out)
+
+
+def test_dxt5_alpha_search_every_mode_endpoint_pair_and_alpha(emu):
+    """EXHAUSTIVE for the alpha half: every (6-/8-alpha mode, a0, a1) the statistics can produce, with every alpha value
+    between the endpoints (and 0 / 255 where the mode has them as explicit candidates) -- 536,064 blocks.  The crossing
+    table was verified as a Python model when it was generated (tools/gen_dxt5_alpha_table.py); this runs the device
+    function itself (packed-half statistics, table look-up, seven-crossing search, bit packing)."""
+    def make(family):
+        for lo in range(1, 255):
+            for hi in range(lo, 255):
+                inner = np.arange(lo, hi + 1)
+                family([lo, hi], inner)                    # 8-alpha mode: a0 = hi, a1 = lo (lo == hi: the '<=' branch)
+                family([0, 0, lo, hi], inner)              # 6-alpha mode through two zeros: a0 = lo, a1 = hi
+                if (lo + hi) % 7 == 0:                     # the other ways into 6-alpha mode, thinned
+                    family([255, 255, lo, hi], inner)
+                    family([0, 255, 255, lo, hi], inner)
+        for hi in range(1, 255):
+            family([0, hi], np.arange(1, hi + 1))          # exactly one zero: a1 = 0
+            family([hi, 255], np.arange(hi, 255))          # exactly one 255: a0 = 255
+        family([0, 255], np.arange(1, 255))
+        family([0, 0, 255, 255], [0, 255])                 # nothing but extremes: 0 / 255 endpoints
+    plane = _blocks_to_plane(_families(make))
+    img = np.empty(plane.shape + (4,), np.uint8)
+    img[..., :3] = (90, 160, 30)
+    img[..., 3] = plane
+    h, w = plane.shape
+    assert np.array_equal(encode(emu, 1, 4, img.ravel(), h, w), ck.oracle_dxt(ck.RGBA, img.ravel(), h, w))
+
+
+@pytest.mark.parametrize("fmt", [ck.RGB, ck.BGR])
+def test_dxt1_colour_search_every_endpoint_pair_on_an_axis(emu, fmt):
+    """EXHAUSTIVE along single colour axes: every pair of extreme values lo <= hi with every value in between, the
+    extremes placed first or last in raster order (first-minimum / first-maximum rules), on the gray axis, on each
+    single channel and on a skewed axis -- 217,645 blocks per axis, under both answers of the warp vote."""
+    def make(family):
+        for lo in range(256):
+            for hi in range(lo, 256):
+                family([lo, hi] if (lo + hi) & 1 else [hi, lo], np.arange(lo, hi + 1), prefix_last=bool(lo & 1))
+    plane = _blocks_to_plane(_families(make)).astype(np.uint16)
+    h, w = plane.shape
+    swap = 1 if fmt == ck.BGR else 0
+    for weights in ((256, 256, 256), (256, 0, 0), (0, 256, 0), (0, 0, 256), (0, 128, 256), (256, 85, 170)):
+        img = np.ascontiguousarray(np.stack([(plane * k) >> 8 for k in weights], -1).astype(np.uint8))
+        want = ck.oracle_dxt(fmt, img.ravel(), h, w)
+        for vote in VOTES:
+            assert np.array_equal(encode(emu, 0, 3, img.ravel(), h, w, swap=swap, vote=vote), want), (weights, vote)
+
+
+def test_dxt_soak_small_palettes(emu):
+    """Two million blocks whose 16 pixels come from palettes of 1-4 nearby colours: equal luminances with different
+    colours, constant blocks (the endpoint table path), crossed and coinciding interpolants -- the general path of the
+    colour search and its tie rules, which uniform random pixels almost never reach."""
+    rng = np.random.default_rng(77)
+    n = 2_000_000
+    base = rng.integers(0, 256, (n, 1, 4), dtype=np.int16)
+    spread = rng.choice(np.array([0, 1, 2, 3, 8, 40], np.int16), (n, 1, 1))
+    palette = np.clip(base + rng.integers(-1, 2, (n, 4, 4), dtype=np.int16) * spread, 0, 255).astype(np.uint8)
+    pick = rng.integers(0, 4, (n, 16)) % rng.integers(1, 5, (n, 1))
+    blocks = np.take_along_axis(palette, pick[..., None].astype(np.intp), axis=1)          # (n, 16, 4)
+    cols = 2000
+    img = np.ascontiguousarray(blocks.reshape(n // cols, cols, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(n // cols * 4, cols * 4, 4))
+    h, w = img.shape[:2]
+    want1 = ck.oracle_dxt1_rgba(img.ravel(), h, w)
+    for vote in VOTES:
+        assert np.array_equal(encode(emu, 0, 4, img.ravel(), h, w, vote=vote), want1), vote
+    quarter = np.ascontiguousarray(img[: h // 4])
+    assert np.array_equal(encode(emu, 1, 4, quarter.ravel(), h // 4, w), ck.oracle_dxt(ck.RGBA, quarter.ravel(), h // 4, w))
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3])
+def test_etc1_soak_clamping_and_ties(emu, strategy):
+    """Sixty thousand blocks per strategy near black and near white (every codeword clamps), on flat and two-level
+    content (ties between codewords and between the two orientations: '<=' keeps the unflipped block)."""
+    rng = np.random.default_rng(78 + strategy)
+    n = 60_000
+    centre = rng.choice(np.array([0, 3, 16, 60, 128, 200, 240, 252, 255], np.int16), (n, 1, 1))
+    spread = rng.choice(np.array([0, 1, 2, 6, 20, 90], np.int16), (n, 1, 1))
+    blocks = np.clip(centre + rng.integers(-1, 2, (n, 16, 3), dtype=np.int16) * spread + rng.integers(-2, 3, (n, 1, 3), dtype=np.int16), 0, 255)
+    cols = 500
+    img = np.ascontiguousarray(blocks.astype(np.uint8).reshape(n // cols, cols, 4, 4, 3).transpose(0, 2, 1, 3, 4).reshape(n // cols * 4, cols * 4, 3))
+    h, w = img.shape[:2]
+    assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy), ck.oracle_etc1(strategy, img.ravel(), h, w))
+
+
 def test_device_code_addressing_under_sanitizers():
     """The same device code built with AddressSanitizer + UBSan and driven through the encoders that index memory in
     interesting ways: clamp-to-edge windows on ragged images with row padding, CompressAndPad grids, and PVRTC halo
