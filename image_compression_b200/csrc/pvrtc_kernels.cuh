@@ -3,10 +3,12 @@
 // Encode :551-580).
 //
 // Three kernels, all coalesced and small enough to stay in the instruction cache:
-//   pvrtc_morph_kernel     one thread per 8x4 block -> bit-reduced A and B colours (two w/8 x h/4 images, scratch)
-//   pvrtc_modulate_kernel  one thread per 8-pixel row segment: bilinear upscale of A and B (toroidal), modulation
-//                          choice per pixel, eight 2-bit values packed into one uint16 of scratch.  The
-//                          reference's byte-per-pixel modulation image becomes 2 bits per pixel and stays in L2.
+//   pvrtc_morph_kernel     one thread per 8x4 block -> bit-reduced A and B colours (one (A, B) pair per block: the
+//                          reference's two w/8 x h/4 images, interleaved, in scratch)
+//   pvrtc_modulate_kernel  one thread per 8-pixel segment of kModRows consecutive rows: bilinear upscale of A and B
+//                          (toroidal), modulation choice per pixel, eight 2-bit values packed into one uint16 of
+//                          scratch.  The reference's byte-per-pixel modulation image becomes 2 bits per pixel and
+//                          stays in L2.
 //   pvrtc_pack_kernel      one thread per block: its 4 row words plus the wrapped column to the right and row
 //                          below (all the mode decision needs), mode + bit packing, store at the Z-order slot.
 #pragma once
