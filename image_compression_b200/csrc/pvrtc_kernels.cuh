@@ -94,7 +94,10 @@ __device__ __forceinline__ const uint32_t *pv_src_row(const PvrtcParams &p, uint
 // its launch and prologue at once (launch_dependents) and waits for the kernel before it to be complete, its memory
 // flushed, before its own first global access (griddepcontrol.wait) -- only the launch latency overlaps, which is what
 // separates three 10-35 us kernels.  Morph waits too: it may follow the kernel that produced the image, and it
-// overwrites the A/B colours the previous encode's Pack is still reading.
+// overwrites the A/B colours the previous encode's Pack is still reading.  Because a programmatically launched kernel
+// is alive before its predecessor has finished writing, every global load in these kernels is a plain load: the
+// non-coherent path (__ldg) is defined only for data that stays read-only for the kernel's whole lifetime, and both the
+// image (written by whatever precedes Morph in the stream) and the scratch images (written by the kernel before) are not.
 #ifdef ICB_HOST_EMULATION  // tests/hostemu only: kernels run one after another on the CPU, nothing to order
 __device__ __forceinline__ void pv_launch_dependents() {}
 __device__ __forceinline__ void pv_wait_for_previous() {}
@@ -118,13 +121,13 @@ __global__ void __launch_bounds__(128, 8) pvrtc_morph_kernel(const PvrtcParams p
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
     const uint4 *row = reinterpret_cast<const uint4 *>(origin + static_cast<size_t>(y) * p.width);
-    const uint4 u = __ldg(row), v = __ldg(row + 1);
+    const uint4 u = row[0], v = row[1];
     px[8 * y + 0] = u.x; px[8 * y + 1] = u.y; px[8 * y + 2] = u.z; px[8 * y + 3] = u.w;
     px[8 * y + 4] = v.x; px[8 * y + 5] = v.y; px[8 * y + 6] = v.z; px[8 * y + 7] = v.w;
   }
-  auto fetch = [&](uint32_t j) { return __ldg(origin + static_cast<size_t>(j >> 3) * p.width + (j & 7u)); };
+  auto fetch = [&](uint32_t j) { return origin[static_cast<size_t>(j >> 3) * p.width + (j & 7u)]; };
   uint32_t ca, cb;
-  pv_block_extremes(px, __ldg(p.first_pixel), p.key_scale, fetch, &ca, &cb);
+  pv_block_extremes(px, *p.first_pixel, p.key_scale, fetch, &ca, &cb);
   p.low[by * lw + bx] = make_uint2(ca, cb);
 }
 
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kModThreads) pvrtc_modulate_kernel(const Pvrtc
   PvLanes at[3], ab[3], bt[3], bb[3];  // A and B colours of the top / bottom low-resolution row, three columns
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const uint2 ct = __ldg(p.low + top * lw + col[i]), cb = __ldg(p.low + bottom * lw + col[i]);
+    const uint2 ct = p.low[top * lw + col[i]], cb = p.low[bottom * lw + col[i]];
     at[i] = pv_split(ct.x); ab[i] = pv_split(cb.x); bt[i] = pv_split(ct.y); bb[i] = pv_split(cb.y);
   }
 #pragma unroll
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kModThreads) pvrtc_modulate_kernel(const Pvrtc
       vb[i].ga = bt[i].ga * (4u - fy) + bb[i].ga * fy;
     }
     const uint4 *row = reinterpret_cast<const uint4 *>(pv_src_row(p, y) + bx * 8);
-    const uint4 u = __ldg(row), v = __ldg(row + 1);
+    const uint4 u = row[0], v = row[1];
     const uint32_t px[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
     uint32_t bits = 0;
 #pragma unroll
