@@ -306,8 +306,17 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t addr, uint3
   return old;
 }
 
+// Resident CTAs per SM the DXT5 build of the ring kernel is compiled for.  4 = 64 registers (the measured default).
+// Experiment prepared for the next GPU visit (tools/build_variants.sh dxt5x5 "-DICB_DXT5_RING_MIN_CTAS=5"): 5 = 48
+// registers, which ptxas reaches with 8 bytes of spill and 16 more instructions (2040 instead of 2024 static); the
+// launcher's occupancy query then runs 40 warps per SM instead of 32 for a kernel that leaves 25 % of its issue slots empty.
+#ifndef ICB_DXT5_RING_MIN_CTAS
+#define ICB_DXT5_RING_MIN_CTAS 4
+#endif
+
 template <int kCodec, int kNcomp, int kTmaStages>
-__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads, kCodec == kCodecEtc1 ? 3 : 4)
+__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
+                                  kCodec == kCodecEtc1 ? 3 : (kCodec == kCodecDxt5 ? ICB_DXT5_RING_MIN_CTAS : 4))
     encode4x4_ring_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                           uint32_t num_tiles) {
   using Shape = TileShape<kNcomp>;

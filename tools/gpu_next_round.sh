@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU visit of the next round: the experiments this round prepared on the CPU but could not measure.
+#   (in the container)  tools/build_variants.sh dxt5x5 "-DICB_DXT5_RING_MIN_CTAS=5"
+#   (under gpurun)      bash tools/gpu_next_round.sh <tag>
+# 1. DXT5 ring kernel compiled for five resident CTAs per SM (48 registers, 8 bytes of spill; block4x4_kernels.cuh):
+#    parity of the variant library through the whole 4x4 GPU suite, then A/B against the product build.
+TAG=${1:-nr1}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+V=$PWD/image_compression_b200/lib/variants
+if [ -f $V/libicb200_dxt5x5.so ]; then
+  ICB200_LIB=$V/libicb200_dxt5x5.so timeout 300 python -m pytest tests -x -q -m gpu -k "not pvrtc and not multigpu" > $OUT/pytest_dxt5x5.log 2>&1
+  echo "variant parity exit $?"; tail -2 $OUT/pytest_dxt5x5.log
+  bash tools/gpu_ab.sh $TAG dxt5_rgba8 base dxt5x5:ICB200_LIB=$V/libicb200_dxt5x5.so base2 dxt5x5b:ICB200_LIB=$V/libicb200_dxt5x5.so
+else
+  echo "build the variant first: tools/build_variants.sh dxt5x5 \"-DICB_DXT5_RING_MIN_CTAS=5\""
+fi
