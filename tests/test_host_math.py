@@ -59,3 +59,54 @@ def test_line_search_equals_first_strict_minimum():
             L = [base + rng.choice([0, 0, 1, 2, 50, 51, 100]) for _ in range(4)]
         l = rng.randint(max(0, min(L) - 3), min(3315, max(L) + 3))
         assert line_search(L, l, rng.randint(0, 15)) == direct_first_min(L, l), (L, l)
+
+
+# ---- addressing identities of the TMA drivers (block4x4_kernels.cuh); the host emulation does not run those kernels ----
+
+def test_tile_window_offset_trick():
+    """fetch(i) in an RGBA tile: (i >> 2) rows of 1024 bytes + (i & 3) pixels of 4 bytes == (i * 0x104) & 0xc0c."""
+    for i in range(16):
+        assert (i * 0x104) & 0xc0c == (i >> 2) * 1024 + (i & 3) * 4
+
+
+def test_rgb888_row_words_unpack():
+    """Four packed RGB pixels from three little-endian words with two funnel shifts (the TMA consumers' form)."""
+    import random
+    rng = random.Random(3)
+    for _ in range(2000):
+        b = [rng.randrange(256) for _ in range(12)]
+        w0, w1, w2 = (int.from_bytes(bytes(b[4 * k:4 * k + 4]), "little") for k in range(3))
+        funnel = lambda lo, hi, s: (((hi << 32) | lo) >> s) & 0xffffffff
+        px = [w0 & 0xffffff, funnel(w0, w1, 24) & 0xffffff, funnel(w1, w2, 16) & 0xffffff, w2 >> 8]
+        assert px == [b[3 * k] | b[3 * k + 1] << 8 | b[3 * k + 2] << 16 for k in range(4)]
+
+
+def test_persistent_tile_walk_and_shifted_last_tile():
+    """A CTA walks tiles blockIdx, blockIdx + grid, ... as (tx, ty) without dividing; the last tile of a row / column is
+    shifted back to end at col1 / row1.  Every block of [row0,row1) x [col0,col1) must be covered, none outside."""
+    import random
+    rng = random.Random(5)
+    BX, BY = 64, 4
+    for _ in range(300):
+        col0, row0 = 0, rng.randrange(0, 50)
+        ncols, nrows = rng.randrange(BX, 700), rng.randrange(BY, 60)
+        col1, row1 = col0 + ncols, row0 + nrows
+        tiles_x, tiles_y = (ncols + BX - 1) // BX, (nrows + BY - 1) // BY
+        num_tiles, grid = tiles_x * tiles_y, rng.randrange(1, 40)
+        covered = set()
+        step_y, step_x = divmod(grid, tiles_x)
+        for cta in range(min(grid, num_tiles)):
+            ty, tx = divmod(cta, tiles_x)
+            tile = cta
+            while tile < num_tiles:
+                assert (ty, tx) == divmod(tile, tiles_x)
+                bc, br = min(col0 + tx * BX, col1 - BX), min(row0 + ty * BY, row1 - BY)
+                assert bc >= col0 and br >= row0
+                covered.update((r, c) for r in range(br, br + BY) for c in range(bc, bc + BX))
+                tile += grid
+                tx += step_x
+                ty += step_y
+                if tx >= tiles_x:
+                    tx -= tiles_x
+                    ty += 1
+        assert covered == {(r, c) for r in range(row0, row1) for c in range(col0, col1)}
