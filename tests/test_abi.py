@@ -76,3 +76,25 @@ def test_argument_validation_needs_no_device(icb):
     assert L.icb_compress_host(icb.CODEC_ETC1, icb.BGR, 4, 4, 0, 0, 0, 2, src.ctypes.data, out.ctypes.data, 8) == -1
     assert L.icb_compress_host(icb.CODEC_DXT5, icb.RGB, 4, 4, 0, 0, 0, 2, src.ctypes.data, out.ctypes.data, 16) == -1
     assert b"" != L.icb_last_error()
+
+
+def test_host_emulation_macro_is_test_only():
+    """ICB_HOST_EMULATION (device headers compiled for the CPU) is defined by tests/hostemu alone: no build recipe of
+    the product sets it, and nothing in the package outside the guarded #ifdef branches mentions it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    recipes = ["image_compression_b200/csrc/Makefile", "image_compression_b200/cpp/Makefile", "oracle/Makefile",
+               "tools/build_variants.sh", "__graft_entry__.py", "bench.py", "image_compression_b200/binding.py"]
+    for rel in recipes:
+        assert "ICB_HOST_EMULATION" not in open(os.path.join(root, rel)).read(), rel
+    definers = []
+    for base, _, files in os.walk(root):
+        if any(part in base for part in (".git", "gpurun_out", "__pycache__")):
+            continue
+        for f in files:
+            if f.endswith((".h", ".cuh", ".cu", ".cc", ".c", ".cpp")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                if re.search(r"^\s*#\s*define\s+ICB_HOST_EMULATION", text, re.M):
+                    definers.append(os.path.relpath(os.path.join(base, f), root))
+    assert definers == ["tests/hostemu/cuda_emulation.h"], definers
