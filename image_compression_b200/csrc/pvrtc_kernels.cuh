@@ -132,13 +132,18 @@ __global__ void __launch_bounds__(128, 8) pvrtc_morph_kernel(const PvrtcParams p
 }
 
 // Thread t handles pixels 8*bx .. 8*bx+7 of rows y0 .. y0+kModRows-1, y0 = 2 + kModRows * (mod_unit0 + t / lw) mod h.
-// Launch bounds as a build macro for A/B runs (tools/gpu_next_round.sh): with no minimum-CTA argument ptxas takes 80
-// registers (6 CTAs = 24 warps per SM); "kModThreads, 7" gives 72 registers without spills, "kModThreads, 8" 64 with
-// 32 bytes of spill.  Unmeasured so far.
-#ifndef ICB_PVRTC_MOD_BOUNDS
-#define ICB_PVRTC_MOD_BOUNDS kModThreads
+// Resident CTAs per SM to compile for, as a build macro for A/B runs (tools/gpu_next_round.sh).  0 = no minimum: ptxas
+// takes 80 registers (6 CTAs = 24 warps per SM); 7 gives 72 registers without spills, 8 gives 64 with 32 bytes of
+// spill.  Unmeasured so far.
+#ifndef ICB_PVRTC_MOD_MIN_CTAS
+#define ICB_PVRTC_MOD_MIN_CTAS 0
 #endif
-__global__ void __launch_bounds__(ICB_PVRTC_MOD_BOUNDS) pvrtc_modulate_kernel(const PvrtcParams p) {
+#if ICB_PVRTC_MOD_MIN_CTAS > 0
+#define ICB_PVRTC_MOD_BOUNDS __launch_bounds__(kModThreads, ICB_PVRTC_MOD_MIN_CTAS)
+#else
+#define ICB_PVRTC_MOD_BOUNDS __launch_bounds__(kModThreads)
+#endif
+__global__ void ICB_PVRTC_MOD_BOUNDS pvrtc_modulate_kernel(const PvrtcParams p) {
   pv_launch_dependents();
   pv_wait_for_previous();  // Morph's A/B colours
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU visit of the next round: the experiments this round prepared on the CPU but could not measure.
-#   (in the container)  tools/build_variants.sh dxt5x5 "-DICB_DXT5_RING_MIN_CTAS=5" mod7 "-DICB_PVRTC_MOD_BOUNDS=kModThreads,7" \
-#                                               mod8 "-DICB_PVRTC_MOD_BOUNDS=kModThreads,8"
+#   (in the container)  tools/build_variants.sh dxt5x5 "-DICB_DXT5_RING_MIN_CTAS=5" mod7 "-DICB_PVRTC_MOD_MIN_CTAS=7" \
+#                                               mod8 "-DICB_PVRTC_MOD_MIN_CTAS=8"
 #   (under gpurun)      bash tools/gpu_next_round.sh <tag>
 # 1. DXT5 ring kernel compiled for five resident CTAs per SM (48 registers, 8 bytes of spill; block4x4_kernels.cuh):
 #    parity of the variant library through the whole 4x4 GPU suite, then A/B against the product build.
