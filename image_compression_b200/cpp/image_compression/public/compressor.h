@@ -28,17 +28,19 @@ class Compressor {
   virtual bool IsValidCompressedImage(const CompressedImage &image) = 0;
   virtual size_t ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) = 0;
 
-  // The hot path (GPU).
+  // Declaration order IS the vtable layout and follows the reference header line for line
+  // (public/compressor.h:52,61,68,77,85,95,105,114,125,134), so that an object compiled against the reference's
+  // headers dispatches into this library correctly (tests/test_cpp_api.py::test_vtable_layout_matches_reference).
+  // Compress and CompressAndPad are the hot path (GPU).
   virtual bool Compress(CompressedImage::Format format, uint32 height, uint32 width, uint32 padding_bytes_per_row,
                         const uint8 *buffer, CompressedImage *image) = 0;
-  virtual bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,
-                              uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,
-                              CompressedImage *padded_image) = 0;
-
   virtual bool Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) = 0;
   virtual bool Downsample(const CompressedImage &image, CompressedImage *downsampled_image) = 0;
   virtual bool Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width,
                    CompressedImage *padded_image) = 0;
+  virtual bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,
+                              uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,
+                              CompressedImage *padded_image) = 0;
   virtual bool CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,
                                 CompressedImage *image) = 0;
   virtual bool CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height,
@@ -55,13 +57,13 @@ class Compressor {
   size_t ComputeCompressedDataSize(CompressedImage::Format format, uint32 height, uint32 width) override;               \
   bool Compress(CompressedImage::Format format, uint32 height, uint32 width, uint32 padding_bytes_per_row,              \
                 const uint8 *buffer, CompressedImage *image) override;                                                  \
-  bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,                \
-                      uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,                           \
-                      CompressedImage *padded_image) override;                                                          \
   bool Decompress(const CompressedImage &image, std::vector<uint8> *decompressed_buffer) override;                      \
   bool Downsample(const CompressedImage &image, CompressedImage *downsampled_image) override;                           \
   bool Pad(const CompressedImage &image, uint32 padded_height, uint32 padded_width, CompressedImage *padded_image)      \
       override;                                                                                                         \
+  bool CompressAndPad(CompressedImage::Format format, uint32 height, uint32 width, uint32 padded_height,                \
+                      uint32 padded_width, uint32 padding_bytes_per_row, const uint8 *buffer,                           \
+                      CompressedImage *padded_image) override;                                                          \
   bool CreateSolidImage(CompressedImage::Format format, uint32 height, uint32 width, const uint8 *color,                \
                         CompressedImage *image) override;                                                               \
   bool CopySubimage(const CompressedImage &image, uint32 start_row, uint32 start_column, uint32 height, uint32 width,   \

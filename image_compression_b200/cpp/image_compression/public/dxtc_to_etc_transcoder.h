@@ -1,7 +1,8 @@
 // In-place DXT1 -> ETC1 transcode (reference: image_compression/public/dxtc_to_etc_transcoder.h:24).
-// Runs on the GPU (icb_transcode_dxt1_to_etc1: DXT1 decode -> ETC1 heuristic encode, one thread per block).  The
-// reference returns void; this build returns false if the CUDA call failed (the image is untouched then).  The
-// mangled name does not include the return type, so callers compiled against the reference header still link.
+// Runs on the GPU (icb_transcode_dxt1_to_etc1: DXT1 decode -> ETC1 heuristic encode, one thread per block).  Same
+// signature as the reference (void).  The reference cannot fail; this build can (no CUDA device): the image is left
+// untouched then and icb_last_error() (include/icb200.h) has the reason.  TranscodeDxt1ToEtc1Checked is an extension
+// of this build that reports it.
 #ifndef IMAGE_COMPRESSION_PUBLIC_DXTC_TO_ETC_TRANSCODER_H_
 #define IMAGE_COMPRESSION_PUBLIC_DXTC_TO_ETC_TRANSCODER_H_
 
@@ -9,7 +10,8 @@
 
 namespace image_codec_compression {
 
-bool TranscodeDxt1ToEtc1(CompressedImage *image);
+void TranscodeDxt1ToEtc1(CompressedImage *image);
+bool TranscodeDxt1ToEtc1Checked(CompressedImage *image);
 
 }  // namespace image_codec_compression
 

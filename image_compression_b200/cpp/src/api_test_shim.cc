@@ -96,8 +96,9 @@ __attribute__((visibility("default"))) long icapi_block_op(int op, int codec, in
     if (op == 1) ok = comp->Pad(in, a, b, &out);
     if (op == 2) ok = comp->CopySubimage(in, a, b, c, d, &out);
     if (op == 4) {
-      ok = TranscodeDxt1ToEtc1(&in);
-      if (ok) out.Duplicate(in);
+      TranscodeDxt1ToEtc1(&in);  // void, as in the reference; a failed call leaves the DXT1 blocks in place,
+      ok = true;                 // which the caller's comparison with the expected ETC1 blocks then reports
+      out.Duplicate(in);
     }
   }
   if (!ok) return 0;
@@ -110,6 +111,58 @@ __attribute__((visibility("default"))) long icapi_block_op(int op, int codec, in
     meta[6] = static_cast<unsigned>(m.compressor_name.size());
   }
   return static_cast<long>(out.GetDataSize());
+}
+// Calls every one of the ten Compressor virtuals through a base-class pointer, in vtable order, on one small image.
+// Results are appended to dst as segments; seg_sizes[k] receives the byte count of call k's result (for the three
+// calls that return no image: one byte holding the bool, or the eight bytes of the size).  Returns a bit mask of the calls
+// that succeeded (0x3ff when all ten did), or -1 when dst is too small.  tests/test_cpp_api.py builds this file twice
+// -- against this build's headers and against the reference's own headers -- and requires identical output from
+// both: that is the check that the vtable layout (declaration order in compressor.h) is link-compatible.
+__attribute__((visibility("default"))) long icapi_all_virtuals(int codec, int format, unsigned h, unsigned w,
+                                                               const unsigned char *src, unsigned char *dst,
+                                                               size_t dst_cap, unsigned *seg_sizes) {
+  DxtcCompressor dxt;
+  EtcCompressor etc;
+  Compressor *c = codec == 2 ? static_cast<Compressor *>(&etc) : static_cast<Compressor *>(&dxt);
+  const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);
+  size_t used = 0;
+  long mask = 0;
+  bool overflow = false;
+  auto put = [&](int k, bool ok, const void *data, size_t n) {
+    seg_sizes[k] = 0;
+    if (!ok) return;
+    if (used + n > dst_cap) { overflow = true; return; }
+    std::memcpy(dst + used, data, n);
+    used += n;
+    seg_sizes[k] = static_cast<unsigned>(n);
+    mask |= 1L << k;
+  };
+  auto put_image = [&](int k, bool ok, const CompressedImage &im) {
+    put(k, ok && im.GetData() != NULL, im.GetData(), ok ? im.GetDataSize() : 0);
+  };
+  const unsigned char yes = c->SupportsFormat(f) ? 1 : 0;
+  put(0, true, &yes, 1);
+  CompressedImage image;
+  const bool compressed = c->Compress(f, h, w, 0, src, &image);
+  const unsigned char valid = compressed && c->IsValidCompressedImage(image) ? 1 : 0;
+  put(1, true, &valid, 1);
+  const size_t size = c->ComputeCompressedDataSize(f, h, w);
+  put(2, true, &size, sizeof(size));
+  put_image(3, compressed, image);
+  if (compressed) {
+    std::vector<uint8> pixels;
+    const bool ok4 = c->Decompress(image, &pixels);
+    put(4, ok4, pixels.data(), ok4 ? pixels.size() : 0);
+    CompressedImage half, padded, sub;
+    put_image(5, c->Downsample(image, &half), half);
+    put_image(6, c->Pad(image, h + 8, w + 12, &padded), padded);
+    CompressedImage both;
+    put_image(7, c->CompressAndPad(f, h, w, h + 8, w + 12, 0, src, &both), both);
+    CompressedImage solid;
+    put_image(8, c->CreateSolidImage(f, h, w, src, &solid), solid);
+    put_image(9, c->CopySubimage(image, 4, 4, 8, 8, &sub), sub);
+  }
+  return overflow ? -1 : mask;
 }
 __attribute__((visibility("default"))) size_t icapi_size(int codec, int format, unsigned h, unsigned w) {
   const CompressedImage::Format f = static_cast<CompressedImage::Format>(format);

@@ -328,12 +328,14 @@ bool PvrtcCompressor::CopySubimage(const CompressedImage &, uint32, uint32, uint
 // internal/dxtc_to_etc_transcoder.cc:29-40: every 8 bytes of the image are read as a DXT1 block and overwritten with
 // the ETC1 (heuristic strategy) encoding of its 16 decoded pixels.  Like the reference, the metadata is left alone.
 // The reference returns void; this build returns whether the GPU call succeeded (the data is untouched if not).
-bool TranscodeDxt1ToEtc1(CompressedImage *image) {
+bool TranscodeDxt1ToEtc1Checked(CompressedImage *image) {
   if (!image || !image->GetMutableData()) return false;
   const size_t bytes = image->GetDataSize() / 8 * 8;
   if (bytes == 0) return true;
   return icb_blockop_host(ICB_OP_TRANSCODE, ICB_CODEC_DXT1, ICB_ETC_HEURISTIC, NULL, image->GetData(), bytes,
                           image->GetMutableData(), bytes) == ICB_OK;
 }
+
+void TranscodeDxt1ToEtc1(CompressedImage *image) { (void)TranscodeDxt1ToEtc1Checked(image); }
 
 }  // namespace image_codec_compression

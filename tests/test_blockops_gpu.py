@@ -180,9 +180,12 @@ def test_large_downsample_and_transcode(icb):
 _u8p = C.POINTER(C.c_uint8)
 
 
-@pytest.fixture(scope="module")
-def api():
-    path = os.path.join(ROOT, "image_compression_b200", "lib", "libicb_api_test.so")
+@pytest.fixture(scope="module", params=["libicb_api_test.so", "libicb_refabi_test.so"])
+def api(request):
+    # second build: the same doorway compiled against the reference's own headers (see tests/test_cpp_api.py)
+    path = os.path.join(ROOT, "image_compression_b200", "lib", request.param)
+    if not os.path.exists(path) and "refabi" in request.param and not os.path.isdir("/root/reference"):
+        pytest.skip("%s was not built (no /root/reference where build() ran)" % request.param)
     lib = C.CDLL(path)
     lib.icapi_block_op.restype = C.c_long
     lib.icapi_block_op.argtypes = [C.c_int] * 4 + [C.c_uint] * 6 + [_u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(C.c_uint32)]
