@@ -3,16 +3,25 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dxt1_rgba8] [--impl reference]
 
-Default workload (config.workload): DXT1 encode of an 8192x8192 synthetic RGBA8 image (BASELINE.json configs[1]),
-input resident in HBM.  One "step" = one pass of the encoder over the image (one kernel launch).  At N > 1
-(torchrun, one rank per GPU) the image grows to 8192 x (8192*N) and is sharded by block-row stripes -- fixed work
-per GPU, "scaling": "weak", no data-path collective; the NCCL gather of the packed stream the north star names is
-timed separately and reported under "gather".  Prints ONE JSON line (rank 0).
+Default workload (config.workload): DXT1 encode of ONE 8192x8192 synthetic RGBA8 image (BASELINE.json configs[1]),
+input resident in HBM.  One "step" = one pass of the encoder over the image.
 
-Keys beyond the base contract: "roofline" (dominant kernel vs MEASURED_PEAKS.json HBM copy bandwidth),
-"cpu_baseline" (the unmodified reference, or the oracle port, timed on this box's host cores on a bounded sample),
-"e2e" (same metric through icb_compress_host with pinned host buffers: H2D + kernels + D2H inside the timed region),
-"clocks", "gpu_launches".
+N = 1   one kernel launch per step; `value` = 8192^2 / step time.
+N > 1   (torchrun, one rank per GPU) the SAME single image, sharded by block-row stripes: rank r holds and encodes the
+        block rows icb_stripe_partition gives it and its encode kernel stores the blocks straight into rank 0's buffer
+        over NVLink (peer-mapped output, sharding.PeerStream) -- the north star's "gather of the packed block stream"
+        fused into the kernels.  The delivery is INSIDE the timed region: `value` = 8192^2 / (time until the whole
+        stream sits on rank 0), "scaling": "strong".  The job is bounded by rank 0's NVLink ingress from N = 4 up
+        ("delivery" key: bytes into the root / time against 900 GB/s); kernel-only, NCCL-gather and weak-scaling
+        figures are reported beside it under their own keys, not in `value`.
+        PVRTC does not shard through its public shape rules (square power-of-two images): N replicas, "weak".
+
+Keys beyond the base contract: "roofline" (dominant kernel vs MEASURED_PEAKS.json HBM copy bandwidth), "parity" (the
+run's own device output byte-compared with the reference CPU encoder's output of the same input), "cpu_baseline"
+(N = 1: the unmodified reference, or the oracle port, timed on this box's host cores on a bounded sample), "e2e" (ONE
+image through the host-buffer API with pinned buffers: H2D + kernels + D2H inside the timed region; at N > 1 rank 0
+makes one icb_ctx_compress_host call that spreads the image over all N GPUs), "other_workloads" (N = 1: compact records
+for the other BASELINE configurations and for structured image content), "clocks", "gpu_launches".
 
 --impl reference times the reference's own CPU implementation (oracle/_ref when it was built, else the oracle
 port) with all host threads on the same metric; rank 0 only.
@@ -30,14 +39,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
-    # name: (codec, format, ncomp, image size, bytes out per pixel, description)
+    # name: codec, format, components, image side, bytes out per pixel, synthetic seed, description
     "dxt1_rgba8": dict(codec=0, fmt=2, nc=4, n=8192, out_bpp=0.5, seed=2, desc="DXT1 8192x8192 RGBA8 (alpha ignored)"),
     "dxt1_rgb8": dict(codec=0, fmt=0, nc=3, n=8192, out_bpp=0.5, seed=1, desc="DXT1 8192x8192 RGB888"),
     "dxt5_rgba8": dict(codec=1, fmt=2, nc=4, n=8192, out_bpp=1.0, seed=2, desc="DXT5 8192x8192 RGBA8"),
     "etc1_rgb8": dict(codec=2, fmt=0, nc=3, n=4096, out_bpp=0.5, seed=1, desc="ETC1 4096x4096 RGB888, kSmallerError"),
     "pvrtc2_rgba8": dict(codec=3, fmt=2, nc=4, n=4096, out_bpp=0.25, seed=2, desc="PVRTC1 2bpp 4096x4096 RGBA8"),
 }
-
+L2_BYTES = 126 << 20
+NVLINK_INGRESS_GBS = 900.0  # NVLink 5, per direction per GPU (B200_PROFILING.md)
 
 _RESULT_FD = None
 
@@ -62,6 +72,10 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+def metric_name(workload):
+    return "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if workload == "dxt1_rgba8" else "Mpixels/sec " + WORKLOADS[workload]["desc"]
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -72,9 +86,10 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+def profile_constant(filename, workload):
+    """Per-launch figures of the dominant kernel taken from committed ncu captures (profiles/<filename>): DRAM traffic
+    (traffic.json) and integer-pipe instruction counts (pipe_counts.json)."""
+    path = os.path.join(ROOT, "profiles", filename)
     if os.path.exists(path):
         try:
             return json.load(open(path)).get(workload)
@@ -229,10 +244,10 @@ def run_reference_arm(args):
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     cpu = cpu_reference_throughput(args.workload, steps, warmup)
     line = {
-        "impl": "reference", "metric": "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if args.workload == "dxt1_rgba8" else "Mpixels/sec " + wl["desc"],
+        "impl": "reference", "metric": metric_name(args.workload),
         "value": cpu["value"], "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.workload != "pvrtc2_rgba8" else "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": args.workload, "image": "%dx%d" % (wl["n"], wl["n"]), "where": "host CPU, %d threads" % cpu["cores"]},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")},
         "e2e": {"value": cpu["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,266 +260,457 @@ def run_reference_arm(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 
-def bind_to_gpu_numa_node(torch, local_rank):
-    """One rank per GPU: run (and therefore allocate the pinned staging buffers of the end-to-end leg) on the CPUs NVML
-    reports as local to this rank's GPU, so that eight ranks do not pull their H2D traffic through one socket.
-    Returns the number of CPUs bound to, or None when NVML / the affinity call is unavailable (nothing is changed)."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        prop = torch.cuda.get_device_properties(local_rank)
-        bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
-        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
-        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return len(cpus)
-    except Exception:
+class Env:
+    """torch / distributed plumbing shared by the legs of the GPU arm."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        import image_compression_b200 as icb
+        self.torch, self.dist, self.icb = torch, dist, icb
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return int(x)
+        t = self.torch.tensor([int(x)], device="cuda", dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def timed(self, step, steps):
+        """K steps back to back on the current stream between two CUDA events, bracketed by barrier + synchronize on
+        both sides; returns (max over ranks of the elapsed ms, this rank's own ms)."""
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        for i in range(steps):
+            step(i)
+        e1.record(self.stream)
+        self.barrier()
+        mine = e0.elapsed_time(e1)
+        return self.max_over_ranks(mine), mine
+
+    def warm(self, step, warmup, spin_s=0.05):
+        """W untimed steps, then keep stepping until ~50 ms have passed so that the timed region starts with the clocks
+        already up instead of inside the GPU's ramp from idle (the timed region itself is only a few ms long)."""
+        for i in range(warmup):
+            step(i)
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < spin_s:
+            for i in range(16):
+                step(i)
+            self.torch.cuda.synchronize()
+
+
+class StripeJob:
+    """One image of workload `wl`; this rank holds pixel rows of block rows [r0, r1) in `nbuf` rotating buffers (a buffer is
+    reused only after >= 1.5 x the 126 MB L2 of other traffic has passed) and encodes them per step."""
+
+    def __init__(self, env, wl, r0, r1, content=None, nbuf=None):
+        torch, icb = env.torch, env.icb
+        self.env, self.wl, self.r0, self.r1 = env, wl, r0, r1
+        n, nc = wl["n"], wl["nc"]
+        self.pitch = n * nc
+        self.in_bytes = (r1 - r0) * 4 * self.pitch
+        self.out_bytes = int((r1 - r0) * 4 * n * wl["out_bpp"])
+        per_step = max(1, self.in_bytes + self.out_bytes)
+        self.nbuf = nbuf or max(2, 1 + -(-3 * L2_BYTES // (2 * per_step)))
+        self.srcs = [torch.empty(max(16, self.in_bytes), dtype=torch.uint8, device="cuda") for _ in range(self.nbuf)]
+        self.dsts = [torch.empty(max(16, self.out_bytes), dtype=torch.uint8, device="cuda") for _ in range(self.nbuf)]
+        for i, s in enumerate(self.srcs):
+            if content is None:
+                if self.in_bytes:
+                    icb.fill_synthetic(s[:self.in_bytes], wl["seed"] + 16 * i, byte_offset=r0 * 4 * self.pitch)
+            else:
+                s[:self.in_bytes].copy_(content(i, r0 * 4, (r1 - r0) * 4))
+        self.scratch = torch.empty(icb.lib().icb_pvrtc2_scratch_size(n, n), dtype=torch.uint8, device="cuda") if wl["codec"] == 3 else None
+        self.peer_out = None  # raw address of this stripe inside the root's peer-mapped stream
+
+    def step(self, i):
+        icb, wl, n = self.env.icb, self.wl, self.wl["n"]
+        if self.r1 == self.r0:
+            return
+        s = self.srcs[i % self.nbuf]
+        if wl["codec"] == 3:
+            icb.pvrtc_encode_device(s, n, n, out=self.dsts[i % self.nbuf], scratch=self.scratch, stream=self.env.stream)
+            return
+        out = self.peer_out if self.peer_out is not None else self.dsts[i % self.nbuf]
+        # virtual address of pixel (0,0) of the whole image; rows outside the stripe are never touched
+        icb.encode_stripe_device(wl["codec"], wl["fmt"], s.data_ptr() - self.r0 * 4 * self.pitch, n, n, self.pitch, n, n,
+                                 self.r0, self.r1, out, stream=self.env.stream)
+
+
+def host_image(workload, buffer_index=0):
+    """The whole synthetic image of buffer 0 on the host (what the CPU reference is fed for the parity flag)."""
+    import checkers as ck
+    wl = WORKLOADS[workload]
+    return ck.synthetic(wl["n"] * wl["n"] * wl["nc"], wl["seed"] + 16 * buffer_index)
+
+
+def parity_record(workload, got_blocks, host_pixels=None):
+    """Byte-compares `got_blocks` (numpy) with the reference CPU encoder's output for the same input."""
+    import numpy as np
+
+    import checkers as ck
+    wl = WORKLOADS[workload]
+    t0 = time.perf_counter()
+    src = host_image(workload) if host_pixels is None else host_pixels
+    want, kind = ck.cpu_encode_full(workload, src, wl["n"], wl["n"])
+    same = got_blocks.size == want.size and bool(np.array_equal(got_blocks, want))
+    return {"equal": same, "bytes_compared": int(want.size), "against": kind, "fnv1a64": "%016x" % ck.fnv1a64(want),
+            "cpu_seconds": round(time.perf_counter() - t0, 2)}
+
+
+def hbm_roofline(workload, algo_bytes, in_bytes, kernel_ms, extra=None):
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": profile_constant("traffic.json", workload), "traffic_source": "ncu --set full capture of this kernel, profiles/traffic.json (not re-measured in the run)",
+         "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
+         "read_only_frac": (in_bytes / (kernel_ms * 1e-3) / 1e9) / peak}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def int_alu_roofline(workload, kernel_ms, sm_mhz):
+    """ETC1's real bound: integer-pipe warp-instructions per launch (ncu,
+    profiles/pipe_counts.json) / kernel time against the measured pipe rate (profiles/*_b200_pipe_rates.txt: 2.0
+    warp-instr/clk/SM for the LOP3/PRMT/VIMNMX/VABSDIFF pipe) x 148 SMs x the SM clock sampled in this run."""
+    counts = profile_constant("pipe_counts.json", workload)
+    if not counts or not sm_mhz:
         return None
+    peak = 2.0 * 148 * sm_mhz * 1e6 / 1e9  # G warp-instr/s
+    achieved = counts["pipe_alu_warp_inst"] / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s", "frac": achieved / peak,
+            "pipe_alu_warp_inst_per_launch": counts["pipe_alu_warp_inst"], "inst_source": counts.get("source"),
+            "peak_source": "tools/microbench/pipe_rates.cu on B200 (2.0 warp-instr/clk/SM) x 148 SMs x %.0f MHz sampled under load" % sm_mhz}
+
+
+def structured_content(torch, kind, n, nc):
+    """Structured 8192^2 images generated on the device (flat regions, dark gradients, 2-colour cells: what the
+    warp-uniform fast path of the DXT index search does NOT cover).  Returns content(buffer, row0, rows) -> uint8 rows."""
+    def make(i, row0, rows):
+        yy = (torch.arange(rows, device="cuda", dtype=torch.int32) + row0)[:, None]
+        xx = torch.arange(n, device="cuda", dtype=torch.int32)[None, :]
+        if kind == "flat":  # 64-px constant tiles with a little dither in one channel
+            r = ((xx // 64) * 37 + (yy // 64) * 91 + i) % 256 + 0 * yy
+            g = ((xx // 64) * 53 + (yy // 64) * 17) % 256 + 0 * yy
+            b = ((xx // 64) * 11 + (yy // 64) * 7) % 256 + ((xx ^ yy) & 1)
+        elif kind == "dark":  # slow gradients near black
+            r = (xx // 256 + i) % 24 + 0 * yy
+            g = (yy // 256) % 24 + 0 * xx
+            b = ((xx + yy) // 512) % 16
+        elif kind == "checker":  # two colours, cell 8 px
+            c = ((xx // 8) ^ (yy // 8)) & 1
+            r, g, b = c * 255, c * 255, c * 255
+        else:  # "gradient": smooth ramps, every block regular
+            r = (xx // 32 + i) % 256 + 0 * yy
+            g = (yy // 32) % 256 + 0 * xx
+            b = ((xx + yy) // 64) % 256
+        chans = [r, g, b] + ([255 - (r % 256)] if nc == 4 else [])
+        return torch.stack([c.expand(rows, n) for c in chans], -1).to(torch.uint8).contiguous().view(-1)
+    return make
+
+
+def measure_single(env, workload, steps, warmup, content_kind=None, want_parity=True, isolated=0):
+    """One GPU, whole image: kernel ms (K launches back to back between two events), optional isolated-launch pass,
+    parity of buffer 0's output against the CPU reference."""
+    torch, icb = env.torch, env.icb
+    wl = WORKLOADS[workload]
+    n = wl["n"]
+    content = structured_content(torch, content_kind, n, wl["nc"]) if content_kind else None
+    job = StripeJob(env, wl, 0, n // 4, content=content)
+    env.warm(job.step, warmup)
+    before = icb.launch_count()
+    _, ms = env.timed(job.step, steps)
+    launches = icb.launch_count() - before
+    rec = {"kernel_ms": ms / steps, "mpix_s": n * n / (ms / steps * 1e-3) / 1e6, "steps": steps, "launches_per_step": launches // max(1, steps),
+           "buffers": job.nbuf}
+    iso = []
+    if isolated:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(isolated)]
+        for i in range(isolated):
+            ev[i][0].record(env.stream)
+            job.step(i)
+            ev[i][1].record(env.stream)
+        torch.cuda.synchronize()
+        iso = sorted(a.elapsed_time(b) for a, b in ev)
+    if want_parity:
+        job.step(0)
+        torch.cuda.synchronize()
+        host_px = job.srcs[0][:job.in_bytes].cpu().numpy() if content_kind else None
+        rec["parity"] = parity_record(workload, job.dsts[0][:job.out_bytes].cpu().numpy(), host_px)
+    return job, rec, iso, launches
+
+
+def other_workloads(env, headline, clocks_mhz):
+    """Compact records for the BASELINE configurations the headline does not cover, and for structured content on the
+    headline workload (the DXT index search is data dependent).  N = 1 only; ~20 steps each."""
+    out = {}
+    for name in ("dxt5_rgba8", "dxt1_rgb8", "etc1_rgb8", "pvrtc2_rgba8", "dxt1_rgba8"):
+        if name == headline:
+            continue
+        wl = WORKLOADS[name]
+        job, rec, _, _ = measure_single(env, name, 20, 3)
+        algo = job.in_bytes + job.out_bytes
+        rec["roofline"] = hbm_roofline(name, algo, job.in_bytes, rec["kernel_ms"])
+        for k in ("traffic_source", "peak_source"):
+            rec["roofline"].pop(k, None)
+        if name == "etc1_rgb8":
+            rec["roofline_int_alu"] = int_alu_roofline(name, rec["kernel_ms"], clocks_mhz)
+            rec["bound"] = "int_alu (exhaustive search: ~1024 colour-distance evaluations per block); the HBM fraction is reported as required, not attainable"
+        elif name == "pvrtc2_rgba8":
+            rec["bound"] = "hbm (fused-ideal bytes 4.25 B/px); three kernels per step, integer-pipe / latency limited today"
+        rec["desc"] = wl["desc"]
+        del job
+        env.torch.cuda.empty_cache()
+        out[name] = rec
+    if headline in ("dxt1_rgba8", "dxt5_rgba8"):
+        content = {}
+        for kind in ("gradient", "flat", "dark", "checker"):
+            job, rec, _, _ = measure_single(env, headline, 20, 3, content_kind=kind)
+            rec["roofline_frac"] = hbm_roofline(headline, job.in_bytes + job.out_bytes, job.in_bytes, rec["kernel_ms"])["frac"]
+            content[kind] = rec
+            del job
+            env.torch.cuda.empty_cache()
+        out["content_dependence_" + headline] = content
+    return out
 
 
 def run_gpu_arm(args):
     import ctypes as C
 
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
-    import image_compression_b200 as icb
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = Env()
+    torch, dist, icb = env.torch, env.dist, env.icb
+    world, rank = env.world, env.rank
     wl = WORKLOADS[args.workload]
     n, nc, codec, fmt = wl["n"], wl["nc"], wl["codec"], wl["fmt"]
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    grid_rows, grid_cols = n // 4, n // 4
+    block_bytes = 16 if codec == 1 else 8
+    replicas = codec == 3 and world > 1  # PVRTC: square power-of-two images only -> N independent replicas
+    L = icb.lib()
 
-    # Weak scaling: the job is an n-wide image of n*world rows, sharded by block-row stripes; this rank owns
-    # block rows [r0, r1) and holds only those pixel rows.  PVRTC does not shard (toroidal wrap): replicas.
-    pitch = n * nc
-    total_rows = n * world
-    grid_rows = total_rows // 4
-    r0, r1 = icb.stripe_rows(grid_rows, rank, world)
-    my_px_rows = (r1 - r0) * 4
-    in_bytes = my_px_rows * pitch
-    out_bytes = int(my_px_rows * n * wl["out_bpp"])
-    # Rotate over enough buffer pairs that a buffer is reused only after >= 1.5 x the 126 MB L2 of other traffic has
-    # passed through: 2 for the 8192^2 workloads (302+ MB per step), 4-5 for the 4096^2 ones (59-71 MB per step).
-    l2_bytes = 126 << 20
-    nbuf = max(2, 1 + -(-3 * l2_bytes // (2 * (in_bytes + out_bytes))))
-    srcs = [torch.empty(in_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
-    dsts = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
-    for i, s in enumerate(srcs):
-        icb.fill_synthetic(s, wl["seed"] + 16 * i, byte_offset=r0 * 4 * pitch)
-    scratch = torch.empty(icb.lib().icb_pvrtc2_scratch_size(n, n), dtype=torch.uint8, device="cuda") if codec == 3 else None
-    stream = torch.cuda.current_stream()
+    # ---- partition of the ONE image over the ranks
+    if world == 1 or replicas:
+        splits, share = [0, grid_rows] if world == 1 else None, None
+    else:
+        share = {"even": -1, "auto": icb.root_share_permille(codec, fmt, world)}.get(args.partition)
+        if share is None:
+            share = int(args.partition)
+        splits = icb.stripe_partition(world, grid_rows, share)
+    r0, r1 = (0, grid_rows) if (world == 1 or replicas) else (splits[rank], splits[rank + 1])
+    job = StripeJob(env, wl, r0, r1)
+    total_out = grid_rows * grid_cols * block_bytes if codec != 3 else n * n // 4
 
-    def step(i):
-        s, d = srcs[i % nbuf], dsts[i % nbuf]
-        if codec == 3:
-            icb.pvrtc_encode_device(s, n, n, out=d, scratch=scratch, stream=stream)
-        else:
-            # virtual address of pixel (0,0) of the whole tall image; rows outside the stripe are never touched
-            base = s.data_ptr() - r0 * 4 * pitch
-            icb.encode_stripe_device(codec, fmt, base, total_rows, n, pitch, total_rows, n, r0, r1, d, stream=stream)
+    ps = None
+    if world > 1 and not replicas:
+        from image_compression_b200 import sharding
+        ps = sharding.PeerStream(total_out, dst=0)  # collective; raises on every rank or on none
+        job.peer_out = ps.stripe_ptr(r0 * grid_cols * block_bytes)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
-    # Warm-up: W steps, then keep stepping (untimed) until ~50 ms have passed, so that the timed region starts with the
-    # clocks already up instead of inside the GPU's ramp from idle (the timed region itself is only a few ms long).
-    for i in range(warmup):
-        step(i)
-    torch.cuda.synchronize()
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.05:
-        for i in range(16):
-            step(i)
-        torch.cuda.synchronize()
+    env.barrier()
+    env.warm(job.step, warmup)
     launches_before = icb.launch_count()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    # Timed region: exactly K steps back to back on one stream between two CUDA events.  (Consecutive launches
-    # overlap their launch latency through programmatic dependent launch; nothing else sits between them.)
-    t_begin.record(stream)
-    for i in range(steps):
-        step(i)
-    t_end.record(stream)
-    barrier()
-    launches = icb.launch_count() - launches_before
-    total_ms = t_begin.elapsed_time(t_end)
-    # Second, untimed-for-the-metric pass: each launch bracketed by its own pair of events (isolated launch durations;
-    # the events themselves keep consecutive launches from overlapping).
-    iso = min(steps, 20)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iso)]
-    for i in range(iso):
-        ev[i][0].record(stream)
-        step(i)
-        ev[i][1].record(stream)
-    barrier()
+    # Timed region: exactly K steps back to back on one stream between two CUDA events, max over ranks.  (Consecutive
+    # launches overlap their launch latency through programmatic dependent launch; nothing else sits between them.)  At
+    # N > 1 a step ends when this rank's blocks have been stored into rank 0's buffer (peer stores complete with the kernel).
+    total_ms, my_ms = env.timed(job.step, steps)
+    launches = env.sum_over_ranks(icb.launch_count() - launches_before)
+    ms_per_step = total_ms / steps
+    job_px = n * n * (world if replicas else 1)
+    value = job_px / (ms_per_step * 1e-3) / 1e6
+
+    # isolated launches (each between its own two events; the events keep consecutive launches from overlapping)
+    iso_n = min(steps, 20)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iso_n)]
+    for i in range(iso_n):
+        ev[i][0].record(env.stream)
+        job.step(i)
+        ev[i][1].record(env.stream)
+    env.barrier()
+    kernel_iso = sorted(a.elapsed_time(b) for a, b in ev)
     # The timed region lasts milliseconds, shorter than one nvidia-smi sample: keep the identical launches going for
     # ~0.5 s (untimed) so that the clock / throttle record is taken under this kernel's load, not at idle.
     t_hold = time.perf_counter()
     i = 0
     while time.perf_counter() - t_hold < 0.5:
         for _ in range(64):
-            step(i)
+            job.step(i)
             i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    kernel_ms = sorted(a.elapsed_time(b) for a, b in ev)
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / steps
-    job_px = n * total_rows if codec != 3 else n * n * world
-    value = job_px / (ms_per_step * 1e-3) / 1e6
 
-    # ---- NCCL gather of the packed block stream to rank 0 (reported separately, not part of `value`)
-    gather = None
-    if world > 1 and codec != 3:
-        from image_compression_b200 import sharding
-        block_bytes = 16 if codec == 1 else 8
-        for _ in range(3):
-            sharding.gather_blocks(dsts[0], grid_rows, n // 4, block_bytes, dst=0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        reps = 10
-        for _ in range(reps):
-            sharding.gather_blocks(dsts[0], grid_rows, n // 4, block_bytes, dst=0)
-        g1.record(stream)
-        barrier()
-        g_ms = torch.tensor([g0.elapsed_time(g1) / reps], device="cuda")
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(g_ms.item()), "bytes_into_root": out_bytes * (world - 1), "backend": "nccl gather (image_compression_b200.sharding.gather_blocks)",
-                  "encode_plus_gather_mpix_s": job_px / ((ms_per_step + float(g_ms.item())) * 1e-3) / 1e6}
-
-    # ---- fused gather: every rank's encoder stores its blocks straight into rank 0's buffer over NVLink (peer-mapped
-    # output, sharding.PeerStream); timed like `value` (K steps between two events, max over ranks), reported separately
-    fused, ps = None, None
-    if world > 1 and codec != 3:
-        from image_compression_b200 import sharding
-        block_bytes = 16 if codec == 1 else 8
-        total_out = grid_rows * (n // 4) * block_bytes
-        try:
-            ps = sharding.PeerStream(total_out, dst=0)  # collective; fails on every rank or on none
-        except RuntimeError as e:
-            ps = None
-            fused = {"unavailable": str(e)}
+    # ---- parity of THIS run's output: the stream that arrived on rank 0 (buffer 0's input) vs the CPU reference
+    job.step(0)
+    parity = None
     if ps is not None:
-        my_out = ps.stripe_ptr(r0 * (n // 4) * block_bytes)
-
-        def step_peer(i):
-            s = srcs[i % nbuf]
-            icb.encode_stripe_device(codec, fmt, s.data_ptr() - r0 * 4 * pitch, total_rows, n, pitch, total_rows, n, r0, r1, my_out,
-                                     stream=stream)
-        for i in range(warmup):
-            step_peer(i)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for i in range(steps):
-            step_peer(i)
-        f1.record(stream)
-        barrier()
-        f_ms = torch.tensor([f0.elapsed_time(f1) / steps], device="cuda")
-        dist.all_reduce(f_ms, op=dist.ReduceOp.MAX)
-        # check: the stream assembled by peer stores == the NCCL gather of the locally written stripes (same input)
-        step_peer(0)
-        step(0)
         ps.complete()
-        want = sharding.gather_blocks(dsts[0], grid_rows, n // 4, block_bytes, dst=0)
-        same = bool(torch.equal(ps.tensor(), want)) if rank == 0 else True
-        ps.close()
-        fused = {"ms_per_step": float(f_ms.item()), "mpix_s": job_px / (float(f_ms.item()) * 1e-3) / 1e6, "bytes_into_root": out_bytes * (world - 1),
-                 "equals_nccl_gather": same, "how": "encoder block stores go to rank 0's buffer through a CUDA-IPC peer mapping (NVLink); no separate gather pass"}
+        if rank == 0:
+            parity = parity_record(args.workload, ps.tensor().cpu().numpy())
+    else:
+        torch.cuda.synchronize()
+        if rank == 0:
+            parity = parity_record(args.workload, job.dsts[0][:job.out_bytes].cpu().numpy())
 
-    # ---- end to end through the host-buffer entry point (pinned buffers; H2D + kernels + D2H per step)
-    L = icb.lib()
-    e2e_rows = my_px_rows if codec != 3 else n
-    h_in_ptr = L.icb_host_alloc(in_bytes)
-    h_out_ptr = L.icb_host_alloc(out_bytes)
-    if not h_in_ptr or not h_out_ptr:
-        raise SystemExit("pinned allocation failed")
-    h_in = np.ctypeslib.as_array(C.cast(h_in_ptr, C.POINTER(C.c_uint8)), shape=(in_bytes,))
-    h_out = np.ctypeslib.as_array(C.cast(h_out_ptr, C.POINTER(C.c_uint8)), shape=(out_bytes,))
-    h_in[:] = srcs[0].cpu().numpy()
-    e2e_steps = max(3, min(steps, 10))
-    for _ in range(2):
-        icb.compress_host(codec, fmt, h_in, e2e_rows, n, out=h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        icb.compress_host(codec, fmt, h_in, e2e_rows, n, out=h_out)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = job_px / (e2e_ms * 1e-3) / 1e6
-    e2e_check = bool(np.array_equal(h_out, dsts[0].cpu().numpy()))
-    L.icb_host_free(h_in_ptr)
-    L.icb_host_free(h_out_ptr)
+    # ---- N > 1: the pieces that explain `value`
+    multi = {}
+    if ps is not None:
+        from image_compression_b200 import sharding
+        # (a) encode only: same stripes, blocks stored locally (no delivery)
+        job.peer_out = None
+        enc_ms, _ = env.timed(job.step, steps)
+        multi["encode_only"] = {"ms_per_step": enc_ms / steps, "mpix_s": job_px / (enc_ms / steps * 1e-3) / 1e6,
+                                "what": "same stripes, blocks stored to local HBM, nothing delivered (max over ranks)"}
+        # (b) even split delivered the same way, when `value` used a root-heavy one
+        even = icb.stripe_partition(world, grid_rows, -1)
+        if even != splits:
+            ej = StripeJob(env, wl, even[rank], even[rank + 1])
+            ej.peer_out = ps.stripe_ptr(even[rank] * grid_cols * block_bytes)
+            env.warm(ej.step, warmup, spin_s=0.02)
+            e_ms, _ = env.timed(ej.step, steps)
+            multi["even_split_delivered"] = {"ms_per_step": e_ms / steps, "mpix_s": job_px / (e_ms / steps * 1e-3) / 1e6,
+                                             "bytes_into_root": total_out - (even[1] - even[0]) * grid_cols * block_bytes}
+        else:
+            ej = job
+        # (c) the north star's literal form: encode locally, then ONE NCCL gather of the packed stream (even stripes)
+        ej.peer_out = None
+        local = ej.dsts[0][:ej.out_bytes]
+        for _ in range(3):
+            ej.step(0)
+            sharding.gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, splits=even)
+
+        def gather_step(i):
+            ej.step(0)
+            sharding.gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, splits=even)
+        reps = min(steps, 10)
+        g_ms, _ = env.timed(gather_step, reps)
+        got = sharding.gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, splits=even)
+        multi["nccl_gather"] = {"ms_per_step": g_ms / reps, "mpix_s": job_px / (g_ms / reps * 1e-3) / 1e6,
+                                "what": "encode to local HBM + dist.gather of the stripes to rank 0 (reference implementation of the delivery)"}
+        if rank == 0:
+            ps_now = ps.tensor()
+            multi["nccl_gather"]["equals_peer_store_stream"] = bool(torch.equal(got, ps_now))
+        # (d) round 1's figure: every rank a full image of its own, kernel only -- weak scaling of independent kernels
+        del ej
+        wj = StripeJob(env, wl, 0, grid_rows)
+        env.warm(wj.step, warmup, spin_s=0.02)
+        w_ms, _ = env.timed(wj.step, min(steps, 20))
+        multi["weak_scaling_kernel_only"] = {"ms_per_step": w_ms / min(steps, 20), "mpix_s": n * n * world / (w_ms / min(steps, 20) * 1e-3) / 1e6,
+                                             "what": "%d independent %dx%d images, one per GPU, no delivery (round 1's `value`)" % (world, n, n)}
+        del wj
+        ps.close()
+        torch.cuda.empty_cache()
+
+    # ---- end to end: ONE image through the host-buffer API (pinned buffers; H2D + kernels + D2H per step)
+    e2e = None
+    in_total = n * n * nc
+    if rank == 0:
+        h_in_ptr, h_out_ptr = L.icb_host_alloc(in_total), L.icb_host_alloc(total_out)
+        if not h_in_ptr or not h_out_ptr:
+            raise SystemExit("pinned allocation failed")
+        h_in = np.ctypeslib.as_array(C.cast(h_in_ptr, C.POINTER(C.c_uint8)), shape=(in_total,))
+        h_out = np.ctypeslib.as_array(C.cast(h_out_ptr, C.POINTER(C.c_uint8)), shape=(total_out,))
+        h_in[:] = host_image(args.workload)
+        ctx = icb.ShardContext(list(range(world))) if (world > 1 and not replicas) else None
+        call = (lambda: ctx.compress_host(codec, fmt, h_in, n, n, out=h_out)) if ctx else (lambda: icb.compress_host(codec, fmt, h_in, n, n, out=h_out))
+        e2e_steps = max(3, min(steps, 10))
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        import checkers as ck
+        e2e = {"value": n * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": in_total, "d2h_bytes_per_step": total_out,
+               "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "api": "icb_ctx_compress_host: one call from rank 0 spreads the image over %d GPUs, each over its own PCIe link (pinned host buffers)" % world if ctx
+               else "icb_compress_host (pinned host buffers)",
+               "output_fnv1a64": "%016x" % ck.fnv1a64(h_out), "output_equals_reference": (parity or {}).get("fnv1a64") == "%016x" % ck.fnv1a64(h_out)}
+        if ctx:
+            ctx.close()
+        L.icb_host_free(h_in_ptr)
+        L.icb_host_free(h_out_ptr)
+    env.barrier()
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        algo_bytes = in_bytes + out_bytes  # read every source byte once, write every block once
-        k_med = kernel_ms[len(kernel_ms) // 2]
-        k_iso_avg = sum(kernel_ms) / len(kernel_ms)
-        # average launch duration over the timed region (this rank's own clock): the step IS the launch
-        k_avg = t_begin.elapsed_time(t_end) / steps
-        achieved = algo_bytes / (k_avg * 1e-3) / 1e9
-        # the CPU baseline is a one-GPU-run item (rank 0, N = 1): at N > 1 the ranks are pinned to their GPU's NUMA node
-        cpu = cpu_reference_throughput(args.workload, 2, 1) if (world == 1 and not args.no_cpu_baseline) else None
+        k_avg = my_ms / steps if world == 1 else multi.get("encode_only", {}).get("ms_per_step", ms_per_step)
+        algo_bytes = job.in_bytes + job.out_bytes  # this rank's stripe: read every source byte once, write every block once
+        roof = hbm_roofline(args.workload, algo_bytes, job.in_bytes, k_avg, {
+            "kernel_ms_avg_source": "timed region: (end event - begin event) / steps, launches back to back" if world == 1
+            else "rank 0's stripe kernel in the encode-only leg (the timed `value` also contains the delivery)",
+            "kernel_ms_isolated_avg": sum(kernel_iso) / len(kernel_iso), "kernel_ms_isolated_median": kernel_iso[len(kernel_iso) // 2],
+            "kernel_ms_min": kernel_iso[0], "kernel_ms_isolated_source": "separate pass, each launch between its own two events"})
+        if world > 1:
+            roof["traffic"] = None
         line = {
-            "metric": "Mpixels/sec DXT1 encode, 8K x 8K RGBA8" if args.workload == "dxt1_rgba8" else "Mpixels/sec " + wl["desc"],
+            "metric": metric_name(args.workload),
             "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "image": "%dx%d per GPU (%dx%d job, block-row stripes)" % (n, n, n, total_rows),
-                       "input": "splitmix64 byte stream, resident in HBM", "l2": "%d rotating buffer pairs, %d MB of other traffic between two uses of a buffer (126 MB L2)" % (nbuf, ((nbuf - 1) * (in_bytes + out_bytes)) >> 20),
-                       "parallelism": "stripe%d" % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": k_avg,
-                         "kernel_ms_avg_source": "timed region: (end event - begin event) / steps, launches back to back",
-                         "kernel_ms_isolated_avg": k_iso_avg, "kernel_ms_isolated_median": k_med, "kernel_ms_min": kernel_ms[0],
-                         "kernel_ms_isolated_source": "separate pass, each launch between its own two events",
-                         "read_only_frac": (in_bytes / (k_avg * 1e-3) / 1e9) / peak},
-            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "icb_compress_host (pinned host buffers)", "output_equals_device_path": e2e_check,
-                    "cpus_bound_to_gpu_numa_node": numa},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if codec == 3 else "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "image": "%dx%d" % (n, n),
+                       "job": ("%d replicas of one %dx%d image (PVRTC does not shard)" % (world, n, n)) if replicas
+                       else ("one %dx%d image" % (n, n)) + ("" if world == 1 else ", block-row stripes %s over %d GPUs, packed stream delivered to rank 0 inside the timed region" % (splits, world)),
+                       "input": "splitmix64 byte stream, resident in HBM",
+                       "l2": "%d rotating buffer pairs on rank 0, %d MB of other traffic between two uses of a buffer (126 MB L2)" % (job.nbuf, ((job.nbuf - 1) * (job.in_bytes + job.out_bytes)) >> 20),
+                       "parallelism": "stripe%d" % world if not replicas else "replica%d" % world},
+            "roofline": roof,
+            "parity": parity,
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if cpu:
+        if world > 1 and not replicas:
+            into_root = total_out - (r1 - r0) * grid_cols * block_bytes
+            gbs = into_root / (ms_per_step * 1e-3) / 1e9
+            line["delivery"] = {
+                "bound": "nvlink_ingress", "bytes_into_root": into_root, "achieved": gbs, "peak": NVLINK_INGRESS_GBS, "unit": "GB/s",
+                "frac": gbs / NVLINK_INGRESS_GBS, "partition": "root share %s permille" % share if share is not None and share >= 0 else "even",
+                "how": "encoder block stores go to rank 0's buffer through a CUDA-IPC peer mapping (NVLink); no separate gather pass",
+                "limiter": "rank 0's NVLink ingress: every block of the other ranks' stripes crosses one GPU's inbound links; "
+                           "the root encodes its own (larger) stripe while they arrive" if world > 2 else
+                           "encode kernels (two ranks: the transfer of one half hides behind the encode of the other)"}
+            line.update(multi)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_throughput(args.workload, 2, 1)
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "flags")}
-        if gather:
-            line["gather"] = gather
-        if fused:
-            line["fused_gather"] = fused
+        if world == 1 and not args.no_others:
+            del job
+            torch.cuda.empty_cache()
+            line["other_workloads"] = other_workloads(env, args.workload, (clocks or {}).get("sm_mhz"))
         emit(line)
     if world > 1:
         dist.barrier()
@@ -518,7 +724,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dxt1_rgba8", choices=sorted(WORKLOADS))
+    ap.add_argument("--partition", default="auto", help="N > 1: auto (icb_root_share_permille), even, or the root's share in permille")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads records (N = 1)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

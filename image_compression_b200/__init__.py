@@ -12,4 +12,5 @@ from .binding import (  # noqa: F401
     lib, lib_path, pvrtc_encode_device, pvrtc_encode_stripe_device, set_tma_mode, stripe_rows,
     OP_COPY_SUBIMAGE, OP_DOWNSAMPLE, OP_PAD, OP_SOLID, OP_TRANSCODE, block_bytes, blockop_host, copy_subimage_device,
     downsample_device, fill_solid_device, pad_device, transcode_dxt1_to_etc1_device,
+    ShardContext, root_share_permille, stripe_partition,
 )

@@ -57,6 +57,18 @@ PROTOTYPES = {
     "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "icb_launch_count": (C.c_uint64, []),
     "icb_set_tma_mode": (C.c_int, [C.c_int]),
+    "icb_set_host_devices": (C.c_int, [C.c_int]),
+    "icb_trim": (C.c_size_t, []),
+    "icb_idle_pipes": (C.c_size_t, []),
+    "icb_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "icb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "icb_ctx_device_count": (C.c_int, [C.c_void_p]),
+    "icb_ctx_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "icb_ctx_peer_stores": (C.c_int, [C.c_void_p]),
+    "icb_stripe_partition": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]),
+    "icb_root_share_permille": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "icb_encode_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "icb_ctx_compress_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 
@@ -282,3 +294,63 @@ def blockop_host(op, codec, args, src, out_size, strategy=ETC_SMALLER_ERROR):
     src_ptr, src_size = (src.ctypes.data, src.size) if src is not None else (None, 0)
     _check(lib().icb_blockop_host(op, codec, strategy, arr, src_ptr, src_size, out.ctypes.data, out.size))
     return out
+
+
+# ---- one image over several GPUs from one process (icb_ctx_*) -------------------------------
+
+def stripe_partition(n, grid_rows, root_share_permille=-1):
+    """Block-row splits [s0=0, s1, ..., sn=grid_rows] of icb_stripe_partition (no device needed)."""
+    splits = (C.c_uint32 * (n + 1))()
+    _check(lib().icb_stripe_partition(n, grid_rows, root_share_permille, splits))
+    return [int(x) for x in splits]
+
+
+def root_share_permille(codec, fmt, n):
+    return int(lib().icb_root_share_permille(codec, ncomp_of(fmt), n))
+
+
+class ShardContext:
+    """icb_ctx: N GPUs of this process, device ids[0] the root that receives the packed stream by peer stores."""
+
+    def __init__(self, device_ids=None, n=None):
+        self._h = C.c_void_p()
+        ids = list(device_ids) if device_ids is not None else None
+        count = len(ids) if ids is not None else (0 if n is None else n)
+        arr = (C.c_int * count)(*ids) if ids is not None else None
+        _check(lib().icb_ctx_create(count, arr, C.byref(self._h)))
+        self.devices = [lib().icb_ctx_device(self._h, k) for k in range(lib().icb_ctx_device_count(self._h))]
+
+    @property
+    def peer_stores(self):
+        return bool(lib().icb_ctx_peer_stores(self._h))
+
+    def encode(self, codec, fmt, stripes, h, w, splits, out, pitch=None, strategy=ETC_SMALLER_ERROR, stream=None):
+        """stripes[r]: uint8 CUDA tensor on device r of the context holding pixel rows 4*splits[r] .. of the image;
+        out: uint8 CUDA tensor on the root for the whole stream.  Asynchronous on `stream` (a stream of the root)."""
+        import torch
+        pitch = w * ncomp_of(fmt) if pitch is None else pitch
+        n = len(self.devices)
+        ptrs = (C.c_void_p * n)(*[(t.data_ptr() if t is not None and t.numel() else None) for t in stripes])
+        sp = (C.c_uint32 * (n + 1))(*splits)
+        with torch.cuda.device(self.devices[0]):
+            _check(lib().icb_encode_sharded(self._h, codec, fmt, h, w, pitch, strategy, sp, ptrs, out.data_ptr(), _stream_ptr(stream)))
+        return out
+
+    def compress_host(self, codec, fmt, src, h, w, padded=None, padding=0, strategy=ETC_SMALLER_ERROR, out=None):
+        ph, pw = padded if padded else (0, 0)
+        size = compressed_size(codec, max(h, ph), max(w, pw)) if codec != CODEC_PVRTC2 else w * h // 4
+        if out is None:
+            out = np.empty(size, np.uint8)
+        _check(lib().icb_ctx_compress_host(self._h, codec, fmt, h, w, ph, pw, padding, strategy, src.ctypes.data, out.ctypes.data, out.size))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().icb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

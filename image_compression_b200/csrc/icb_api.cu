@@ -51,9 +51,17 @@ int fail(int status, const char *fmt, ...) {
 // Scratch the library allocates on a caller's stream (PVRTC without a caller-provided buffer) comes from the library's
 // own memory pool, which keeps freed blocks instead of returning them to the driver at the next synchronisation: the
 // default pool's release threshold of zero turns every call after a sync into a fresh device allocation.
+std::mutex g_scratch_mu;
+cudaMemPool_t g_scratch_pools[64] = {};
+
+cudaMemPool_t scratch_pool_if_created(int dev) {
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  return (dev >= 0 && dev < 64) ? g_scratch_pools[dev] : nullptr;
+}
+
 int scratch_pool(cudaMemPool_t *out) {
-  static std::mutex mu;
-  static cudaMemPool_t pools[64] = {};
+  std::mutex &mu = g_scratch_mu;
+  cudaMemPool_t *pools = g_scratch_pools;
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
@@ -269,6 +277,12 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
   return ICB_OK;
 }
 
+// Block streams are read and written with 8-byte (DXT1, ETC1, PVRTC) or 16-byte (DXT5 output) vector accesses.
+bool block_aligned(int codec, const void *p, bool as_input = false) {
+  const uintptr_t a = (codec == ICB_CODEC_DXT5 && !as_input) ? 16 : 8;
+  return reinterpret_cast<uintptr_t>(p) % a == 0;
+}
+
 int encode4x4(int codec, int ncomp, const void *d_src, uint32_t h, uint32_t w, size_t pitch, uint32_t coded_h,
               uint32_t coded_w, int swap_rb, int strategy, uint32_t r0, uint32_t r1, void *d_dst, void *stream) {
   if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
@@ -276,6 +290,9 @@ int encode4x4(int codec, int ncomp, const void *d_src, uint32_t h, uint32_t w, s
   if (coded_h < h || coded_w < w) return fail(ICB_ERR_INVALID, "coded size %ux%u smaller than image %ux%u", coded_h, coded_w, h, w);
   if (pitch < static_cast<size_t>(w) * ncomp || pitch > 0xffffffffull) return fail(ICB_ERR_INVALID, "bad source pitch %zu", pitch);
   if (strategy < 0 || strategy > 3) return fail(ICB_ERR_INVALID, "unknown ETC strategy %d", strategy);
+  // blocks are stored with one 8- or 16-byte vector store each: a misaligned destination would raise a sticky
+  // misaligned-address fault instead of an error code
+  if (!block_aligned(codec, d_dst)) return fail(ICB_ERR_INVALID, "destination %p is not aligned to the %d-byte block", d_dst, codec == ICB_CODEC_DXT5 ? 16 : 8);
   Encode4x4Params p{};
   p.src = static_cast<const uint8_t *>(d_src);
   p.dst = static_cast<uint8_t *>(d_dst);
@@ -471,11 +488,13 @@ struct HostPipe {  // per host thread, per device: streams, events and grow-only
   size_t stage_in_cap = 0, stage_out_cap = 0;
   cudaEvent_t stage_in_free[kStageBufs] = {}, out_done[kMaxChunks] = {};
 
+  // Creates the streams and events on the CURRENT device (once per pipe; a pipe never changes device).
   int prepare() {
     int dev = 0;
     ICB_CUDA(cudaGetDevice(&dev));
     if (device == dev) return ICB_OK;
     release();
+    device = dev;  // from here on release() has something to undo, also after a partial failure below
     ICB_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
     ICB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     ICB_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
@@ -485,9 +504,22 @@ struct HostPipe {  // per host thread, per device: streams, events and grow-only
       ICB_CUDA(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < kStageBufs; ++i) ICB_CUDA(cudaEventCreateWithFlags(&stage_in_free[i], cudaEventDisableTiming));
-    device = dev;
     return ICB_OK;
   }
+  // Waits for everything this pipe has in flight (error paths: the next user may free or overwrite its buffers).
+  void quiesce() {
+    if (device < 0) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    if (copy_in) cudaStreamSynchronize(copy_in);
+    if (compute) cudaStreamSynchronize(compute);
+    if (copy_out) cudaStreamSynchronize(copy_out);
+    cudaGetLastError();
+    if (cur != device) cudaSetDevice(cur);
+  }
+  size_t device_bytes() const { return src_cap + dst_cap + scratch_cap; }
+  size_t pinned_bytes() const { return kStageBufs * (stage_in_cap + stage_out_cap); }
   static int grow_pinned(void *(&bufs)[kStageBufs], size_t *cap, size_t need) {
     if (*cap >= need) return ICB_OK;
     for (int i = 0; i < kStageBufs; ++i) {
@@ -536,17 +568,108 @@ struct HostPipe {  // per host thread, per device: streams, events and grow-only
   // Deliberately no destructor work: at process exit the CUDA context may already be gone.
 };
 
-thread_local HostPipe t_pipes[64];  // one per device ordinal this host thread has used
+// Pipes live in a process-wide pool, one free list per device, and are LEASED for the duration of one host-buffer call:
+// a thread that exits leaves nothing behind (round 1 kept them thread_local, so a thread-per-request caller leaked
+// three streams, 51 events and up to ~300 MB of device + pinned memory per dead thread), and concurrent callers each
+// get their own pipe.  Buffers are grow-only while a pipe is pooled -- a pipe that has encoded an 8192^2 RGBA8 image
+// keeps 268 MB + the output on the device -- so the pool holds at most `max concurrent calls` pipes per device;
+// icb_trim() releases the idle ones.
+class PipePool {
+ public:
+  static PipePool &get() {
+    static PipePool *pool = new PipePool();  // never destroyed (see HostPipe: no CUDA calls at static destruction)
+    return *pool;
+  }
+  // A prepared pipe for the CURRENT device.
+  int acquire(HostPipe **out) {
+    int dev = 0;
+    ICB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
+    HostPipe *pipe = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      if (!idle_[dev].empty()) {
+        pipe = idle_[dev].back();
+        idle_[dev].pop_back();
+      }
+    }
+    if (!pipe) {
+      pipe = new HostPipe();
+      if (int s = pipe->prepare()) {
+        pipe->release();
+        delete pipe;
+        return s;
+      }
+    }
+    *out = pipe;
+    return ICB_OK;
+  }
+  void give_back(HostPipe *pipe, bool clean) {
+    if (!pipe) return;
+    if (!clean) pipe->quiesce();
+    std::lock_guard<std::mutex> lock(mu_);
+    idle_[pipe->device].push_back(pipe);
+  }
+  // Frees every idle pipe (streams, events, device and pinned buffers).  Returns the bytes released.
+  size_t trim() {
+    std::vector<HostPipe *> victims;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      for (auto &list : idle_) {
+        victims.insert(victims.end(), list.begin(), list.end());
+        list.clear();
+      }
+    }
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    size_t bytes = 0;
+    for (HostPipe *pipe : victims) {
+      bytes += pipe->device_bytes() + pipe->pinned_bytes();
+      cudaSetDevice(pipe->device);
+      pipe->quiesce();
+      pipe->release();
+      delete pipe;
+    }
+    if (have_cur) cudaSetDevice(cur);
+    cudaGetLastError();
+    return bytes;
+  }
+  size_t idle_count() {
+    std::lock_guard<std::mutex> lock(mu_);
+    size_t n = 0;
+    for (auto &list : idle_) n += list.size();
+    return n;
+  }
 
-// The calling thread's pipe for the CURRENT device, prepared.
-int current_pipe(HostPipe **out) {
-  int dev = 0;
-  ICB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(ICB_ERR_CUDA, "device ordinal %d out of range", dev);
-  if (int s = t_pipes[dev].prepare()) return s;
-  *out = &t_pipes[dev];
-  return ICB_OK;
-}
+ private:
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu_;
+  std::vector<HostPipe *> idle_[kMaxDevices];
+};
+
+// The lease of one call: pipes are handed back when it goes out of scope -- after a quiesce unless the call said
+// it finished cleanly (every exit path of the host entry points that does not reach `clean = true` is an error path,
+// possibly with copies or kernels still in flight).
+struct PipeLease {
+  HostPipe *pipes[16] = {};
+  int count = 0;
+  bool clean = false;
+  int acquire(HostPipe **out) {  // for the current device
+    if (count >= 16) return fail(ICB_ERR_INVALID, "too many devices in one call");
+    if (int s = PipePool::get().acquire(out)) return s;
+    pipes[count++] = *out;
+    return ICB_OK;
+  }
+  int finish(int status) {
+    clean = status == ICB_OK;
+    return status;
+  }
+  ~PipeLease() {
+    for (int i = 0; i < count; ++i) PipePool::get().give_back(pipes[i], clean);
+  }
+};
+
+std::atomic<int> g_host_devices{-1};  // icb_set_host_devices(); -1 = ICB_HOST_DEVICES from the environment, else one
 
 // Devices icb_compress_host spreads one image over: the current device only, unless ICB_HOST_DEVICES=N|all asks for
 // more -- then the current device and the next N-1 ordinals (modulo the device count).
@@ -554,8 +677,12 @@ int host_devices(int *devs, int *count) {
   int cur = 0, total = 0;
   ICB_CUDA(cudaGetDevice(&cur));
   ICB_CUDA(cudaGetDeviceCount(&total));
-  int want = 1;
-  if (const char *e = getenv("ICB_HOST_DEVICES")) want = strcmp(e, "all") == 0 ? total : atoi(e);
+  int want = g_host_devices.load(std::memory_order_relaxed);
+  if (want == 0) want = total;  // "all"
+  if (want < 0) {
+    want = 1;
+    if (const char *e = getenv("ICB_HOST_DEVICES")) want = strcmp(e, "all") == 0 ? total : atoi(e);
+  }
   if (want < 1) want = 1;
   if (want > total) want = total;
   if (want > 16) want = 16;
@@ -704,16 +831,27 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   cfg.numAttrs = getenv("ICB_NO_PDL") ? 0 : 1;
   cfg.gridDim = dim3((lw * p.morph_rows + 127) / 128);
   cfg.blockDim = dim3(128);
-  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p));
-  cfg.gridDim = dim3((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads);
-  cfg.blockDim = dim3(icb::kModThreads);
-  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p));
-  cfg.gridDim = dim3((lw * p.pack_rows + 127) / 128);
-  cfg.blockDim = dim3(128);
-  ICB_CUDA(cudaLaunchKernelEx(&cfg, icb::pvrtc_pack_kernel, p));
-  g_launches.fetch_add(3, std::memory_order_relaxed);
-  ICB_CUDA(cudaGetLastError());
-  if (!d_scratch) ICB_CUDA(cudaFreeAsync(scratch, st));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p);
+  if (e == cudaSuccess) {
+    cfg.gridDim = dim3((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads);
+    cfg.blockDim = dim3(icb::kModThreads);
+    e = cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p);
+  }
+  if (e == cudaSuccess) {
+    cfg.gridDim = dim3((lw * p.pack_rows + 127) / 128);
+    cfg.blockDim = dim3(128);
+    e = cudaLaunchKernelEx(&cfg, icb::pvrtc_pack_kernel, p);
+  }
+  if (e == cudaSuccess) {
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    e = cudaGetLastError();
+  }
+  // the library's own scratch goes back to the pool on every path (stream-ordered: after whatever did launch)
+  if (!d_scratch) {
+    const cudaError_t f = cudaFreeAsync(scratch, st);
+    if (e == cudaSuccess) e = f;
+  }
+  if (e != cudaSuccess) return fail(ICB_ERR_CUDA, "PVRTC launch: %s", cudaGetErrorString(e));
   return ICB_OK;
 }
 
@@ -729,6 +867,7 @@ int icb_pvrtc2_encode_rgba8(const void *d_src, uint32_t h, uint32_t w, void *d_d
   if (!d_src || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
   if (int s = pvrtc_check_shape(h, w)) return s;
   if (reinterpret_cast<uintptr_t>(d_src) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d_dst) % 8 != 0) return fail(ICB_ERR_INVALID, "PVRTC destination must be 8-byte aligned");
   return pvrtc_launch(d_src, d_src, h, w, 0, 0, h / 4, true, d_dst, d_scratch, static_cast<cudaStream_t>(stream));
 }
 
@@ -737,6 +876,8 @@ int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pixel, uint
   if (!d_rows || !d_first_pixel || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
   if (int s = pvrtc_check_shape(h, w)) return s;
   if (reinterpret_cast<uintptr_t>(d_rows) % 16 != 0) return fail(ICB_ERR_INVALID, "PVRTC source must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d_dst) % 8 != 0) return fail(ICB_ERR_INVALID, "PVRTC destination must be 8-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d_first_pixel) % 4 != 0) return fail(ICB_ERR_INVALID, "first-pixel copy must be 4-byte aligned");
   const uint32_t lh = h / 4;
   if (block_row_begin >= block_row_end || block_row_end > lh)
     return fail(ICB_ERR_INVALID, "block row range [%u,%u) outside grid of %u rows", block_row_begin, block_row_end, lh);
@@ -752,6 +893,7 @@ int icb_decode4x4(int codec, const void *d_blocks, uint32_t h, uint32_t w, uint3
   if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
   if (h == 0 || w == 0 || block_cols == 0) return fail(ICB_ERR_INVALID, "zero dimension");
   if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_INVALID, "codec %d has no decoder", codec);
+  if (!block_aligned(codec, d_blocks, true)) return fail(ICB_ERR_INVALID, "block stream %p is not 8-byte aligned", d_blocks);
   const size_t ncomp = codec == ICB_CODEC_DXT5 ? 4 : 3;
   if (dst_pitch < w * ncomp || dst_pitch > 0xffffffffull) return fail(ICB_ERR_INVALID, "bad destination pitch %zu", dst_pitch);
   DeviceInfo info;
@@ -790,15 +932,16 @@ int icb_decompress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t 
   const size_t need_in = static_cast<size_t>((h + 3) / 4) * block_cols * block_bytes, need_out = static_cast<size_t>(h) * w * ncomp;
   if (blocks_size < need_in) return fail(ICB_ERR_SIZE, "block stream is %zu bytes, need %zu", blocks_size, need_in);
   if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
+  PipeLease lease;
   HostPipe *pipe_ptr = nullptr;
-  if (int s = current_pipe(&pipe_ptr)) return s;
+  if (int s = lease.acquire(&pipe_ptr)) return s;
   HostPipe &pipe = *pipe_ptr;
   if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_in)) return s;     // blocks live in the "dst" buffer
   if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_out)) return s;    // pixels in the "src" buffer
   if (int s = upload_contiguous(pipe, pipe.d_dst, blocks, need_in, pipe.compute)) return s;
   const int swap_rb = (format == ICB_BGR || format == ICB_BGRA);
   if (int s = icb_decode4x4(codec, pipe.d_dst, h, w, block_cols, swap_rb, pipe.d_src, w * ncomp, pipe.compute)) return s;
-  return download_contiguous_sync(pipe, dst, pipe.d_src, need_out, pipe.compute);
+  return lease.finish(download_contiguous_sync(pipe, dst, pipe.d_src, need_out, pipe.compute));
 }
 
 // ---- compressed-domain operations ----------------------------------------------------------------------------
@@ -813,16 +956,18 @@ static int blockop_grid(uint64_t total, int threads, uint32_t *grid) {
   return ICB_OK;
 }
 
-static int check_4x4_codec(int codec, int strategy) {
+static int check_4x4_codec(int codec, int strategy, const void *d_in = nullptr, const void *d_out = nullptr) {
   if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_INVALID, "codec %d is not a 4x4 block codec", codec);
   if (strategy < 0 || strategy > 3) return fail(ICB_ERR_INVALID, "unknown ETC strategy %d", strategy);
+  if (!block_aligned(codec, d_in, true)) return fail(ICB_ERR_INVALID, "block stream %p is not 8-byte aligned", d_in);
+  if (!block_aligned(codec, d_out)) return fail(ICB_ERR_INVALID, "destination %p is not aligned to the %d-byte block", d_out, codec == ICB_CODEC_DXT5 ? 16 : 8);
   return ICB_OK;
 }
 
 int icb_downsample4x4(int codec, int strategy, const void *d_blocks, uint32_t h, uint32_t w, void *d_dst, void *stream) {
   if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
   if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero dimension");
-  if (int s = check_4x4_codec(codec, strategy)) return s;
+  if (int s = check_4x4_codec(codec, strategy, d_blocks, d_dst)) return s;
   icb::Downsample4x4Params p;
   p.in = static_cast<const uint8_t *>(d_blocks);
   p.out = static_cast<uint8_t *>(d_dst);
@@ -853,7 +998,7 @@ int icb_pad4x4(int codec, int strategy, const void *d_blocks, uint32_t ch, uint3
                void *d_dst, void *stream) {
   if (!d_blocks || !d_dst) return fail(ICB_ERR_INVALID, "null device pointer");
   if (ch == 0 || cw == 0) return fail(ICB_ERR_INVALID, "zero dimension");
-  if (int s = check_4x4_codec(codec, strategy)) return s;
+  if (int s = check_4x4_codec(codec, strategy, d_blocks, d_dst)) return s;
   const size_t block_bytes = codec == ICB_CODEC_DXT5 ? 16 : 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   icb::Pad4x4Params p;
@@ -899,7 +1044,7 @@ int icb_copy_subimage4x4(int codec, const void *d_blocks, uint32_t ch, uint32_t 
 int icb_fill_solid4x4(int codec, const uint8_t *colour, uint32_t h, uint32_t w, void *d_dst, void *stream) {
   if (!d_dst || !colour) return fail(ICB_ERR_INVALID, "null pointer");
   if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero dimension");
-  if (int s = check_4x4_codec(codec, 0)) return s;
+  if (int s = check_4x4_codec(codec, 0, nullptr, d_dst)) return s;
   const uint32_t packed = colour[0] | (colour[1] << 8) | (colour[2] << 16) |
                           (codec == ICB_CODEC_DXT5 ? static_cast<uint32_t>(colour[3]) << 24 : 0u);
   const uint64_t n = static_cast<uint64_t>(blocks_of(h)) * blocks_of(w);
@@ -918,6 +1063,7 @@ int icb_fill_solid4x4(int codec, const uint8_t *colour, uint32_t h, uint32_t w, 
 int icb_transcode_dxt1_to_etc1(void *d_blocks, size_t num_blocks, void *stream) {
   if (num_blocks == 0) return ICB_OK;
   if (!d_blocks) return fail(ICB_ERR_INVALID, "null device pointer");
+  if (reinterpret_cast<uintptr_t>(d_blocks) % 8 != 0) return fail(ICB_ERR_INVALID, "block stream %p is not 8-byte aligned", d_blocks);
   uint32_t grid;
   if (int s = blockop_grid(num_blocks, icb::kBlockOpThreads, &grid)) return s;
   icb::transcode_dxt1_to_etc1_kernel<<<grid, icb::kBlockOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -964,8 +1110,9 @@ int icb_blockop_host(int op, int codec, int strategy, const uint32_t *args, cons
   }
   if (op != ICB_OP_SOLID && src_size < need_in) return fail(ICB_ERR_SIZE, "source is %zu bytes, need %zu", src_size, need_in);
   if (dst_size != need_out) return fail(ICB_ERR_SIZE, "destination is %zu bytes, need %zu", dst_size, need_out);
+  PipeLease lease;
   HostPipe *pipe_ptr = nullptr;
-  if (int s = current_pipe(&pipe_ptr)) return s;
+  if (int s = lease.acquire(&pipe_ptr)) return s;
   HostPipe &pipe = *pipe_ptr;
   if (int s = HostPipe::grow(&pipe.d_src, &pipe.src_cap, need_in > 16 ? need_in : 16)) return s;
   if (int s = HostPipe::grow(&pipe.d_dst, &pipe.dst_cap, need_out > 16 ? need_out : 16)) return s;
@@ -991,13 +1138,10 @@ int icb_blockop_host(int op, int codec, int strategy, const uint32_t *args, cons
       result = pipe.d_src;
       break;
   }
-  if (s != ICB_OK) {
-    cudaStreamSynchronize(st);
-    return s;
-  }
-  if (need_out) return download_contiguous_sync(pipe, dst, result, need_out, st);
+  if (s != ICB_OK) return s;  // the lease quiesces the pipe
+  if (need_out) return lease.finish(download_contiguous_sync(pipe, dst, result, need_out, st));
   ICB_CUDA(cudaStreamSynchronize(st));
-  return ICB_OK;
+  return lease.finish(ICB_OK);
 }
 
 int icb_fill_synthetic(void *d_dst, size_t bytes, uint64_t seed, uint64_t byte_offset, void *stream) {
@@ -1064,8 +1208,11 @@ int icb_ipc_close(void *d_ptr) {
   return ICB_OK;
 }
 
-int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t padded_h, uint32_t padded_w,
-                      uint32_t padding, int strategy, const void *src, void *dst, size_t dst_size) {
+// Body of icb_compress_host / icb_ctx_compress_host.  ctx_devs == NULL: the current device (plus ICB_HOST_DEVICES /
+// icb_set_host_devices); otherwise exactly those devices, the first being the one that takes the single-device cases.
+static int compress_host_impl(const int *ctx_devs, int ctx_ndev, int codec, int format, uint32_t h, uint32_t w,
+                              uint32_t padded_h, uint32_t padded_w, uint32_t padding, int strategy, const void *src,
+                              void *dst, size_t dst_size) {
   // Same rejections, in the same order of concern, as the reference entry points
   // (dxtc_compressor.cc:739, etc_compressor.cc:751-754, pvrtc_compressor.cc:640-650).
   if (!src || !dst || h == 0 || w == 0) return fail(ICB_ERR_INVALID, "null buffer or zero dimension");
@@ -1076,8 +1223,19 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   if (codec == ICB_CODEC_ETC1 && format != ICB_RGB) return fail(ICB_ERR_INVALID, "ETC1 supports kRGB only");
   if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_PVRTC2) return fail(ICB_ERR_INVALID, "unknown codec %d", codec);
 
+  struct RestoreDevice {  // the caller's current device is unchanged on return, whatever path is taken
+    int dev = -1;
+    ~RestoreDevice() {
+      if (dev >= 0) cudaSetDevice(dev);
+    }
+  } restore;
+  if (ctx_devs) {
+    ICB_CUDA(cudaGetDevice(&restore.dev));
+    ICB_CUDA(cudaSetDevice(ctx_devs[0]));
+  }
+  PipeLease lease;
   HostPipe *pipe_ptr = nullptr;
-  if (int s = current_pipe(&pipe_ptr)) return s;
+  if (int s = lease.acquire(&pipe_ptr)) return s;
   HostPipe &pipe = *pipe_ptr;
 
   if (codec == ICB_CODEC_PVRTC2) {
@@ -1091,7 +1249,7 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
     if (int s = HostPipe::grow(&pipe.d_scratch, &pipe.scratch_cap, icb_pvrtc2_scratch_size(h, w))) return s;
     if (int s = upload_contiguous(pipe, pipe.d_src, src, src_bytes, pipe.compute)) return s;
     if (int s = icb_pvrtc2_encode_rgba8(pipe.d_src, h, w, pipe.d_dst, pipe.d_scratch, pipe.compute)) return s;
-    return download_contiguous_sync(pipe, dst, pipe.d_dst, need, pipe.compute);
+    return lease.finish(download_contiguous_sync(pipe, dst, pipe.d_dst, need, pipe.compute));
   }
 
   const uint32_t coded_h = padded_h > h ? padded_h : h, coded_w = padded_w > w ? padded_w : w;
@@ -1120,14 +1278,19 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   // that case stays on one device.
   int devs[16], ndev = 1, home = 0;
   ICB_CUDA(cudaGetDevice(&home));
-  if (int s = host_devices(devs, &ndev)) return s;
+  if (ctx_devs) {
+    ndev = ctx_ndev < 16 ? ctx_ndev : 16;
+    for (int k = 0; k < ndev; ++k) devs[k] = ctx_devs[k];
+  } else if (int s = host_devices(devs, &ndev)) {
+    return s;
+  }
   if (static_cast<uint32_t>(ndev) > num_chunks) ndev = static_cast<int>(num_chunks);
   if (coded_h > (h + 3) / 4 * 4) ndev = 1;
   HostPipe *pipes[16];
   pipes[0] = &pipe;
   for (int k = 1; k < ndev; ++k) {
     ICB_CUDA(cudaSetDevice(devs[k]));
-    const int s = current_pipe(&pipes[k]);
+    const int s = lease.acquire(&pipes[k]);
     if (s != ICB_OK) {
       cudaSetDevice(home);
       return s;
@@ -1224,7 +1387,224 @@ int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t pa
   };
   const int status = run();
   if (ndev > 1) cudaSetDevice(home);
+  return lease.finish(status);
+}
+
+int icb_compress_host(int codec, int format, uint32_t h, uint32_t w, uint32_t padded_h, uint32_t padded_w,
+                      uint32_t padding, int strategy, const void *src, void *dst, size_t dst_size) {
+  return compress_host_impl(nullptr, 0, codec, format, h, w, padded_h, padded_w, padding, strategy, src, dst, dst_size);
+}
+
+int icb_set_host_devices(int n) {
+  int total = 0;
+  if (n > 0 && (cudaGetDeviceCount(&total) != cudaSuccess || n > total)) {
+    cudaGetLastError();
+    return fail(ICB_ERR_INVALID, "icb_set_host_devices(%d): only %d device(s) visible", n, total);
+  }
+  const int prev = g_host_devices.exchange(n < 0 ? -1 : n);
+  return prev < 0 ? 0x7fffffff : prev;
+}
+
+size_t icb_trim(void) {
+  size_t bytes = PipePool::get().trim();
+  // the stream-ordered scratch pools of the devices this process has used
+  int cur = 0, total = 0;
+  if (cudaGetDevice(&cur) == cudaSuccess && cudaGetDeviceCount(&total) == cudaSuccess) {
+    for (int d = 0; d < total && d < 64; ++d) {
+      cudaMemPool_t pool = scratch_pool_if_created(d);
+      if (pool) cudaMemPoolTrimTo(pool, 0);
+    }
+  }
+  cudaGetLastError();
+  return bytes;
+}
+
+size_t icb_idle_pipes(void) { return PipePool::get().idle_count(); }
+
+// ---- one image over several GPUs from ONE process -----------------------------
+
+struct icb_ctx {
+  int n = 0;
+  int devs[16] = {};
+  cudaStream_t streams[16] = {};  // [0] unused: the root works on the caller's stream
+  cudaEvent_t fork = nullptr, done[16] = {};
+  bool peer_stores = false;       // every non-root device can store into the root's memory
+};
+
+int icb_ctx_create(int n_dev, const int *dev_ids, icb_ctx **out) {
+  if (!out) return fail(ICB_ERR_INVALID, "null result pointer");
+  *out = nullptr;
+  int total = 0;
+  ICB_CUDA(cudaGetDeviceCount(&total));
+  if (n_dev == 0) n_dev = total;  // "all"
+  if (n_dev < 1 || n_dev > 16 || n_dev > total) return fail(ICB_ERR_INVALID, "asked for %d devices, %d visible (at most 16 per context)", n_dev, total);
+  int home = 0;
+  ICB_CUDA(cudaGetDevice(&home));
+  icb_ctx *ctx = new icb_ctx();
+  ctx->n = n_dev;
+  for (int k = 0; k < n_dev; ++k) {
+    ctx->devs[k] = dev_ids ? dev_ids[k] : k;
+    bool dup = ctx->devs[k] < 0 || ctx->devs[k] >= total;
+    for (int j = 0; j < k; ++j) dup = dup || ctx->devs[j] == ctx->devs[k];
+    if (dup) {
+      delete ctx;
+      return fail(ICB_ERR_INVALID, "device list entry %d (ordinal %d) is out of range or repeated", k, dev_ids ? dev_ids[k] : k);
+    }
+  }
+  auto bail = [&](int status) {
+    icb_ctx_destroy(ctx);
+    cudaSetDevice(home);
+    return status;
+  };
+  ctx->peer_stores = true;
+  for (int k = 0; k < n_dev; ++k) {
+    if (cudaSetDevice(ctx->devs[k]) != cudaSuccess) return bail(fail(ICB_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->devs[k]));
+    DeviceInfo info;
+    if (int s = device_info(&info)) return bail(s);
+    if (k == 0) {
+      if (cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(ICB_ERR_CUDA, "event creation failed"));
+      continue;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->streams[k], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->done[k], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(ICB_ERR_CUDA, "stream / event creation on device %d failed", ctx->devs[k]));
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->devs[k], ctx->devs[0]);
+    if (can) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ctx->devs[0], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+      cudaGetLastError();
+    }
+    if (!can) ctx->peer_stores = false;
+  }
+  cudaSetDevice(home);
+  *out = ctx;
+  return ICB_OK;
+}
+
+int icb_ctx_destroy(icb_ctx *ctx) {
+  if (!ctx) return ICB_OK;
+  int home = 0;
+  const bool have_home = cudaGetDevice(&home) == cudaSuccess;
+  for (int k = 0; k < ctx->n; ++k) {
+    if (cudaSetDevice(ctx->devs[k]) != cudaSuccess) continue;
+    if (ctx->streams[k]) {
+      cudaStreamSynchronize(ctx->streams[k]);
+      cudaStreamDestroy(ctx->streams[k]);
+    }
+    if (ctx->done[k]) cudaEventDestroy(ctx->done[k]);
+    if (k == 0 && ctx->fork) cudaEventDestroy(ctx->fork);
+  }
+  if (have_home) cudaSetDevice(home);
+  cudaGetLastError();
+  delete ctx;
+  return ICB_OK;
+}
+
+int icb_ctx_device_count(const icb_ctx *ctx) { return ctx ? ctx->n : 0; }
+int icb_ctx_device(const icb_ctx *ctx, int k) { return (ctx && k >= 0 && k < ctx->n) ? ctx->devs[k] : -1; }
+int icb_ctx_peer_stores(const icb_ctx *ctx) { return ctx && ctx->peer_stores ? 1 : 0; }
+
+int icb_stripe_partition(int n, uint32_t grid_rows, int root_share_permille, uint32_t *splits) {
+  if (n < 1 || !splits) return fail(ICB_ERR_INVALID, "bad partition request");
+  if (root_share_permille > 1000) root_share_permille = 1000;
+  // Stripes are whole tile rows (4 block rows) wherever the grid allows it, so that only the last stripe can leave
+  // rows to the generic kernel.
+  const uint32_t unit = grid_rows >= 4u * static_cast<uint32_t>(n) ? 4u : 1u;
+  const uint32_t units = grid_rows / unit;  // the remainder goes to the last stripe
+  uint32_t root_units = units / n + (units % n ? 1u : 0u);  // even split: the first ranks take the extra unit
+  if (n > 1 && root_share_permille >= 0) {
+    const uint64_t want = (static_cast<uint64_t>(units) * root_share_permille + 500) / 1000;
+    if (want > root_units) root_units = static_cast<uint32_t>(want);
+    if (root_units > units) root_units = units;
+  }
+  splits[0] = 0;
+  if (n == 1) {
+    splits[1] = grid_rows;
+    return ICB_OK;
+  }
+  const bool even = root_share_permille < 0 || root_units == units / n + (units % n ? 1u : 0u);
+  if (even) {
+    const uint32_t base = units / n, extra = units % n;
+    for (int r = 0; r < n; ++r) splits[r + 1] = splits[r] + (base + (static_cast<uint32_t>(r) < extra ? 1u : 0u)) * unit;
+  } else {
+    splits[1] = root_units * unit;
+    const uint32_t rest = units - root_units, base = rest / (n - 1), extra = rest % (n - 1);
+    for (int r = 1; r < n; ++r) splits[r + 1] = splits[r] + (base + (static_cast<uint32_t>(r - 1) < extra ? 1u : 0u)) * unit;
+  }
+  splits[n] = grid_rows;
+  return ICB_OK;
+}
+
+int icb_root_share_permille(int codec, int format_components, int n) {
+  if (n <= 1) return 1000;
+  // Root share f that equalises "root encodes f of the image" with "the other 1-f arrives over the root's NVLink
+  // ingress": f = t_link / (t_link + t_kernel), both for the whole image.  Measured on B200:
+  // NVLink ingress by peer stores ~720 GB/s; whole-image kernel times per output byte below.
+  double t_kernel_per_out_byte, t_link_per_out_byte = 1.0 / 720e9;
+  switch (codec) {
+    case ICB_CODEC_DXT1: t_kernel_per_out_byte = (format_components == 4 ? 51.5e-6 : 53.0e-6) / 33554432.0; break;
+    case ICB_CODEC_DXT5: t_kernel_per_out_byte = 80e-6 / 67108864.0; break;
+    case ICB_CODEC_ETC1: t_kernel_per_out_byte = 156e-6 / 8388608.0; break;
+    default: return -1;
+  }
+  const double f = t_link_per_out_byte / (t_link_per_out_byte + t_kernel_per_out_byte);
+  const int permille = static_cast<int>(f * 1000.0 + 0.5);
+  const int even = (1000 + n - 1) / n;
+  return permille > even ? permille : -1;  // -1: an even split is already compute-bound
+}
+
+int icb_encode_sharded(icb_ctx *ctx, int codec, int format, uint32_t h, uint32_t w, size_t src_pitch, int strategy,
+                       const uint32_t *splits, const void *const *d_src_stripes, void *d_dst, void *stream) {
+  if (!ctx || !splits || !d_src_stripes || !d_dst) return fail(ICB_ERR_INVALID, "null argument");
+  if (codec < ICB_CODEC_DXT1 || codec > ICB_CODEC_ETC1) return fail(ICB_ERR_UNSUPPORTED, "sharded encode covers the 4x4 codecs (PVRTC: icb_pvrtc2_encode_stripe)");
+  if (format < ICB_RGB || format > ICB_BGRA) return fail(ICB_ERR_INVALID, "unknown format %d", format);
+  if (h == 0 || w == 0) return fail(ICB_ERR_INVALID, "zero image dimension");
+  const int ncomp = (format == ICB_RGB || format == ICB_BGR) ? 3 : 4;
+  const int swap_rb = (format == ICB_BGR || format == ICB_BGRA);
+  if (codec == ICB_CODEC_DXT5 && ncomp != 4) return fail(ICB_ERR_INVALID, "DXT5 needs a 4-component format");
+  if (codec == ICB_CODEC_ETC1 && format != ICB_RGB) return fail(ICB_ERR_INVALID, "ETC1 supports kRGB only");
+  if (ctx->n > 1 && !ctx->peer_stores) return fail(ICB_ERR_UNSUPPORTED, "no peer access from every device of the context to device %d", ctx->devs[0]);
+  const uint32_t grid_rows = (h + 3) / 4, grid_cols = (w + 3) / 4;
+  if (splits[0] != 0 || splits[ctx->n] != grid_rows) return fail(ICB_ERR_INVALID, "splits must run from 0 to %u", grid_rows);
+  for (int r = 0; r < ctx->n; ++r)
+    if (splits[r] > splits[r + 1]) return fail(ICB_ERR_INVALID, "splits must be non-decreasing");
+  const size_t bb = codec == ICB_CODEC_DXT5 ? 16 : 8;
+  int home = 0;
+  ICB_CUDA(cudaGetDevice(&home));
+  cudaStream_t root_stream = static_cast<cudaStream_t>(stream);
+  auto run = [&]() -> int {
+    ICB_CUDA(cudaSetDevice(ctx->devs[0]));
+    if (ctx->n > 1) ICB_CUDA(cudaEventRecord(ctx->fork, root_stream));
+    // peers first: their kernels are the ones whose stores cross NVLink, so they should start earliest
+    for (int k = 1; k <= ctx->n; ++k) {
+      const int r = k % ctx->n;  // 1, 2, ..., n-1, 0
+      const uint32_t r0 = splits[r], r1 = splits[r + 1];
+      if (r1 == r0) continue;
+      if (!d_src_stripes[r]) return fail(ICB_ERR_INVALID, "null stripe pointer for device %d", r);
+      ICB_CUDA(cudaSetDevice(ctx->devs[r]));
+      cudaStream_t st = r == 0 ? root_stream : ctx->streams[r];
+      if (r != 0) ICB_CUDA(cudaStreamWaitEvent(st, ctx->fork, 0));
+      // virtual address of pixel (0,0): rows above the stripe are never touched
+      const uint8_t *base = static_cast<const uint8_t *>(d_src_stripes[r]) - static_cast<size_t>(r0) * 4 * src_pitch;
+      uint8_t *out = static_cast<uint8_t *>(d_dst) + static_cast<size_t>(r0) * grid_cols * bb;
+      if (int s = encode4x4(codec, ncomp, base, h, w, src_pitch, h, w, swap_rb, strategy, r0, r1, out, st)) return s;
+      if (r != 0) ICB_CUDA(cudaEventRecord(ctx->done[r], st));
+    }
+    ICB_CUDA(cudaSetDevice(ctx->devs[0]));
+    for (int r = 1; r < ctx->n; ++r)
+      if (splits[r + 1] > splits[r]) ICB_CUDA(cudaStreamWaitEvent(root_stream, ctx->done[r], 0));
+    return ICB_OK;
+  };
+  const int status = run();
+  cudaSetDevice(home);
   return status;
+}
+
+int icb_ctx_compress_host(icb_ctx *ctx, int codec, int format, uint32_t h, uint32_t w, uint32_t padded_h,
+                          uint32_t padded_w, uint32_t padding, int strategy, const void *src, void *dst, size_t dst_size) {
+  if (!ctx) return fail(ICB_ERR_INVALID, "null context");
+  return compress_host_impl(ctx->devs, ctx->n, codec, format, h, w, padded_h, padded_w, padding, strategy, src, dst, dst_size);
 }
 
 }  // extern "C"

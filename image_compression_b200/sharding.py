@@ -31,11 +31,16 @@ def pvrtc_stripe_row_indices(height, r0, r1):
     return [(4 * (r0 - 1) + k) % height for k in range(4 * (r1 - r0 + 2))]
 
 
-def gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, group=None):
+def gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, group=None, splits=None):
     """Gathers every rank's stripe of packed blocks (uint8 tensor) onto `dst`; returns the whole stream there and
-    None elsewhere.  Equal stripes use one gather; uneven ones are padded to the largest stripe and trimmed."""
+    None elsewhere.  Equal stripes use one gather; uneven ones are padded to the largest stripe and trimmed.
+    `splits` (world + 1 block-row boundaries, e.g. from icb_stripe_partition) overrides the stripe_rows partition."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = [stripe_bytes(grid_rows, grid_cols, block_bytes, r, world) for r in range(world)]
+    if splits is not None:
+        assert len(splits) == world + 1 and splits[0] == 0 and splits[-1] == grid_rows
+        sizes = [(splits[r + 1] - splits[r]) * grid_cols * block_bytes for r in range(world)]
+    else:
+        sizes = [stripe_bytes(grid_rows, grid_cols, block_bytes, r, world) for r in range(world)]
     assert local.numel() == sizes[rank] and local.dtype == torch.uint8
     biggest = max(sizes)
     send = local if sizes[rank] == biggest else torch.cat([local, local.new_zeros(biggest - sizes[rank])])

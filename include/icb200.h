@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ICB_ABI_VERSION 1
+#define ICB_ABI_VERSION 2
 
 typedef enum icb_status {
   ICB_OK = 0,
@@ -79,6 +79,9 @@ ICB_API size_t icb_compressed_size(int codec, uint32_t coded_height, uint32_t co
  * The block grid covers coded_height x coded_width pixels (>= height, width; equal for Compress, the padded size
  * for CompressAndPad); windows beyond the image replicate its last row / column.  d_dst receives
  * ceil(coded_height/4) * ceil(coded_width/4) blocks in raster order.  swap_rb selects kBGR / kBGRA.
+ * Alignment: d_dst (here and in every entry point that writes blocks) must be aligned to the block size, 8 bytes
+ * (DXT1, ETC1, PVRTC) or 16 (DXT5); block streams that are READ (decoders, block operations) to 8 bytes;
+ * ICB_ERR_INVALID otherwise.  d_src may have any alignment and pitch (16-byte aligned base and pitch take the TMA path).
  */
 ICB_API int icb_dxt1_encode_rgb8(const void *d_src, uint32_t height, uint32_t width, size_t src_pitch, uint32_t coded_height,
                          uint32_t coded_width, int swap_rb, void *d_dst, void *stream);
@@ -135,6 +138,67 @@ ICB_API int icb_pvrtc2_encode_stripe(const void *d_rows, const void *d_first_pix
 ICB_API int icb_compress_host(int codec, int format, uint32_t height, uint32_t width, uint32_t padded_height,
                       uint32_t padded_width, uint32_t padding_bytes_per_row, int etc_strategy, const void *src,
                       void *dst, size_t dst_size);
+
+/*
+ * How many GPUs icb_compress_host spreads one call over, set by program instead of by ICB_HOST_DEVICES (what a C++
+ * caller of Compress() uses: the classes call icb_compress_host).  n >= 1: that many (the current device and the next
+ * ordinals); 0: all visible devices; < 0: back to the environment variable / one device.  Process-wide.  Returns the
+ * previous setting (0x7fffffff if there was none) or a negative icb_status.
+ */
+ICB_API int icb_set_host_devices(int n);
+
+/*
+ * Host-path resources.  The host-buffer entry points (icb_compress_host, icb_decompress_host, icb_blockop_host) work
+ * through "pipes" -- three streams, events, device buffers for the image and its blocks, pinned staging rings -- that
+ * are leased from a process-wide pool for the duration of one call and handed back afterwards; concurrent calls get a
+ * pipe each, and a host thread that exits leaves nothing behind.  A pooled pipe's buffers only ever grow (a pipe that
+ * has encoded an 8192x8192 RGBA8 image keeps ~300 MB of device memory plus up to 96 MB of pinned memory), so the pool
+ * holds `peak concurrent calls` pipes per device until icb_trim() frees the idle ones (and trims the library's
+ * stream-ordered scratch pools).  icb_trim returns the bytes it released; icb_idle_pipes the number of pooled pipes.
+ */
+ICB_API size_t icb_trim(void);
+ICB_API size_t icb_idle_pipes(void);
+
+/*
+ * One image over several GPUs from ONE process -- the C-ABI form of the row-stripe
+ * sharding that bench.py / image_compression_b200.sharding do with one process per GPU.  Replaces the same loop as
+ * the single-GPU encoders, Compressor4x4Helper::Compress (internal/compressor4x4_helper.h:202-214), cut into stripes
+ * of whole block rows.
+ *
+ * icb_ctx_create        n_dev devices (dev_ids NULL = ordinals 0..n_dev-1; n_dev 0 = all visible).  dev_ids[0] is the
+ *                       ROOT: the device that ends up holding the packed block stream.  Creates one stream per
+ *                       non-root device and enables peer access from every device to the root
+ *                       (cudaDeviceEnablePeerAccess -- one process, so no IPC handles are needed).
+ * icb_stripe_partition  block rows of stripe r = [splits[r], splits[r+1]), n+1 entries.  root_share_permille < 0: even
+ *                       split.  Otherwise the root's stripe is at least that share of the rows and the rest is split
+ *                       evenly: with the stream delivered to the root, the job is bounded by the root's NVLink ingress
+ *                       from N = 4 up, and the fastest partition lets the root encode while the others' blocks arrive
+ *                       (icb_root_share_permille gives the share that balances the two on B200; it returns -1 where
+ *                       an even split is already compute-bound, e.g. ETC1).  Stripes are multiples of 4 block rows.
+ * icb_encode_sharded    d_src_stripes[r]: device pointer, resident on device r of the context, to the first pixel row
+ *                       (row 4*splits[r]) of stripe r, src_pitch bytes per row.  d_dst: on the root, the WHOLE
+ *                       stream (icb_compressed_size bytes).  Every device encodes its stripe and stores the blocks
+ *                       straight into d_dst -- peer stores over NVLink, no gather pass.  `stream` is a stream of the
+ *                       root device: the other devices' work is ordered after what it holds (event fork) and it
+ *                       waits for all of them (event join), so the call is asynchronous and stream-ordered like the
+ *                       single-GPU encoders.  The caller's current device is unchanged on return.
+ * icb_ctx_compress_host icb_compress_host over exactly the context's devices (each uploads, encodes and downloads its
+ *                       own chunks over its own PCIe link; nothing is gathered).
+ */
+typedef struct icb_ctx icb_ctx;
+ICB_API int icb_ctx_create(int n_dev, const int *dev_ids, icb_ctx **ctx);
+ICB_API int icb_ctx_destroy(icb_ctx *ctx);
+ICB_API int icb_ctx_device_count(const icb_ctx *ctx);
+ICB_API int icb_ctx_device(const icb_ctx *ctx, int k);
+ICB_API int icb_ctx_peer_stores(const icb_ctx *ctx);
+ICB_API int icb_stripe_partition(int n, uint32_t grid_rows, int root_share_permille, uint32_t *splits);
+ICB_API int icb_root_share_permille(int codec, int format_components, int n);
+ICB_API int icb_encode_sharded(icb_ctx *ctx, int codec, int format, uint32_t height, uint32_t width, size_t src_pitch,
+                               int etc_strategy, const uint32_t *splits, const void *const *d_src_stripes, void *d_dst,
+                               void *stream);
+ICB_API int icb_ctx_compress_host(icb_ctx *ctx, int codec, int format, uint32_t height, uint32_t width,
+                                  uint32_t padded_height, uint32_t padded_width, uint32_t padding_bytes_per_row,
+                                  int etc_strategy, const void *src, void *dst, size_t dst_size);
 
 /*
  * Block decoders (DXT1 -> RGB888, DXT5 -> RGBA8888, ETC1 -> RGB888), the step after the compress path:

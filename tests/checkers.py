@@ -263,3 +263,61 @@ def ref_transcode(blocks):
     out = np.ascontiguousarray(blocks).copy()
     ref().icref_transcode(_ptr(out), out.size)
     return out
+
+
+# ---- whole-image CPU answers at benchmark sizes ------------------------------------------------------------------
+
+def cpu_encode_full(workload, img, h, w, threads=None):
+    """The CPU answer for a whole BASELINE-size image in about a second: the unmodified reference (oracle/_ref) when it
+    was built, else the oracle port, run on T row stripes from T threads, each writing its slice of the output through
+    an external-storage CompressedImage -- byte-identical to the one-thread result because
+    4x4 blocks are independent (tests/test_oracle.py checks that claim on small images).  PVRTC cannot be split
+    (toroidal wrap, Z-order): one thread.  workload: dxt1_rgb8 | dxt1_rgba8 | dxt5_rgba8 | etc1_rgb8 | pvrtc2_rgba8;
+    `img` is the image in the workload's own pixel format (dxt1_rgba8: RGBA, alpha stripped here for the reference,
+    which has no such entry).  Returns (blocks, kind) with kind "reference" or "port"."""
+    import threading
+    use_ref = have_ref()
+    kind = "reference" if use_ref else "port"
+    img = np.ascontiguousarray(img).reshape(-1)
+    if workload == "pvrtc2_rgba8":
+        return (ref_pvrtc(img, h, w) if use_ref else oracle_pvrtc(img, h, w)), kind
+    assert h % 4 == 0 and w % 4 == 0, "stripe split is for block-aligned sizes"
+    nc_in = 3 if workload in ("dxt1_rgb8", "etc1_rgb8") else 4
+    nc = nc_in
+    if workload == "dxt1_rgba8":
+        img = np.ascontiguousarray(img.reshape(-1, 4)[:, :3]).reshape(-1)
+        nc = 3
+    bb = 16 if workload == "dxt5_rgba8" else 8
+    threads = threads or min(os.cpu_count() or 1, 64)
+    grid_rows = h // 4
+    threads = max(1, min(threads, grid_rows))
+    out = np.zeros(grid_rows * (w // 4) * bb, np.uint8)
+    bounds = [grid_rows * t // threads for t in range(threads + 1)]
+    errors = []
+
+    def job(t):
+        r0, r1 = bounds[t], bounds[t + 1]
+        if r1 == r0:
+            return
+        rows = (r1 - r0) * 4
+        s = img[r0 * 4 * w * nc:r1 * 4 * w * nc]
+        o = out[r0 * (w // 4) * bb:r1 * (w // 4) * bb]
+        if use_ref:
+            if workload == "etc1_rgb8":
+                ok = ref().icref_etc_external(ETC_SMALLER_ERROR, rows, w, 0, _ptr(s), _ptr(o), o.size)
+            else:
+                ok = ref().icref_dxt_external(RGB if nc == 3 else RGBA, rows, w, 0, _ptr(s), _ptr(o), o.size)
+            if ok != 1:
+                errors.append(t)
+        elif workload == "etc1_rgb8":
+            oracle().orc_etc1_compress(ETC_SMALLER_ERROR, rows, w, rows, w, 0, _ptr(s), _ptr(o))
+        else:
+            oracle().orc_dxt_compress(RGB if nc == 3 else RGBA, rows, w, rows, w, 0, _ptr(s), _ptr(o))
+
+    ts = [threading.Thread(target=job, args=(t,)) for t in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, "reference refused stripes %s" % errors
+    return out, kind

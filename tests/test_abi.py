@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(icb):
     handle = C.CDLL(icb.lib_path())
     for name in header_functions():
         assert hasattr(handle, name), name
-    assert icb.lib().icb_abi_version() == 1
+    assert icb.lib().icb_abi_version() == 2
 
 
 def test_compressed_size_rules(icb):
@@ -54,6 +54,53 @@ def test_stripe_partition_covers_grid(icb):
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_c_abi_stripe_partition(icb):
+    """icb_stripe_partition: contiguous cover of the grid, whole tile rows (4 block rows) per stripe where the grid allows,
+    even split == sizes within one unit, root-heavy split gives the root at least its share and splits the rest evenly."""
+    for rows in (1, 7, 8, 31, 2048, 2049, 513, 1024):
+        for n in (1, 2, 3, 4, 8):
+            s = icb.stripe_partition(n, rows)
+            assert s[0] == 0 and s[-1] == rows and all(a <= b for a, b in zip(s, s[1:])) and len(s) == n + 1
+            unit = 4 if rows >= 4 * n else 1
+            assert all(x % unit == 0 for x in s[:-1])
+            sizes = [b - a for a, b in zip(s, s[1:])]
+            assert max(sizes) - min(sizes) <= unit + rows % unit
+            for share in (0, 300, 475, 900, 1000):
+                t = icb.stripe_partition(n, rows, share)
+                assert t[0] == 0 and t[-1] == rows and all(a <= b for a, b in zip(t, t[1:]))
+                if n > 1 and rows >= 4 * n:
+                    assert t[1] >= max(s[1], (rows // 4 * share + 500) // 1000 * 4) - 4
+                    rest = [b - a for a, b in zip(t[1:], t[2:])]
+                    assert max(rest[:-1] or [0]) - min(rest[:-1] or [0]) <= 4
+    assert icb.stripe_partition(8, 2048, 475)[1] == 972
+    # B200 balance points: DXT1/DXT5 are NVLink-ingress bound from N = 4 up (root-heavy), ETC1 never is (even split)
+    assert icb.root_share_permille(icb.CODEC_DXT1, icb.RGBA, 1) == 1000
+    assert icb.root_share_permille(icb.CODEC_DXT1, icb.RGBA, 2) == -1 or icb.root_share_permille(icb.CODEC_DXT1, icb.RGBA, 2) >= 500
+    assert 400 <= icb.root_share_permille(icb.CODEC_DXT1, icb.RGBA, 8) <= 600
+    assert 400 <= icb.root_share_permille(icb.CODEC_DXT5, icb.RGBA, 8) <= 650
+    assert icb.root_share_permille(icb.CODEC_ETC1, icb.RGB, 8) == -1
+
+
+def test_misaligned_block_pointers_are_rejected_before_any_launch(icb):
+    """Blocks move as 8/16-byte vectors: a misaligned stream pointer is ICB_ERR_INVALID, not a sticky device fault."""
+    L = icb.lib()
+    base = 0x7f0000000000
+    assert L.icb_dxt1_encode_rgba8(base, 16, 16, 64, 16, 16, 0, base + 4, None) == -1
+    assert L.icb_dxt5_encode_rgba8(base, 16, 16, 64, 16, 16, 0, base + 8, None) == -1
+    assert L.icb_encode4x4_stripe(icb.CODEC_ETC1, 3, base, 16, 16, 48, 16, 16, 0, 2, 0, 4, base + 2, None) == -1
+    assert L.icb_decode4x4(icb.CODEC_DXT1, base + 4, 16, 16, 4, 0, base, 48, None) == -1
+    assert L.icb_downsample4x4(icb.CODEC_DXT5, 2, base, 16, 16, base + 8, None) == -1
+    assert L.icb_pvrtc2_encode_rgba8(base, 8, 8, base + 4, None, None) == -1
+    assert b"align" in L.icb_last_error()
+
+
+def test_pipe_pool_entry_points_need_no_device(icb):
+    L = icb.lib()
+    assert L.icb_idle_pipes() == 0
+    assert L.icb_trim() == 0
+    assert L.icb_set_host_devices(-1) == 0x7fffffff  # nothing was set before: "no previous setting"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device failure mode")

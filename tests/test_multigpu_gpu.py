@@ -129,3 +129,63 @@ def test_host_path_spread_over_two_gpus(icb):
             del os.environ["ICB_HOST_DEVICES"]
         else:
             os.environ["ICB_HOST_DEVICES"] = old
+
+
+def _want(icb, codec, nc, img, h, w):
+    if codec == icb.CODEC_ETC1:
+        return ck.oracle_etc1(ck.ETC_SMALLER_ERROR, img, h, w)
+    if codec == icb.CODEC_DXT1 and nc == 4:
+        return ck.oracle_dxt1_rgba(img, h, w)
+    return ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, img, h, w)
+
+
+def _sharded_case(icb, ctx, codec, fmt, nc, h, w, share):
+    n = len(ctx.devices)
+    pitch = w * nc
+    img = ck.synthetic(h * pitch, 12)
+    splits = icb.stripe_partition(n, (h + 3) // 4, share)
+    stripes = []
+    for r in range(n):
+        y0, y1 = min(4 * splits[r], h), min(4 * splits[r + 1], h)
+        stripes.append(torch.from_numpy(img[y0 * pitch:y1 * pitch].copy()).to("cuda:%d" % ctx.devices[r]) if y1 > y0 else None)
+    with torch.cuda.device(ctx.devices[0]):
+        out = torch.zeros(icb.compressed_size(codec, h, w), dtype=torch.uint8, device="cuda:%d" % ctx.devices[0])
+        ctx.encode(codec, fmt, stripes, h, w, splits, out)
+        torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), _want(icb, codec, nc, img, h, w)), (codec, fmt, h, w, share, splits)
+
+
+def test_shard_context_one_device(icb):
+    """icb_ctx_* / icb_encode_sharded with a single device (what a one-GPU box can run): same bytes as the oracle, the
+    call is stream-ordered, the caller's device is untouched."""
+    with icb.ShardContext([0]) as ctx:
+        assert ctx.devices == [0]
+        for codec, fmt, nc, h, w in ((icb.CODEC_DXT1, icb.RGBA, 4, 256, 512), (icb.CODEC_DXT5, icb.RGBA, 4, 130, 256),
+                                     (icb.CODEC_DXT1, icb.BGR, 3, 64, 256), (icb.CODEC_ETC1, icb.RGB, 3, 32, 256)):
+            _sharded_case(icb, ctx, codec, fmt, nc, h, w, -1)
+        img = ck.synthetic(512 * 512 * 4, 13)
+        assert np.array_equal(ctx.compress_host(icb.CODEC_DXT5, icb.RGBA, img, 512, 512), ck.oracle_dxt(ck.RGBA, img, 512, 512))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_shard_context_single_process_multi_gpu(icb):
+    """One process, N GPUs, no IPC: every device encodes its stripe and stores the blocks into the root's buffer through
+    cudaDeviceEnablePeerAccess mappings.  Even and root-heavy partitions, ragged heights, every 4x4 codec; then the
+    host-buffer form over the same devices, and icb_set_host_devices as the programmatic ICB_HOST_DEVICES."""
+    ndev = torch.cuda.device_count()
+    for ids in ([0, 1], [1, 0], list(range(min(ndev, 8)))):
+        with icb.ShardContext(ids) as ctx:
+            assert ctx.peer_stores
+            for codec, fmt, nc, h, w in ((icb.CODEC_DXT1, icb.RGBA, 4, 1024, 512), (icb.CODEC_DXT5, icb.RGBA, 4, 522, 256),
+                                         (icb.CODEC_DXT1, icb.RGB, 3, 260, 512), (icb.CODEC_ETC1, icb.RGB, 3, 64, 256)):
+                for share in (-1, 475, 900):
+                    _sharded_case(icb, ctx, codec, fmt, nc, h, w, share)
+            img = ck.synthetic(4096 * 4096 * 4, 14)
+            want = ck.oracle_dxt1_rgba(img, 4096, 4096)
+            assert np.array_equal(ctx.compress_host(icb.CODEC_DXT1, icb.RGBA, img, 4096, 4096), want)
+            assert torch.cuda.current_device() == 0
+    prev = icb.lib().icb_set_host_devices(2)
+    try:
+        assert np.array_equal(icb.compress_host(icb.CODEC_DXT1, icb.RGBA, img, 4096, 4096), want)
+    finally:
+        icb.lib().icb_set_host_devices(-1 if prev == 0x7fffffff else prev)

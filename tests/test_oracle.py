@@ -280,3 +280,24 @@ def test_oracle_block_ops_match_golden(golden_ops):
         if not meta["refused"]:
             assert np.array_equal(got, want), meta
     assert seen == {"downsample", "pad", "copy_subimage", "solid", "transcode"}
+
+
+def test_threaded_stripe_reference_equals_one_thread():
+    """cpu_encode_full (the full-size checker of tests/test_parity_gpu.py and bench.py's in-run parity flag): T row stripes
+    from T threads == the one-thread answer, for every 4x4 workload, uneven stripe counts included."""
+    for wl, nc in (("dxt1_rgba8", 4), ("dxt1_rgb8", 3), ("dxt5_rgba8", 4), ("etc1_rgb8", 3)):
+        h, w = 52, 64
+        img = ck.synthetic(h * w * nc, 3)
+        if wl == "dxt1_rgba8":
+            want = ck.oracle_dxt1_rgba(img, h, w)
+        elif wl == "etc1_rgb8":
+            want = ck.oracle_etc1(ck.ETC_SMALLER_ERROR, img, h, w)
+        else:
+            want = ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, img, h, w)
+        for threads in (1, 3, 5, 64):
+            got, kind = ck.cpu_encode_full(wl, img, h, w, threads=threads)
+            assert kind == ("reference" if ck.have_ref() else "port")
+            assert np.array_equal(got, want), (wl, threads)
+    img = ck.synthetic(32 * 32 * 4, 2)
+    got, _ = ck.cpu_encode_full("pvrtc2_rgba8", img, 32, 32)
+    assert np.array_equal(got, ck.oracle_pvrtc(img, 32, 32))

@@ -189,6 +189,58 @@ def test_stripes_equal_whole_image(icb):
             assert np.array_equal(np.concatenate(parts), whole), (codec, fmt, world)
 
 
+FULL_SIZE = {  # BASELINE.json configs 1-4 (+ the API-faithful RGB888 DXT1): workload -> (codec, format, ncomp, side, seed)
+    "dxt1_rgba8": (0, ck.RGBA, 4, 8192, 2), "dxt1_rgb8": (0, ck.RGB, 3, 8192, 1), "dxt5_rgba8": (1, ck.RGBA, 4, 8192, 2),
+    "etc1_rgb8": (2, ck.RGB, 3, 4096, 1), "pvrtc2_rgba8": (3, ck.RGBA, 4, 4096, 2),
+}
+
+
+@pytest.mark.parametrize("workload", sorted(FULL_SIZE))
+def test_full_size_byte_compare_with_cpu_reference(icb, workload):
+    """Every benchmarked configuration at its FULL size, all output bytes: device path (the exact call bench.py times)
+    and host path against the reference's own CPU encoder (oracle/_ref, unmodified, multi-threaded over row stripes;
+    the oracle port where _ref was not built).  Input = the bench's synthetic stream S(seed)."""
+    codec, fmt, nc, n, seed = FULL_SIZE[workload]
+    src = torch.empty(n * n * nc, dtype=torch.uint8, device="cuda")
+    icb.fill_synthetic(src, seed)
+    host = src.cpu().numpy()
+    want, kind = ck.cpu_encode_full(workload, host, n, n)
+    if codec == 3:
+        got = icb.pvrtc_encode_device(src, n, n)
+    else:
+        got = icb.encode_device(codec, fmt, src, n, n)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.size == want.size
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "%s: %d bytes differ from the CPU %s, first at byte %d" % (workload, bad.size, kind, bad[0])
+    via_host = icb.compress_host(codec, fmt, host, n, n)
+    assert np.array_equal(via_host, want), "%s: icb_compress_host differs from the CPU %s" % (workload, kind)
+
+
+def test_full_size_structured_content_dxt(icb):
+    """8192^2 structured content (what real textures look like: flat regions, gradients, dark areas, 2-colour cells),
+    DXT1 and DXT5, every byte against the CPU reference -- the general (non-fast-path) index search, the constant-
+    colour table and the 6-alpha mode at scale, which uniform random bytes almost never reach."""
+    n = 8192
+    yy, xx = torch.meshgrid(torch.arange(n, device="cuda", dtype=torch.int32), torch.arange(n, device="cuda", dtype=torch.int32), indexing="ij")
+    noise = torch.empty(n * n * 4, dtype=torch.uint8, device="cuda")
+    icb.fill_synthetic(noise, 77)
+    noise = noise.view(n, n, 4).int()
+    r = torch.where((xx // 512 + yy // 512) % 4 == 0, (xx // 32) % 256, torch.where((xx // 512 + yy // 512) % 4 == 1, noise[..., 0] // 16, (xx // 8 ^ yy // 8) % 2 * 255))
+    g = torch.where((xx // 512 + yy // 512) % 4 == 2, torch.full_like(xx, 150), (yy // 16) % 256)
+    b = torch.where((xx // 1024) % 2 == 0, ((xx + yy) // 64) % 256, noise[..., 2] % 3)
+    a = torch.where((yy // 256) % 3 == 0, torch.full_like(xx, 255), torch.where((yy // 256) % 3 == 1, noise[..., 3] // 128 * 255, (xx // 4) % 256))
+    img = torch.stack([r, g, b, a], -1).to(torch.uint8).contiguous()
+    del noise, r, g, b, a, xx, yy
+    host = img.cpu().numpy()
+    for workload, codec in (("dxt1_rgba8", 0), ("dxt5_rgba8", 1)):
+        want, kind = ck.cpu_encode_full(workload, host, n, n)
+        got = icb.encode_device(codec, ck.RGBA, img.view(-1), n, n).cpu().numpy()
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, "%s structured: %d bytes differ from the CPU %s, first at byte %d" % (workload, bad.size, kind, bad[0])
+
+
 def test_full_size_properties(icb):
     """BASELINE.json full sizes, where the scalar oracle would take minutes: size-independent properties.
     (a) TMA path == generic path byte for byte; (b) block-row translation invariance: encoding rows [k, k+256)
@@ -388,3 +440,48 @@ def test_pvrtc_stripe_rejections(icb):
     for (h, w, r0, r1) in ((64, 64, 0, 16), (64, 64, 3, 3), (64, 64, 5, 17), (48, 48, 0, 2), (64, 32, 0, 2)):
         with pytest.raises(icb.IcbError):
             icb.pvrtc_encode_stripe_device(rows, first, h, w, r0, r1, out)
+
+
+def test_host_pipes_are_pooled_not_leaked_per_thread(icb):
+    """the host path used to keep its streams, events, pinned rings and image-sized device buffers in
+    thread_local storage for ever.  Now they are leased from a pool: 24 short-lived threads (at most 3 at a time)
+    leave at most 3 pipes behind, free device memory stops shrinking after the first wave, and icb_trim() gives the
+    memory back."""
+    import threading
+    L = icb.lib()
+    L.icb_trim()
+    h = w = 1024
+    img = ck.synthetic(h * w * 4, 15)
+    want = ck.oracle_dxt(ck.RGBA, img, h, w)
+    failures = []
+
+    def request():
+        got = icb.compress_host(icb.CODEC_DXT5, icb.RGBA, img, h, w)
+        if not np.array_equal(got, want):
+            failures.append(1)
+
+    free_after_wave = []
+    for wave in range(8):
+        ts = [threading.Thread(target=request) for _ in range(3)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        torch.cuda.synchronize()
+        free_after_wave.append(torch.cuda.mem_get_info()[0])
+    assert not failures
+    assert 1 <= L.icb_idle_pipes() <= 3
+    assert free_after_wave[-1] >= free_after_wave[1] - (8 << 20), free_after_wave   # no growth after warm-up
+    released = L.icb_trim()
+    assert released >= h * w * 4 and L.icb_idle_pipes() == 0
+    assert np.array_equal(icb.compress_host(icb.CODEC_DXT5, icb.RGBA, img, h, w), want)   # and it comes back
+
+
+def test_failed_host_call_leaves_the_pipe_usable(icb):
+    """An error after work has been queued (a destination-size check passes, then a refused block operation) must not
+    poison the pooled pipe for the next caller."""
+    img = ck.synthetic(64 * 64 * 3, 16)
+    blocks = icb.compress_host(icb.CODEC_DXT1, icb.RGB, img, 64, 64)
+    with pytest.raises(icb.IcbError):
+        icb.blockop_host(icb.OP_PAD, icb.CODEC_DXT1, [64, 64, 32, 128], blocks, 8 * 32 * 8)   # shrinks one way, grows the other
+    assert np.array_equal(icb.compress_host(icb.CODEC_DXT1, icb.RGB, img, 64, 64), ck.oracle_dxt(ck.RGB, img, 64, 64))
