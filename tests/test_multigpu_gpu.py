@@ -131,12 +131,12 @@ def test_host_path_spread_over_two_gpus(icb):
             os.environ["ICB_HOST_DEVICES"] = old
 
 
-def _want(icb, codec, nc, img, h, w):
+def _want(icb, codec, fmt, img, h, w):
     if codec == icb.CODEC_ETC1:
         return ck.oracle_etc1(ck.ETC_SMALLER_ERROR, img, h, w)
-    if codec == icb.CODEC_DXT1 and nc == 4:
-        return ck.oracle_dxt1_rgba(img, h, w)
-    return ck.oracle_dxt(ck.RGB if nc == 3 else ck.RGBA, img, h, w)
+    if codec == icb.CODEC_DXT1 and ck.ncomp(fmt) == 4:
+        return ck.oracle_dxt1_rgba(img, h, w, swap_rb=1 if fmt == ck.BGRA else 0)
+    return ck.oracle_dxt(fmt, img, h, w)
 
 
 def _sharded_case(icb, ctx, codec, fmt, nc, h, w, share):
@@ -152,7 +152,7 @@ def _sharded_case(icb, ctx, codec, fmt, nc, h, w, share):
         out = torch.zeros(icb.compressed_size(codec, h, w), dtype=torch.uint8, device="cuda:%d" % ctx.devices[0])
         ctx.encode(codec, fmt, stripes, h, w, splits, out)
         torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy(), _want(icb, codec, nc, img, h, w)), (codec, fmt, h, w, share, splits)
+    assert np.array_equal(out.cpu().numpy(), _want(icb, codec, fmt, img, h, w)), (codec, fmt, h, w, share, splits)
 
 
 def test_shard_context_one_device(icb):
