@@ -144,19 +144,14 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32, kCod
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
   const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
-  // DXT5 keeps its 8 KB crossing-point table behind the ring
-  const uint4 *alpha_table = reinterpret_cast<const uint4 *>(smem_raw + kTmaStages * (Shape::kBytes + 16));
-  if constexpr (kCodec == kCodecDxt5) {
-    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + kTmaStages * (Shape::kBytes + 16));
-    const uint4 *src = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
-    for (uint32_t i = threadIdx.x; i < kDxt5AlphaTableBytes / 16; i += blockDim.x) dst[i] = src[i];
-  }
+  // DXT5's 32 KB crossing table is read from global memory (four 16-byte loads per block, L1-resident)
+  const uint4 *alpha_table = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
 
   uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
   const uint32_t warp = threadIdx.x >> 5;
   // ---- producer: one lane of the last warp streams this CTA's tiles through the ring.  It also sets the barriers
   // up and fills the ring BEFORE the CTA-wide sync, so the first tiles are already in flight while the other warps
-  // are still starting (and, for DXT5, copying the crossing table).
+  // are still starting.
   const bool is_producer = threadIdx.x == Shape::kConsumerThreads;
   uint32_t p_stage = 0, p_phase = 0, p_tile = blockIdx.x;
   const uint64_t policy = is_producer ? l2_evict_first_policy() : 0ull;  // the source is read exactly once
@@ -330,8 +325,8 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
   const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
-  // DXT5's 8 KB crossing table is read from global memory (one 16-byte load per block, L1-resident): a shared-memory
-  // copy would cost the fourth resident CTA per SM.
+  // DXT5's 32 KB crossing table is read from global memory (four 16-byte loads per block, L1-resident): a
+  // shared-memory copy would cost resident CTAs.
   const uint4 *alpha_table = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
   const uint32_t last_bc = p.col1 - Shape::kBlocksX, last_br = p.row1 - Shape::kBlocksY;
 

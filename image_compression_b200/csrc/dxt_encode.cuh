@@ -25,12 +25,16 @@ namespace icb {
 
 // Table of optimal endpoint pairs for a constant channel value; regenerated, not copied
 // (tools/gen_dxt_const_table.py re-runs the published search and checks it against the reference).
-__device__ __align__(8) const uint8_t g_dxt_const_endpoints[256][8] = {
-#include "dxt_const_table.inc"
+// Row v: {5-bit 1/3 e0,e1, 5-bit 1/2 e0,e1, 6-bit 1/3 e0,e1, 6-bit 1/2 e0,e1}.
+struct DxtConstEndpoints {
+  uint8_t v[256][8];
 };
+constexpr DxtConstEndpoints kDxtConstEndpoints = {{
+#include "dxt_const_table.inc"
+}};
 
 // Blinn rounded quantiser: round(v * max / 255)  (internal/color_util.h:156-164).
-__device__ __forceinline__ uint32_t quant_round(uint32_t v, uint32_t maxv) {
+constexpr __host__ __device__ uint32_t quant_round(uint32_t v, uint32_t maxv) {
   const uint32_t i = v * maxv + 128u;
   return (i + (i >> 8)) >> 8;
 }
@@ -39,64 +43,80 @@ __device__ __forceinline__ uint32_t to_565(uint32_t r, uint32_t g, uint32_t b) {
   return (quant_round(r, 31u) << 11) | (quant_round(g, 63u) << 5) | quant_round(b, 31u);
 }
 
-__device__ __forceinline__ uint32_t expand5(uint32_t v) { return (v << 3) | (v >> 2); }
-__device__ __forceinline__ uint32_t expand6(uint32_t v) { return (v << 2) | (v >> 4); }
+constexpr __host__ __device__ uint32_t expand5(uint32_t v) { return (v << 3) | (v >> 2); }
+constexpr __host__ __device__ uint32_t expand6(uint32_t v) { return (v << 2) | (v >> 4); }
 
 // floor(x / 3) for 0 <= x <= 765 (one IMAD + one shift).
 __device__ __forceinline__ uint32_t div3_small(uint32_t x) { return (x * 683u) >> 11; }
 
-// (4|dr| + 8|dg| + |db|)^2 between target t and colour (r,g,b)  (internal/color_util.h:410-417).
-__device__ __forceinline__ uint32_t lum_of_diff_sq(uint32_t tr, uint32_t tg, uint32_t tb, uint32_t r, uint32_t g,
-                                                   uint32_t b) {
-  const uint32_t d = 4u * __usad(tr, r, 0u) + 8u * __usad(tg, g, 0u) + __usad(tb, b, 0u);
-  return d * d;
-}
-
-// Constant-colour block (rare path, divergent by design).  `t` is the target colour as (r,g,b) bytes.
-// Returns c0 | c1 << 16 | index << 32: the two 565 endpoints and the 2-bit index to replicate.  (Packed return
-// value: pointer out-parameters of a non-inlined function would force the caller's registers through local
-// memory on every block, not just on constant ones.)
-__device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
-  const uint32_t tr = t & 255u, tg = (t >> 8) & 255u, tb = (t >> 16) & 255u;
-  const uint32_t qr = quant_round(tr, 31u), qg = quant_round(tg, 63u), qb = quant_round(tb, 31u);
-  uint32_t c0 = (qr << 11) | (qg << 5) | qb, c1 = c0, which = 0;
-  uint32_t best = lum_of_diff_sq(tr, tg, tb, expand5(qr), expand6(qg), expand5(qb));
-  // one 8-byte load per channel row (the table rows are 8-byte aligned), bytes picked out of the two words
-  const uint2 row_r = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tr]);
-  const uint2 row_g = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tg]);
-  const uint2 row_b = *reinterpret_cast<const uint2 *>(g_dxt_const_endpoints[tb]);
-  auto byte_of = [](uint32_t word, int k) { return (word >> (8 * k)) & 255u; };
-  if (!always4) {  // 1/2 blend of a three-colour block (DXT1 only): columns 2,3 (r, b) and 6,7 (g)
-    const uint32_t e0r = byte_of(row_r.x, 2), e1r = byte_of(row_r.x, 3), e0g = byte_of(row_g.y, 2), e1g = byte_of(row_g.y, 3),
-                   e0b = byte_of(row_b.x, 2), e1b = byte_of(row_b.x, 3);
-    const uint32_t err = lum_of_diff_sq(tr, tg, tb, (expand5(e0r) + expand5(e1r)) >> 1,
-                                        (expand6(e0g) + expand6(e1g)) >> 1, (expand5(e0b) + expand5(e1b)) >> 1);
-    if (err < best) {
-      const uint32_t p0 = (e0r << 11) | (e0g << 5) | e0b, p1 = (e1r << 11) | (e1g << 5) | e1b;
-      which = 2;
-      c0 = p0 < p1 ? p0 : p1;
-      c1 = p0 < p1 ? p1 : p0;
-      best = err;
-    }
+// What the constant-colour search (GetBestDxtcConstColors, internal/dxtc_const_color_table.cc:322-392) needs to know
+// about one 8-bit channel value v, derived from the endpoint table at compile time.  The search compares
+// (4|dr| + 8|dg| + |db|)^2 of three candidate colours -- v quantised, the 1/2 blend and the 1/3 blend of the table's
+// endpoint pairs -- and every |d| depends on its own channel only, so it is tabulated: one 16-byte row per value,
+//   bytes 0-3   5-bit endpoints  {1/3 e0, 1/3 e1, 1/2 e0, 1/2 e1}          (v as red or blue)
+//   bytes 4-7   6-bit endpoints  {1/3 e0, 1/3 e1, 1/2 e0, 1/2 e1}          (v as green)
+//   bytes 8-11  5-bit {|v - expand(q)|, |v - 1/2 blend|, |v - 1/3 blend|, q = quantised v}
+//   bytes 12-15 6-bit, the same.
+// No |d| exceeds 4 (checked below), so the three weighted sums of a colour fit side by side in the bytes of one word.
+struct DxtConstRows {
+  uint8_t v[256][16];
+};
+constexpr uint32_t dxt_abs_diff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+constexpr DxtConstRows make_dxt_const_rows() {
+  DxtConstRows t = {};
+  for (uint32_t v = 0; v < 256; ++v) {
+    const uint8_t(&e)[8] = kDxtConstEndpoints.v[v];
+    for (int k = 0; k < 8; ++k) t.v[v][k] = e[k];
+    const uint32_t q5 = quant_round(v, 31u), q6 = quant_round(v, 63u);
+    t.v[v][8] = static_cast<uint8_t>(dxt_abs_diff(v, expand5(q5)));
+    t.v[v][9] = static_cast<uint8_t>(dxt_abs_diff(v, (expand5(e[2]) + expand5(e[3])) >> 1));
+    t.v[v][10] = static_cast<uint8_t>(dxt_abs_diff(v, (2u * expand5(e[0]) + expand5(e[1])) / 3u));
+    t.v[v][11] = static_cast<uint8_t>(q5);
+    t.v[v][12] = static_cast<uint8_t>(dxt_abs_diff(v, expand6(q6)));
+    t.v[v][13] = static_cast<uint8_t>(dxt_abs_diff(v, (expand6(e[6]) + expand6(e[7])) >> 1));
+    t.v[v][14] = static_cast<uint8_t>(dxt_abs_diff(v, (2u * expand6(e[4]) + expand6(e[5])) / 3u));
+    t.v[v][15] = static_cast<uint8_t>(q6);
   }
-  {  // 1/3 blend of a four-colour block: columns 0,1 (r, b) and 4,5 (g)
-    const uint32_t e0r = byte_of(row_r.x, 0), e1r = byte_of(row_r.x, 1), e0g = byte_of(row_g.y, 0), e1g = byte_of(row_g.y, 1),
-                   e0b = byte_of(row_b.x, 0), e1b = byte_of(row_b.x, 1);
-    const uint32_t err = lum_of_diff_sq(tr, tg, tb, div3_small(2u * expand5(e0r) + expand5(e1r)),
-                                        div3_small(2u * expand6(e0g) + expand6(e1g)),
-                                        div3_small(2u * expand5(e0b) + expand5(e1b)));
-    if (err < best) {
-      const uint32_t p0 = (e0r << 11) | (e0g << 5) | e0b, p1 = (e1r << 11) | (e1g << 5) | e1b;
-      if (p0 > p1) {
-        which = 2;
-        c0 = p0;
-        c1 = p1;
-      } else {
-        which = 3;
-        c0 = p1;
-        c1 = p0;
-      }
-    }
+  return t;
+}
+constexpr uint32_t dxt_const_rows_max_diff(const DxtConstRows &t) {
+  uint32_t m = 0;
+  for (int v = 0; v < 256; ++v)
+    for (int k : {8, 9, 10, 12, 13, 14}) m = t.v[v][k] > m ? t.v[v][k] : m;
+  return m;
+}
+constexpr DxtConstRows kDxtConstRows = make_dxt_const_rows();
+static_assert(13u * dxt_const_rows_max_diff(kDxtConstRows) < 256u, "weighted error sums must fit one byte each");
+__device__ __align__(16) const DxtConstRows g_dxt_const_rows = kDxtConstRows;
+
+// Constant-colour block (rare path, divergent by design).  `t` is the target colour as bytes (c0,c1,c2) in the order
+// the reference looks it up (memory order, see the caller).  Returns c0 | c1 << 16 | index << 32: the two 565
+// endpoints and the 2-bit index to replicate.  (Packed return value: pointer out-parameters of a non-inlined function
+// would force the caller's registers through local memory on every block, not just on constant ones.)
+// Squared errors compare like their roots, so the search compares the weighted sums themselves; three 16-byte loads
+// and about forty instructions replace the expansion, blending and squaring of the three candidates.
+__device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
+  const uint4 *rows = reinterpret_cast<const uint4 *>(g_dxt_const_rows.v);
+  const uint4 r = rows[t & 255u], g = rows[(t >> 8) & 255u], b = rows[(t >> 16) & 255u];
+  // byte 0: quantised colour, byte 1: 1/2 blend (three-colour block, DXT1 only), byte 2: 1/3 blend; byte 3 is junk
+  const uint32_t sums = (r.z << 2) + (g.w << 3) + b.z;
+  const uint32_t err_q = sums & 255u, err_half = (sums >> 8) & 255u, err_third = (sums >> 16) & 255u;
+  const bool half = !always4 && err_half < err_q;                  // strict, in the reference's order of trials
+  const bool third = err_third < (half ? err_half : err_q);
+  // endpoint bytes of the chosen blend: (e0, e1) are bytes (0,1) of the row word for thirds, (2,3) for halves
+  const uint32_t shift = third ? 0u : 16u;
+  const uint32_t er = r.x >> shift, eg = g.y >> shift, eb = b.x >> shift;
+  const uint32_t p0 = ((er & 255u) << 11) | ((eg & 255u) << 5) | (eb & 255u);
+  const uint32_t p1 = (((er >> 8) & 255u) << 11) | (((eg >> 8) & 255u) << 5) | ((eb >> 8) & 255u);
+  uint32_t c0 = ((r.z >> 24) << 11) | ((g.w >> 24) << 5) | (b.z >> 24), c1 = c0, which = 0;
+  if (third) {
+    which = p0 > p1 ? 2u : 3u;
+    c0 = p0 > p1 ? p0 : p1;
+    c1 = p0 > p1 ? p1 : p0;
+  } else if (half) {
+    which = 2;
+    c0 = p0 < p1 ? p0 : p1;
+    c1 = p0 < p1 ? p1 : p0;
   }
   return c0 | (c1 << 16) | (static_cast<uint64_t>(which) << 32);
 }
@@ -192,7 +212,16 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // warp's other blocks down the slower general path -- flat image regions would pay for it.)
   const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
   const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
-  const bool all_regular = __all_sync(kFullWarp ? 0xffffffffu : __activemask(), constant || rising || falling);
+  const uint32_t vote_mask = kFullWarp ? 0xffffffffu : __activemask();
+  const bool all_regular = __all_sync(vote_mask, constant || rising || falling);
+  // Second chance for the line search, again decided once per warp: blocks whose interpolants are only WEAKLY between
+  // the base colours (equal luminances: narrow-range blocks in flat, dark or slowly varying image regions -- most of a
+  // real texture).  Candidates that tie with a lower index never win ("first strict minimum"), so they drop out of the
+  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0) along the line and the same two band tests classify
+  // it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
+  const bool up = lum0 < lum1;
+  const bool weakly = up ? (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) : (lum0 > lum1 && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1);
+  const bool all_monotone = all_regular || __all_sync(vote_mask, constant || weakly);
   uint32_t bits;
   if (constant) {
     // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
@@ -201,22 +230,44 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     c0 = static_cast<uint32_t>(packed) & 0xffffu;
     c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
     bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
-  } else if (all_regular) {
+  } else if (all_monotone) {
     // Ascending index sequence along the luminance line: rising 0,2,3,1, falling 1,3,2,0; a tie goes to the smaller
-    // index.  Crossing points h1 < h2 < h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
+    // index.  Crossing points h1 <= h2 <= h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
     // index bit is set exactly between the outer crossings and the low bit flips at the middle one:
     //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 16]
     //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(+-v -+ h2 ...)
     // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
     // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
-    const uint32_t a0 = rising ? lum0 : lum1, a1 = rising ? lum2 : lum3, a2 = rising ? lum3 : lum2, a3 = rising ? lum1 : lum0;
-    const uint32_t h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
-    const uint32_t h2 = ((a1 + a2 + (rising ? 32u : 16u)) >> 1) & ~15u;    // 2->3 stays on tie, 3->2 moves
-    const uint32_t h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
+    const uint32_t a0 = up ? lum0 : lum1, a1 = up ? lum2 : lum3, a2 = up ? lum3 : lum2, a3 = up ? lum1 : lum0;
+    uint32_t h1, h2, h3;
+    if (all_regular) {
+      h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
+      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;        // 2->3 stays on tie, 3->2 moves
+      h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
+    } else {
+      // Which of the two inner candidates survive.  Ascending order carries indices (0,2,3,1) when rising and (1,3,2,0)
+      // when falling; a candidate is dead when an equal luminance exists under a smaller index.
+      const bool inner_tie = a1 == a2;
+      const bool dead1 = a1 == a0 || a1 == a3 || (!up && inner_tie);   // index 2 (rising) / 3 (falling)
+      const bool dead2 = a2 == a0 || a2 == a3 || (up && inner_tie);    // index 3 (rising) / 2 (falling)
+      const uint32_t first_above = !dead1 ? a1 : (!dead2 ? a2 : a3);   // first live candidate above a0
+      const uint32_t last_below = !dead2 ? a2 : (!dead1 ? a1 : a0);    // last live candidate below a3
+      h1 = ((a0 + first_above + 32u) >> 1) & ~15u;            // into a larger index: a tie stays
+      h3 = ((last_below + a3 + 16u) >> 1) & ~15u;             // into a smaller index: a tie moves
+      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;
+      if (dead1 && dead2) {                                   // only the base colours are left: one crossing, 0->1 / 1->0
+        h1 = up ? h1 : h3;
+        h3 = h1;
+      }
+      // The low bit is set for indices 3 and 1: it flips at the inner crossing; without the second inner candidate
+      // (index 3 rising, 2 falling) it flips with the band's far edge, without the first one with its near edge.
+      if (dead1 || dead2) h2 = dead2 ? h3 : h1;
+    }
     const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 16u) >> 1));
-    const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1 - 16u) >> 1) + 1u) - 8388608.0f;  // R + 1
-    const float sgn = rising ? 1.0f : -1.0f;
-    const float k2 = __uint_as_float(rising ? 0xcb000000u + h2 - 1u : kDxtLumBias + h2);
+    // R + 1 = (h3 - h1 - 16) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -7: never set
+    const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388615.0f;
+    const float sgn = up ? 1.0f : -1.0f;
+    const float k2 = __uint_as_float(up ? 0xcb000000u + h2 - 1u : kDxtLumBias + h2);
     float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -302,56 +353,30 @@ __device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[
 // DXT5 alpha block
 // ---------------------------------------------------------------------------------------------------------
 
-// Crossing-point table, 512 entries x 16 bytes; layout and derivation in tools/gen_dxt5_alpha_table.py, which also
+// Crossing-point table, 512 entries x 16 words; layout and derivation in tools/gen_dxt5_alpha_table.py, which also
 // verifies the table-driven search against the reference's direct search for every (a0, a1, alpha).
-__device__ __align__(16) const uint8_t g_dxt5_alpha_table[512 * 16] = {
+__device__ __align__(16) const uint32_t g_dxt5_alpha_table[512 * 16] = {
 #include "dxt5_alpha_table.inc"
 };
-constexpr int kDxt5AlphaTableBytes = 512 * 16;
-
-// Packed fp16 helpers on raw 32-bit registers (two lanes per instruction; HFMA2 / HADD2 in SASS).
-// ICB_HOST_EMULATION is defined only by tests/hostemu (the encoders compiled for the CPU to be checked against the
-// oracle without a GPU); the library itself is never built that way.
-#ifdef ICB_HOST_EMULATION
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return icb_emu::fma_f16x2(a, b, c, false); }
-__device__ __forceinline__ uint32_t h2_fma_sat(uint32_t a, uint32_t b, uint32_t c) { return icb_emu::fma_f16x2(a, b, c, true); }
-__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { return icb_emu::add_f16x2(a, b, false); }
-__device__ __forceinline__ uint32_t h2_add_sat(uint32_t a, uint32_t b) { return icb_emu::add_f16x2(a, b, true); }
-#else
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_fma_sat(uint32_t a, uint32_t b, uint32_t c) {  // clamps each lane to [0, 1]
-  uint32_t d;
-  asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_add_sat(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.sat.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-#endif
+constexpr int kDxt5AlphaTableBytes = 512 * 64;
 
 // Encodes the DXT5 alpha half from the top byte of each pixel (ComputeBaseAlphas, dxtc_compressor.cc:374-424;
 // ComputeAlphaBits :427-479; bit layout Dxt5AlphaBits :103-158).  Returns the 8 output bytes as two words.
-// `table` points at the crossing-point table (shared memory in the TMA kernel, global memory otherwise).
+// `table` points at the crossing-point table (global memory, L1-resident).
 //
-// Alphas and every threshold are integers <= 256, exact in fp16, so the block is processed two pixels per
-// instruction: pixel pair (i, i+8) lives in one register as half2(1280 + a_i, 1280 + a_{i+8}) -- the bit pattern
-// 0x6500 | a, so building it costs a byte permute and a mask, no conversion.
-//   statistics  [a >= 1] and [a == 255] are saturating adds; "min over alphas that are not 0" and "max over
-//               alphas that are not 255" become min/max over x - 255*[..] on the raw bit patterns (VIMNMX.U16x2);
-//               the counts accumulate as 1024 + n so they can be read back from the mantissa.
-//   indices     nearest-candidate search as seven crossings: t = sat(+-x + K_p) is 1 once the pixel has crossed,
-//               acc += t * step_p accumulates the candidate index modulo 8 in the mantissa of 1024 + index.
+// Everything runs two pixels per instruction on 16-bit integer lanes (VIADD.16x2, VIMNMX3.U16x2,
+// VIADDMNMX.S16x2.RELU in SASS): pixel pair (i, i+8) lives in one register as (a_{i+8} << 16) | a_i.
+//   statistics  a - 1 (mod 2^16) sends 0 to 0xffff: the unsigned minimum of those keys is the smallest alpha that is
+//               not 0, and the keys' high bytes add up to 255 * (number of zeros) in one IDP.4A per register;
+//               a + 0xff01 (mod 2^16) sends 255 to 0: the maximum is the largest alpha that is not 255 and the high
+//               bytes add up to 255 * (number of alphas that are not 255).
+//   indices     nearest-candidate search as seven crossings walked in ascending order (see the table generator):
+//               t = relu(min(a - a0 + c_s, 1)) is 1 once the pixel has passed crossing s (one VIADDMNMX, integer
+//               pipe), acc += t * step_s (one IMAD, FMA pipe).  Steps are the true signed index differences, so every
+//               partial sum is an index 0..7: no masking, and the two pixel pairs of an accumulator keep their 3-bit
+//               fields apart without borrows.
+// Round 1 ran this on packed fp16 (HFMA2.SAT + HFMA2 per crossing, both on the half-rate FMA pipe, 322 instructions
+// per block); this form needs about 240 and splits them between the two pipes.
 __device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], bool one_pixel, const uint4 *table) {
   if (one_pixel) {  // window entirely outside the image: both endpoints = that alpha, all indices 0
     const uint32_t a = px[0] >> 24;
@@ -359,34 +384,39 @@ __device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], boo
   }
   uint32_t x[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = (__byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu) | 0x65006500u;
+  for (int i = 0; i < 8; ++i) x[i] = __byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu;
 
   // ---- statistics
-  uint32_t fmin = 0xffffffffu, gmax = 0u, nz = 0x64006400u, n255 = 0x64006400u;
+  uint32_t fk[8], gk[8], zeros255 = 0, not255 = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint32_t z = h2_add_sat(x[i], 0xe500e500u);        // [a >= 1]      (x - 1280, clamped to [0,1])
-    const uint32_t y = h2_add_sat(x[i], 0xe5fee5feu);        // [a == 255]    (x - 1534)
-    fmin = __vminu2(fmin, h2_fma(z, 0xdbf8dbf8u, x[i]));     // 1025 + (a == 0 ? 255 : a)
-    gmax = __vmaxu2(gmax, h2_fma(y, 0xdbf8dbf8u, x[i]));     // 1280 + (a == 255 ? 0 : a)
-    nz = h2_add(nz, z);
-    n255 = h2_add(n255, y);
+    fk[i] = __vadd2(x[i], 0xffffffffu);              // a - 1; a == 0 -> 0xffff
+    gk[i] = __vadd2(x[i], 0xff01ff01u);              // a + 0xff01; a == 255 -> 0
+    zeros255 = __dp4a(fk[i], 0x01000100u, zeros255);  // += high bytes: 255 per zero alpha
+    not255 = __dp4a(gk[i], 0x01000100u, not255);      // += 255 per alpha that is not 255
   }
-  int lo = static_cast<int>(min(fmin & 0xffffu, fmin >> 16) & 0x3ffu) - 1;
-  int hi = static_cast<int>(max(gmax & 0xffffu, gmax >> 16) & 0x3ffu) - 256;
-  const uint32_t num_nonzero = (nz & 0x3ffu) + ((nz >> 16) & 0x3ffu);
-  const uint32_t num_opaque = (n255 & 0x3ffu) + ((n255 >> 16) & 0x3ffu);
+  uint32_t fmin = __vimin3_u16x2(fk[0], fk[1], fk[2]);
+  fmin = __vimin3_u16x2(fmin, fk[3], fk[4]);
+  fmin = __vimin3_u16x2(fmin, fk[5], fk[6]);
+  fmin = __vminu2(fmin, fk[7]);
+  uint32_t gmax = __vimax3_u16x2(gk[0], gk[1], gk[2]);
+  gmax = __vimax3_u16x2(gmax, gk[3], gk[4]);
+  gmax = __vimax3_u16x2(gmax, gk[5], gk[6]);
+  gmax = __vmaxu2(gmax, gk[7]);
+  // smallest alpha that is neither 0 nor 255 (255 when there is none), largest such alpha (0 when there is none)
+  int lo = static_cast<int>(min(min(fmin & 0xffffu, fmin >> 16), 254u)) + 1;
+  int hi = max(static_cast<int>(max(gmax & 0xffffu, gmax >> 16)) - 0xff01, 0);
   if (lo > hi) {  // every alpha is 0 or 255
     lo = 0;
     hi = 255;
   }
   uint32_t a0, a1;
-  if (num_nonzero < 15u || num_opaque > 1u) {  // more than one fully transparent or fully opaque pixel
+  if (zeros255 > 255u || not255 < 14u * 255u + 1u) {  // more than one fully transparent or fully opaque pixel
     a0 = lo;
     a1 = hi;
   } else {
-    if (num_nonzero < 16u) lo = 0;
-    if (num_opaque > 0u) hi = 255;
+    if (zeros255 != 0u) lo = 0;
+    if (not255 != 16u * 255u) hi = 255;
     a0 = hi;
     a1 = lo;
   }
@@ -394,49 +424,42 @@ __device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], boo
   // ---- crossings for this (mode, |a0 - a1|)
   const bool six = a0 <= a1;  // 6-alpha mode: candidates 0 and 255 are explicit
   const uint32_t dist = __usad(a0, a1, 0u);
-  const uint4 e = table[(six ? 0u : 256u) + dist];
-  const uint32_t base = (six ? 0xe4ffu : 0x6402u) + a0;
-  uint32_t K[7], S[7];
-  K[0] = __dp4a(e.x, 0x00000001u, base); K[1] = __dp4a(e.x, 0x00000100u, base);
-  K[2] = __dp4a(e.x, 0x00010000u, base); K[3] = __dp4a(e.x, 0x01000000u, base);
-  K[4] = __dp4a(e.y, 0x00000001u, base); K[5] = __dp4a(e.y, 0x00000100u, base);
-  K[6] = __dp4a(e.y, 0x00010000u, base);
-  S[0] = __byte_perm(e.z, 0u, 0x0404); S[1] = __byte_perm(e.z, 0u, 0x1414);
-  S[2] = __byte_perm(e.z, 0u, 0x2424); S[3] = __byte_perm(e.z, 0u, 0x3434);
-  S[4] = __byte_perm(e.w, 0u, 0x0404); S[5] = __byte_perm(e.w, 0u, 0x1414);
-  S[6] = __byte_perm(e.w, 0u, 0x2424);
-  uint32_t start = 0x6400u;
+  const uint4 *e = table + 4u * ((six ? 0u : 256u) + dist);
+  const uint4 e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+  uint32_t c[7] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z};
+  uint32_t step[7] = {e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z};
+  uint32_t start = e1.w;
   if (six) {
-    // crossings against the explicit candidates: 0 (index 6, or 0 when a0 is itself 0) below the line and
-    // 255 (index 7, or the line's last index when a1 is itself 255) above it
-    const uint32_t a0_zero = a0 == 0u ? 1u : 0u, last = e.y >> 24;
-    K[0] = 0xe4ffu + ((a0 + a0_zero + 1u) >> 1);
-    S[0] = a0_zero ? 0u : 0x4000u;                               // 6 -> 0 is +2 (mod 8)
-    K[6] = 0xe4ffu + ((a1 + 257u) >> 1);
-    S[6] = a1 == 255u ? 0u : 0x4700u - (last << 8);              // last -> 7
-    start += a0_zero ? 0u : 6u;
+    // crossings against the explicit candidates: 0 (index 6, or the line's own index 0 when a0 is itself 0) below the
+    // line and 255 (index 7, or the line's last index when a1 is itself 255) above it
+    const uint32_t a0_zero = a0 == 0u ? 1u : 0u, last = e3.w;
+    start = a0_zero ? 0u : 6u;
+    c[0] = ((1u + a0 - ((a0 + a0_zero + 1u) >> 1)) & 0xffffu) * 0x10001u;
+    step[0] = 0u - start;
+    c[6] = ((1u + a0 - ((a1 + 257u) >> 1)) & 0xffffu) * 0x10001u;
+    step[6] = a1 == 255u ? 0u : 7u - last;
   }
-  const uint32_t sign = six ? 0x3c003c00u : 0xbc00bc00u;         // +1 / -1 in both lanes
+  const uint32_t minus_a0 = ((0u - a0) & 0xffffu) * 0x10001u;
   start *= 0x10001u;
-#pragma unroll
-  for (int p = 0; p < 7; ++p) K[p] *= 0x10001u;
-  S[0] *= six ? 0x10001u : 1u;  // table steps are already in both lanes; the on-the-fly ones are not
-  S[6] *= six ? 0x10001u : 1u;
 
-  // ---- indices: words 0..3 and 4..7 accumulate 3-bit codes at bit 3*(w & 3) of each lane
-  uint32_t acc_a = 0, acc_b = 0;
+  // ---- indices: one accumulator per two pixel pairs; word w's 3-bit indices sit at bit 3*(w & 1) of each lane
+  uint32_t acc[4];
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    uint32_t acc = start;
+  for (int k = 0; k < 4; ++k) {
+    uint32_t a = start;
 #pragma unroll
-    for (int p = 0; p < 7; ++p) acc = h2_fma(h2_fma_sat(x[w], sign, K[p]), S[p], acc);
-    const uint32_t code = acc & 0x00070007u;
-    if (w < 4)
-      acc_a += code << (3 * w);
-    else
-      acc_b += code << (3 * (w - 4));
+    for (int half = 1; half >= 0; --half) {
+      const uint32_t d = __vadd2(x[2 * k + half], minus_a0);  // alpha - a0, two's complement per lane
+#pragma unroll
+      for (int s = 0; s < 7; ++s) a += __viaddmin_s16x2_relu(d, c[s], 0x00010001u) * step[s];
+      if (half == 1) a = a * 8u + start;
+    }
+    acc[k] = a;
   }
-  // lanes: low = pixels 0..7, high = pixels 8..15; pixel n's code goes to bit 16 + 3n of the 64-bit block half
+  // lanes of acc[k]: low = pixels 2k, 2k+1 (6 bits), high = pixels 2k+8, 2k+9
+  const uint32_t acc_a = acc[1] * 64u + acc[0];  // low lane: pixels 0..3 (12 bits), high lane: pixels 8..11
+  const uint32_t acc_b = acc[3] * 64u + acc[2];  // low lane: pixels 4..7, high lane: pixels 12..15
+  // pixel n's code goes to bit 16 + 3n of the 64-bit block half
   const uint32_t word0 = a0 | (a1 << 8) | ((acc_a & 0xfffu) << 16) | (acc_b << 28);
   const uint32_t word1 = ((acc_b & 0xfffu) >> 4) | ((acc_a >> 16) << 8) | ((acc_b >> 16) << 20);
   return make_uint2(word0, word1);

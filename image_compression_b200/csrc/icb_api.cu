@@ -170,7 +170,7 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   ICB_CUDA(cudaGetDevice(&dev));
   if (chosen[dev].kernel == nullptr) {
     constexpr size_t kStage = Shape::kBytes + 16;  // tile + its barrier / counter words
-    constexpr size_t kTable = kCodec == icb::kCodecDxt5 ? icb::kDxt5AlphaTableBytes : 0;  // producer kernel: table in smem
+    constexpr size_t kTable = 0;  // (round 1 kept DXT5's crossing table behind the ring; it is read through L1 now)
     const char *driver = getenv("ICB_DRIVER"), *force = getenv("ICB_TMA_STAGES");
     const bool ring = driver ? strcmp(driver, "ring") == 0 : kCodec == icb::kCodecDxt5;
     Config cand[3];

@@ -43,12 +43,21 @@ inline EmuDim3 blockIdx, threadIdx, blockDim, gridDim;
 
 // ---- warp votes.  One thread is emulated at a time, so a vote cannot see the other lanes; the harness chooses what
 // the rest of the warp "said": kEmuVoteAgree -- every other lane voted like this one (the vote returns the lane's own
-// predicate), kEmuVoteNo -- some other lane voted no (the vote returns false).  Encoders whose result must not depend
-// on the vote (dxt1_encode_from_keys' warp-uniform fast path) are run under both.
-enum EmuVote { kEmuVoteAgree = 0, kEmuVoteNo = 1 };
+// predicate), kEmuVoteNo -- some other lane voted no (every vote returns false), kEmuVoteFirstNo -- some other lane
+// voted no in the encoder's FIRST vote and agreed in its second.  Encoders whose result must not depend on the votes
+// (dxt1_encode_from_keys: strict line search / weakly monotone line search / general search, picked by two
+// warp-uniform votes, the second cast only when the first fails) are run under all three.  In the third mode every
+// encode casts exactly two votes, so "first" is simply every even-numbered vote since emu_set_vote().
+enum EmuVote { kEmuVoteAgree = 0, kEmuVoteNo = 1, kEmuVoteFirstNo = 2 };
 inline EmuVote g_emu_vote = kEmuVoteAgree;
+inline int g_emu_votes_cast = 0;
 static inline uint32_t __activemask() { return 0xffffffffu; }
-static inline bool __all_sync(uint32_t, bool pred) { return g_emu_vote == kEmuVoteAgree ? pred : false; }
+static inline bool __all_sync(uint32_t, bool pred) {
+  const int nth = g_emu_votes_cast++;
+  if (g_emu_vote == kEmuVoteAgree) return pred;
+  if (g_emu_vote == kEmuVoteNo) return false;
+  return (nth & 1) ? pred : false;
+}
 
 // ---- scalar helpers
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -109,6 +118,8 @@ static inline uint32_t emu_lanes16(uint32_t a, uint32_t b, uint32_t (*f)(uint32_
 }
 static inline uint32_t emu_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t emu_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t emu_add(uint32_t a, uint32_t b) { return a + b; }
+static inline uint32_t __vadd2(uint32_t a, uint32_t b) { return emu_lanes16(a, b, emu_add); }  // each lane wraps to 16 bits
 static inline uint32_t __vminu2(uint32_t a, uint32_t b) { return emu_lanes16(a, b, emu_umin); }
 static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) { return emu_lanes16(a, b, emu_umax); }
 static inline uint32_t __vimin3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }

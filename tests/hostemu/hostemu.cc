@@ -46,8 +46,12 @@ constexpr int kOk = 0, kInvalid = -1, kUnsupported = -4;  // include/icb200.h st
 
 extern "C" {
 
-// What the other lanes of the (emulated) warp answer to a vote: 0 = like this lane, 1 = "no" (cuda_emulation.h).
-void emu_set_vote(int vote) { g_emu_vote = vote ? kEmuVoteNo : kEmuVoteAgree; }
+// What the other lanes of the (emulated) warp answer to a vote: 0 = like this lane, 1 = "no", 2 = "no" to the
+// thread's first vote only (cuda_emulation.h).
+void emu_set_vote(int vote) {
+  g_emu_vote = vote == 2 ? kEmuVoteFirstNo : (vote ? kEmuVoteNo : kEmuVoteAgree);
+  g_emu_votes_cast = 0;
+}
 
 // Spot checks of the emulated instructions against values worked out by hand from the PTX ISA definitions.
 // Returns 0, or the number of the first check that failed.

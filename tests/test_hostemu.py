@@ -20,7 +20,7 @@ import imagegen
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
 CSRC = os.path.join(ck.ROOT, "image_compression_b200", "csrc")
 _u8p = C.POINTER(C.c_uint8)
-VOTES = (0, 1)  # what the other lanes of the warp answer to a warp vote: like this lane / "no" (cuda_emulation.h)
+VOTES = (0, 1, 2)  # what the other lanes of the warp answer to a warp vote: like this lane / "no" / "no" to the first vote only (cuda_emulation.h)
 
 
 def _ptr(a):

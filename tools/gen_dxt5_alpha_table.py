@@ -1,22 +1,27 @@
 #!/usr/bin/env python3
-"""Generates image_compression_b200/csrc/dxt5_alpha_table.inc: the crossing-point table the DXT5 alpha encoder keeps in
-shared memory, and checks the whole table-driven classification against the reference's direct search
-(ComputeAlphaBits, internal/dxtc_compressor.cc:427-479) for EVERY endpoint pair and EVERY pixel alpha.
+"""Generates image_compression_b200/csrc/dxt5_alpha_table.inc: the crossing-point table of the DXT5 alpha encoder, and
+checks the whole table-driven classification against the reference's direct search (ComputeAlphaBits,
+internal/dxtc_compressor.cc:427-479) for EVERY endpoint pair and EVERY pixel alpha.
 
 Why a table.  The reference scores a pixel alpha against 8 candidate alphas and keeps the first strict minimum.
 The candidates lie on a line, so that is a nearest-neighbour search whose answer changes only at crossing points
 between neighbouring candidates (ties go to the smaller candidate index; candidates with equal value collapse onto
 their smallest index).  Relative to the endpoint a0 the crossing points and the index change at each crossing
-depend only on the mode (6- or 8-alpha) and on D = |a0 - a1|, so they are tabulated: 512 entries x 16 bytes.
+depend only on the mode (6- or 8-alpha) and on D = |a0 - a1|, so they are tabulated: 512 entries x 64 bytes.
 
-Entry layout (index = D for the 6-alpha mode a0 <= a1, 256 + D for the 8-alpha mode a0 > a1):
-  bytes 0..6   slot value for crossings 1..7
-                 8-alpha: 255 - hrel_p   (pixel crosses p iff a <= a0 - hrel_p)
-                 6-alpha: bytes 1..5 = hrel_k, k = 1..5 (pixel crosses iff a >= a0 + hrel_k); bytes 0 and 6 are
-                          the crossings against the explicit 0 and 255 candidates and are computed on the fly
-  byte  7      6-alpha: index the walk is on when it reaches a1 (0 if D == 0 else 1); 8-alpha: 0
-  bytes 8..14  index change (mod 8) at crossings 1..7, stored as the HIGH BYTE of the fp16 value (0, 1.0, 2.0 ...)
-  byte  15     0
+The device code walks the candidates in ASCENDING alpha order in both modes: with d = alpha - a0 (16-bit lanes, two
+pixels per instruction), crossing s is passed iff d + c_s >= 1, and the running index changes by step_s -- the true
+signed difference of the two candidate indices, so every partial sum is itself a valid index 0..7 and several pixels'
+3-bit fields can share one accumulator without borrows.
+
+Entry layout, sixteen 32-bit words (index = D for the 6-alpha mode a0 <= a1, 256 + D for the 8-alpha mode a0 > a1):
+  words 0..6   c_s in both 16-bit lanes (two's complement): 1 - (threshold_s - a0)
+                 6-alpha: slots 1..5 are the line's crossings; slots 0 and 6 are the crossings against the explicit 0
+                          and 255 candidates, which depend on a0 / a1 themselves and are patched in by the encoder
+                 8-alpha: the seven crossings of the line from the a1 end (index 1) up to a0 (index 0)
+  word  7      index the walk starts on (8-alpha; the 6-alpha start depends on a0 and is patched in)
+  words 8..14  step_s (signed)
+  word  15     6-alpha: index the walk is on when it reaches a1 (0 if D == 0 else 1)
 """
 import os
 import sys
@@ -71,50 +76,65 @@ def line_entry(mode8, D):
     return hrel, step, reps
 
 
+def lanes(v):
+    return ((v & 0xFFFF) << 16) | (v & 0xFFFF)
+
+
 def build():
     table = []
-    for D in range(256):      # 6-alpha mode
+    for D in range(256):      # 6-alpha mode: ascending from a0 (index 0) to a1 (index 1)
         hrel, step, reps = line_entry(False, D)
         e = [0] * 16
         for k in range(5):
-            e[1 + k] = min(hrel[k], 255)
-            e[9 + k] = HALF_HI[step[k]]
-        e[7] = reps[5]
+            e[1 + k] = lanes(1 - hrel[k])
+            e[9 + k] = (reps[k + 1] - reps[k]) & 0xFFFFFFFF
+        e[15] = reps[5]
         table.append(e)
-    for D in range(256):      # 8-alpha mode (D == 0 never occurs: a0 > a1)
+    for D in range(256):      # 8-alpha mode (D == 0 never occurs: a0 > a1): ascending from a1 up to a0
         e = [0] * 16
         if D > 0:
-            hrel, step, reps = line_entry(True, D)
-            for p in range(7):
-                e[p] = 255 - hrel[p]
-                e[8 + p] = HALF_HI[step[p]]
+            hrel, step, reps = line_entry(True, D)   # line positions 0..7 run DOWN from a0; crossing p lies hrel[p-1] below a0
+            for s_ in range(7):
+                q = 7 - s_                            # ascending slot s_ is the line's crossing q (between positions q-1 and q)
+                e[s_] = lanes(hrel[q - 1])            # alpha <= a0 - hrel  <=>  NOT (alpha - a0 + hrel >= 1)
+                e[8 + s_] = (reps[q - 1] - reps[q]) & 0xFFFFFFFF
+            e[7] = reps[7]
         table.append(e)
     return table
 
 
-HALF_VAL = {hb: i for i, hb in enumerate(HALF_HI)}
+def s16(v):
+    v &= 0xFFFF
+    return v - 0x10000 if v & 0x8000 else v
+
+
+def s32(v):
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
 
 
 def classify_with_table(table, a0, a1, a):
-    """Integer model of the device code: seven crossings, index change accumulated mod 8."""
-    if a0 <= a1:
-        e = table[a1 - a0]
-        last = e[7]
+    """Integer model of the device code (one 16-bit lane): seven crossings in ascending order, signed steps, every
+    partial sum a valid index."""
+    six = a0 <= a1
+    e = list(table[(0 if six else 256) + abs(a0 - a1)])
+    start = e[7]
+    if six:
+        last = e[15]
         e0 = 0 if a0 == 0 else 6
         e1 = last if a1 == 255 else 7
-        code = e0
-        thr = [(a0 + (1 if a0 == 0 else 0) + 1) >> 1] + [a0 + e[1 + k] for k in range(5)] + [(a1 + 257) >> 1]
-        step = [(0 - e0) % 8] + [HALF_VAL[e[9 + k]] for k in range(5)] + [(e1 - last) % 8]
-        for p in range(7):
-            if a >= thr[p]:
-                code += step[p]
-    else:
-        e = table[256 + a0 - a1]
-        code = 0
-        for p in range(7):
-            if a <= a0 - (255 - e[p]):
-                code += HALF_VAL[e[8 + p]]
-    return code % 8
+        start = e0
+        thr0 = (a0 + (1 if a0 == 0 else 0) + 1) >> 1
+        thr6 = (a1 + 257) >> 1
+        e[0], e[8] = lanes(1 - (thr0 - a0)), (0 - e0) & 0xFFFFFFFF
+        e[6], e[14] = lanes(1 - (thr6 - a0)), (e1 - last) & 0xFFFFFFFF
+    code = start
+    d = a - a0
+    for s_ in range(7):
+        t = max(min(d + s16(e[s_]), 1), 0)
+        code += t * s32(e[8 + s_])
+        assert 0 <= code <= 7, (a0, a1, a, s_, code)
+    return code
 
 
 def main():
@@ -134,9 +154,9 @@ def main():
         sys.exit("table-driven classification differs from the direct search in %d cases" % bad)
     print("verified: all (a0, a1, alpha) combinations agree with the direct search")
     with open(OUT, "w") as f:
-        f.write("// Generated by tools/gen_dxt5_alpha_table.py -- do not edit.  512 entries x 16 bytes.\n")
+        f.write("// Generated by tools/gen_dxt5_alpha_table.py -- do not edit.  512 entries x 16 words.\n")
         for i, e in enumerate(table):
-            f.write("/*%3d*/ %s,\n" % (i, ", ".join("0x%02x" % b for b in e)))
+            f.write("/*%3d*/ %s,\n" % (i, ", ".join("0x%08xu" % w for w in e)))
     print("wrote", OUT)
 
 
