@@ -220,8 +220,11 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0) along the line and the same two band tests classify
   // it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
   const bool up = lum0 < lum1;
-  const bool weakly = up ? (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) : (lum0 > lum1 && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1);
-  const bool all_monotone = all_regular || __all_sync(vote_mask, constant || weakly);
+  bool all_monotone = all_regular;
+  if (!all_regular) {  // (uniform branch: the usual warp does not pay for the six extra comparisons)
+    const bool weakly = up ? (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) : (lum0 > lum1 && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1);
+    all_monotone = __all_sync(vote_mask, constant || weakly);
+  }
   uint32_t bits;
   if (constant) {
     // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
