@@ -279,6 +279,10 @@ class Env:
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # A host-side meeting point: while rank 0 drives ALL GPUs through the one-call host API (end-to-end leg) the
+            # other ranks must not sit in an NCCL barrier -- its kernel would spin on their GPUs and time-slice with
+            # rank 0's work there.
+            self.cpu_group = dist.new_group(backend="gloo")
         self.stream = torch.cuda.current_stream()
 
     def barrier(self):
@@ -286,6 +290,12 @@ class Env:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        """All GPUs idle, every rank met on the host (gloo): nothing of this job runs on any GPU afterwards."""
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x):
         if self.world == 1:
@@ -620,9 +630,9 @@ def run_gpu_arm(args):
         got = sharding.gather_blocks(local, grid_rows, grid_cols, block_bytes, dst=0, splits=even)
         multi["nccl_gather"] = {"ms_per_step": g_ms / reps, "mpix_s": job_px / (g_ms / reps * 1e-3) / 1e6,
                                 "what": "encode to local HBM + dist.gather of the stripes to rank 0 (reference implementation of the delivery)"}
-        if rank == 0:
-            ps_now = ps.tensor()
-            multi["nccl_gather"]["equals_peer_store_stream"] = bool(torch.equal(got, ps_now))
+        if rank == 0:  # the gathered stream is buffer 0's, like the one the parity flag checked
+            import checkers as ck
+            multi["nccl_gather"]["equals_reference"] = ("%016x" % ck.fnv1a64(got.cpu().numpy())) == (parity or {}).get("fnv1a64")
         # (d) round 1's figure: every rank a full image of its own, kernel only -- weak scaling of independent kernels
         del ej
         wj = StripeJob(env, wl, 0, grid_rows)
@@ -637,6 +647,8 @@ def run_gpu_arm(args):
     # ---- end to end: ONE image through the host-buffer API (pinned buffers; H2D + kernels + D2H per step)
     e2e = None
     in_total = n * n * nc
+    env.barrier()
+    env.cpu_barrier()
     if rank == 0:
         h_in_ptr, h_out_ptr = L.icb_host_alloc(in_total), L.icb_host_alloc(total_out)
         if not h_in_ptr or not h_out_ptr:
@@ -664,6 +676,7 @@ def run_gpu_arm(args):
             ctx.close()
         L.icb_host_free(h_in_ptr)
         L.icb_host_free(h_out_ptr)
+    env.cpu_barrier()
     env.barrier()
 
     if rank == 0:

@@ -1540,11 +1540,13 @@ int icb_root_share_permille(int codec, int format_components, int n) {
   if (n <= 1) return 1000;
   // Root share f that equalises "root encodes f of the image" with "the other 1-f arrives over the root's NVLink
   // ingress": f = t_link / (t_link + t_kernel), both for the whole image.  Measured on B200:
-  // NVLink ingress by peer stores ~720 GB/s; whole-image kernel times per output byte below.
-  double t_kernel_per_out_byte, t_link_per_out_byte = 1.0 / 720e9;
+  // peer stores from ONE sending GPU arrive at ~510 GB/s (its encode kernel is slowed by the remote stores), from
+  // three or more senders the root's ingress saturates at ~720 GB/s; whole-image kernel times per output byte below.
+  double t_kernel_per_out_byte;
+  const double link_gbs = n == 2 ? 510.0 : (n == 3 ? 680.0 : 720.0), t_link_per_out_byte = 1.0 / (link_gbs * 1e9);
   switch (codec) {
     case ICB_CODEC_DXT1: t_kernel_per_out_byte = (format_components == 4 ? 51.5e-6 : 53.0e-6) / 33554432.0; break;
-    case ICB_CODEC_DXT5: t_kernel_per_out_byte = 80e-6 / 67108864.0; break;
+    case ICB_CODEC_DXT5: t_kernel_per_out_byte = 90e-6 / 67108864.0; break;
     case ICB_CODEC_ETC1: t_kernel_per_out_byte = 156e-6 / 8388608.0; break;
     default: return -1;
   }

@@ -23,7 +23,7 @@ try:
         print("     delivery %.0f GB/s into root (%.2f of 900), %s, splits %s" % (dl["achieved"], dl["frac"], dl["partition"], d["config"]["job"][-60:]))
     for k in ("encode_only", "even_split_delivered", "nccl_gather", "weak_scaling_kernel_only"):
         if k in d:
-            print("     %-26s %.1f us  %.0f Mpix/s %s" % (k, d[k]["ms_per_step"] * 1e3, d[k]["mpix_s"], d[k].get("equals_peer_store_stream", "")))
+            print("     %-26s %.1f us  %.0f Mpix/s %s" % (k, d[k]["ms_per_step"] * 1e3, d[k]["mpix_s"], d[k].get("equals_reference", "")))
 except Exception as e:
     print("  parse failed", e); print(open(sys.argv[1].replace(".json", ".err")).read()[-1500:])
 PY
