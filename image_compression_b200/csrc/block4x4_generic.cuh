@@ -66,17 +66,13 @@ __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch
     *reinterpret_cast<uint2 *>(out) = c;
 #endif
   } else if constexpr (kCodec == kCodecDxt5) {
-    // Alpha endpoints first: they decide which row of the crossing table the index search needs, and the row's
-    // trip to L1 then hides behind the colour half (ncu, round 2: a tenth of all warp samples sat on that load).
-    uint32_t endpoints = 0;
-    if (!one_pixel) endpoints = dxt5_alpha_endpoints(px, alpha_table);
+    // Colour first: it releases the staged pixels early.  (Tried in round 2: alpha endpoints first with a
+    // prefetch.global.L1 of the crossing-table row behind the colour half -- CCTL.E.PF1 with 32 different addresses per
+    // warp doubled the kernel time, 90 -> 189 us; the row loads hit L1 99 % of the time anyway.  Also tried: half of the
+    // CTA's warps running the alpha half BEFORE the colour half, to stagger the integer-heavy and FP32-heavy phases
+    // across a scheduler's warps -- 88 -> 104 us, the late release of the staged pixels starves the two-stage ring.)
     const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch, release);
-    uint2 a;
-    if (one_pixel) {  // window entirely outside the image: both endpoints = that alpha, all indices 0
-      a = make_uint2((px[0] >> 24) * 0x101u, 0u);
-    } else {
-      a = dxt5_alpha_indices(px, endpoints, alpha_table);
-    }
+    const uint2 a = dxt5_encode_alpha(px, one_pixel, alpha_table);
     *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
   } else {
     release();  // every pixel is already in registers

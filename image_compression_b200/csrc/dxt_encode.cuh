@@ -363,13 +363,6 @@ __device__ __align__(16) const uint32_t g_dxt5_alpha_table[512 * 16] = {
 };
 constexpr int kDxt5AlphaTableBytes = 512 * 64;
 
-// Starts pulling a 64-byte table row into L1 (no register is held while it travels).
-#ifdef ICB_HOST_EMULATION
-__device__ __forceinline__ void dxt5_prefetch_row(const uint4 *) {}
-#else
-__device__ __forceinline__ void dxt5_prefetch_row(const uint4 *row) { asm volatile("prefetch.global.L1 [%0];" ::"l"(row)); }
-#endif
-
 // Encodes the DXT5 alpha half from the top byte of each pixel (ComputeBaseAlphas, dxtc_compressor.cc:374-424;
 // ComputeAlphaBits :427-479; bit layout Dxt5AlphaBits :103-158).  Returns the 8 output bytes as two words.
 // `table` points at the crossing-point table (global memory, L1-resident).
@@ -387,9 +380,8 @@ __device__ __forceinline__ void dxt5_prefetch_row(const uint4 *row) { asm volati
 //               fields apart without borrows.
 // Round 1 ran this on packed fp16 (HFMA2.SAT + HFMA2 per crossing, both on the half-rate FMA pipe, 322 instructions
 // per block); this form needs about 240 and splits them between the two pipes.
-// Part 1: the two endpoint alphas, packed a0 | a1 << 8 (ComputeBaseAlphas).  Also starts fetching the block's row of the
-// crossing table towards L1, so that a caller with other work to do (the colour half) hides that latency.
-__device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&px)[16], const uint4 *table) {
+// Part 1: the two endpoint alphas, packed a0 | a1 << 8 (ComputeBaseAlphas).
+__device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&px)[16]) {
   uint32_t x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = __byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu;
@@ -428,7 +420,6 @@ __device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&px)[16
     a0 = hi;
     a1 = lo;
   }
-  dxt5_prefetch_row(table + 4u * ((a0 <= a1 ? 0u : 256u) + __usad(a0, a1, 0u)));
   return a0 | (a1 << 8);
 }
 
@@ -488,7 +479,7 @@ __device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], boo
     const uint32_t a = px[0] >> 24;
     return make_uint2(a | (a << 8), 0u);
   }
-  return dxt5_alpha_indices(px, dxt5_alpha_endpoints(px, table), table);
+  return dxt5_alpha_indices(px, dxt5_alpha_endpoints(px), table);
 }
 
 }  // namespace icb
