@@ -388,6 +388,11 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
       // warp off; the last warp to do so refills the slot.  The acq_rel atomic (MEMBAR.CTA + ATOMS) completes this
       // warp's shared-memory reads before the count and makes every warp's reads happen-before the refill.
       auto release = [&]() {
+#ifdef ICB_RING_SKEW_TEST
+        // Test builds only (tools/build_variants.sh skew "-DICB_RING_SKEW_TEST"): some warps hand their slot back
+        // microseconds late, a different set on every tile; the output must not change.
+        if ((((threadIdx.x >> 5) * 5u + tile) & 3u) == 0u) __nanosleep(3000);
+#endif
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
           const uint32_t old = atom_add_acq_rel_shared(count_s + 8 * stage, 1u);
@@ -395,6 +400,9 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
         }
         __syncwarp();
       };
+#ifdef ICB_RING_SKEW_TEST
+      if ((((threadIdx.x >> 5) * 3u + tile) & 7u) == 1u) __nanosleep(5000);  // ... and some arrive late at the next tile
+#endif
       mbar_wait(full_s + 8 * stage, phase);
 
       if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
