@@ -479,6 +479,37 @@ def measure_single(env, workload, steps, warmup, content_kind=None, want_parity=
     return job, rec, iso, launches
 
 
+def unaligned_source_record(env, workload):
+    """The same image at a device address that is NOT 16-byte aligned (base + 4 bytes), which TMA cannot describe: the
+    staged tile driver (automatic choice) against the generic per-block kernel it replaced for such sources."""
+    torch, icb = env.torch, env.icb
+    wl = WORKLOADS[workload]
+    if wl["codec"] == 3:
+        return None
+    n, nc = wl["n"], wl["nc"]
+    nbytes = n * n * nc
+    bufs = [torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    outs = [torch.empty(int(n * n * wl["out_bpp"]), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    srcs = [b[4:4 + nbytes] for b in bufs]
+    for i, s_ in enumerate(srcs):
+        icb.fill_synthetic(s_, wl["seed"] + 16 * i)
+    rec = {"what": "%s, source base = 16-byte boundary + 4" % wl["desc"]}
+    for name, mode in (("staged_driver_ms", -1), ("generic_kernel_ms", 0)):
+        prev = icb.set_tma_mode(mode)
+        try:
+            step = lambda i: icb.encode_device(wl["codec"], wl["fmt"], srcs[i % 2], n, n, out=outs[i % 2], stream=env.stream)
+            env.warm(step, 3, spin_s=0.02)
+            _, ms = env.timed(step, 10)
+            rec[name] = ms / 10
+            if mode == -1:
+                step(0)
+                torch.cuda.synchronize()
+                rec["parity"] = parity_record(workload, outs[0].cpu().numpy())
+        finally:
+            icb.set_tma_mode(prev)
+    return rec
+
+
 def other_workloads(env, headline, clocks_mhz):
     """Compact records for the BASELINE configurations the headline does not cover, and for structured content on the
     headline workload (the DXT index search is data dependent).  N = 1 only; ~20 steps each."""
@@ -501,6 +532,7 @@ def other_workloads(env, headline, clocks_mhz):
         del job
         env.torch.cuda.empty_cache()
         out[name] = rec
+    out["unaligned_device_source"] = unaligned_source_record(env, headline)
     if headline in ("dxt1_rgba8", "dxt5_rgba8"):
         content = {}
         for kind in ("gradient", "flat", "dark", "checker"):
