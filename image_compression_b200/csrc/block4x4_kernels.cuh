@@ -4,9 +4,7 @@
 // (/root/reference/image_compression/internal/compressor4x4_helper.h:175-216, 479-520): one 4x4 window per
 // block in raster order.
 //
-// Four drivers:
-//   encode4x4_staged_kernel   same tiles and consumers for sources TMA cannot describe (unaligned base or pitch): the
-//                             CTA copies the tile into shared memory itself, realigning rows by funnel shifts.
+// Three drivers:
 //   encode4x4_ring_kernel     same tiles, ring and consumers as encode4x4_tma_kernel but without a producer warp: the
 //                             consumer warps count themselves off a slot and the last one refills it (DXT5's default;
 //                             see the comment above that kernel for the measured trade-off).
@@ -452,105 +450,5 @@ __global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Staged driver for sources TMA cannot describe
-// ---------------------------------------------------------------------------------------------------------
-//
-// TMA needs a 16-byte aligned base and row pitch.  A device-resident image that has neither -- an RGB888 image whose
-// width is not a multiple of 16 pixels, a sub-image pointer into a larger buffer -- used to go to the generic kernel
-// whole: 48-64 clamped byte loads and a division per block, ~3x the instructions of the tile consumers.  This driver
-// keeps the consumers and replaces only the producer: the CTA's threads copy each 64 x 4-block tile into shared memory
-// themselves, reading the ALIGNED 32-bit words that cover a tile row (coalesced) and funnel-shifting neighbouring words
-// by the row's byte misalignment, so that the tile lands in shared memory exactly as TMA would have written it.  Two
-// buffers: the copy of tile i+1 is issued before tile i is encoded.  Like the TMA kernels it only sees blocks whose
-// windows lie inside the image (the launcher hands edges to the generic kernel); every word it loads contains at
-// least one byte of the image.
-template <int kCodec, int kNcomp>
-__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads, kCodec == kCodecEtc1 ? 3 : 4)
-    encode4x4_staged_kernel(const Encode4x4Params p, uint32_t tiles_x, uint32_t num_tiles) {
-  using Shape = TileShape<kNcomp>;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint32_t tiles_s;
-  asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
-  constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
-  constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
-  constexpr uint32_t kThreads = Shape::kConsumerThreads;
-  static_assert(Shape::kRowWords % 32 == 0, "a warp's words of one copy step must lie in one tile row");
-  const uint32_t last_bc = p.col1 - Shape::kBlocksX, last_br = p.row1 - Shape::kBlocksY;
-  const uint4 *alpha_table = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
-
-  auto tile_origin = [&](uint32_t t, uint32_t *bc, uint32_t *br) {
-    const uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
-    *bc = min(p.col0 + tx * Shape::kBlocksX, last_bc);
-    *br = min(p.row0 + ty * Shape::kBlocksY, last_br);
-  };
-  // Copies tile t into buffer `buf`: word j of tile row r = bytes 4j .. 4j+3 of that row, whatever the row's alignment.
-  auto stage_tile = [&](uint32_t t, uint32_t buf) {
-    uint32_t bc, br;
-    tile_origin(t, &bc, &br);
-    const uint8_t *origin = p.src + static_cast<size_t>(br) * 4u * p.pitch + static_cast<size_t>(bc) * 4u * kNcomp;
-#pragma unroll 4
-    for (uint32_t idx = threadIdx.x; idx < Shape::kRowWords * Shape::kRows; idx += kThreads) {
-      const uint32_t r = idx / Shape::kRowWords, j = idx - r * Shape::kRowWords;
-      const uint8_t *row = origin + static_cast<size_t>(r) * p.pitch;
-      const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(row)) & 3u;
-      const uint32_t *words = reinterpret_cast<const uint32_t *>(row - a);
-      const uint32_t lo = words[j];
-      const uint32_t hi = a ? words[j + 1] : 0u;  // (a > 0: word j+1 still holds bytes of this tile row)
-      const uint32_t v = __funnelshift_r(lo, hi, 8u * a);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tiles_s + buf * Shape::kBytes + idx * 4u), "r"(v) : "memory");
-    }
-  };
-
-  const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
-  const uint32_t win0 = tiles_s + (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;
-  const bool swap_rb = p.swap_rb != 0;
-  uint32_t buf = 0;
-  if (blockIdx.x < num_tiles) stage_tile(blockIdx.x, 0);
-  __syncthreads();
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, buf ^= 1u) {
-    if (tile + gridDim.x < num_tiles) stage_tile(tile + gridDim.x, buf ^ 1u);  // its loads overlap the encode below
-    const uint32_t win = win0 + buf * Shape::kBytes;
-    auto fetch = [&](uint32_t i) {
-      if constexpr (kNcomp == 4) {
-        return lds_u32(win + ((i * 0x104u) & 0xc0cu));
-      } else {
-        const uint32_t q = win + (i >> 2) * kRowBytes + (i & 3u) * 3u;
-        return lds_u8(q) | (lds_u8(q + 1) << 8) | (lds_u8(q + 2) << 16);
-      }
-    };
-    uint32_t bc, br;
-    tile_origin(tile, &bc, &br);
-    uint8_t *out = p.dst + (static_cast<size_t>(br + lby) * p.grid_cols + bc + lbx) * kBlockBytes;
-    if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
-      uint32_t rows[4][3];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        rows[y][0] = lds_u32(win + y * kRowBytes);
-        rows[y][1] = lds_u32(win + y * kRowBytes + 4);
-        rows[y][2] = lds_u32(win + y * kRowBytes + 8);
-      }
-      *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch);
-    } else {
-      uint32_t px[16];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        if constexpr (kNcomp == 4) {
-          const uint4 v = lds_v4(win + y * kRowBytes);
-          px[4 * y + 0] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w;
-        } else {
-          const uint32_t w0 = lds_u32(win + y * kRowBytes), w1 = lds_u32(win + y * kRowBytes + 4),
-                         w2 = lds_u32(win + y * kRowBytes + 8);
-          px[4 * y + 0] = w0 & 0x00ffffffu;
-          px[4 * y + 1] = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
-          px[4 * y + 2] = __funnelshift_r(w1, w2, 16) & 0x00ffffffu;
-          px[4 * y + 3] = w2 >> 8;
-        }
-      }
-      encode_and_store<kCodec, true>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
-    }
-    __syncthreads();  // the next tile is staged; nobody still reads this buffer when it is overwritten a round later
-  }
-}
 
 }  // namespace icb

@@ -227,32 +227,6 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
 }
 
 template <int kCodec, int kNcomp>
-int launch_staged(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
-  using Shape = icb::TileShape<kNcomp>;
-  constexpr size_t kSmem = 2 * Shape::kBytes;
-  static thread_local int ctas_per_sm[64] = {};
-  int dev = 0;
-  ICB_CUDA(cudaGetDevice(&dev));
-  auto kernel = icb::encode4x4_staged_kernel<kCodec, kNcomp>;
-  if (ctas_per_sm[dev] == 0) {
-    ICB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
-    ICB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, Shape::kConsumerThreads, kSmem));
-    if (ctas_per_sm[dev] < 1) ctas_per_sm[dev] = 1;
-  }
-  const uint32_t tiles_x = (p.col1 - p.col0 + Shape::kBlocksX - 1) / Shape::kBlocksX;
-  const uint32_t tiles_y = (p.row1 - p.row0 + Shape::kBlocksY - 1) / Shape::kBlocksY;
-  const uint64_t num_tiles64 = static_cast<uint64_t>(tiles_x) * tiles_y;
-  if (num_tiles64 == 0) return ICB_OK;
-  if (num_tiles64 > 0x7fffffffull) return fail(ICB_ERR_INVALID, "image too large");
-  const uint32_t num_tiles = static_cast<uint32_t>(num_tiles64);
-  const uint32_t max_ctas = static_cast<uint32_t>(sm_count * ctas_per_sm[dev]);
-  kernel<<<num_tiles < max_ctas ? num_tiles : max_ctas, Shape::kConsumerThreads, kSmem, stream>>>(p, tiles_x, num_tiles);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  ICB_CUDA(cudaGetLastError());
-  return ICB_OK;
-}
-
-template <int kCodec, int kNcomp>
 int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint32_t r0, uint32_t r1,
                     cudaStream_t stream) {
   DeviceInfo info;
@@ -267,26 +241,22 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
   const bool aligned = (reinterpret_cast<uintptr_t>(p.src) % 16 == 0) && (p.pitch % 16 == 0) &&
                        (kNcomp == 4 || p.width % 4 == 0);
   if (mode == 1 && !aligned) return fail(ICB_ERR_INVALID, "TMA path forced but source base/pitch is not 16-byte aligned");
-  // Tile drivers: TMA when the source can be described to it, else the staged driver (the CTA copies and realigns the
-  // tile itself); mode 0 forbids both (tests: everything through the generic kernel), mode 2 forces the staged one.
-  const bool use_tma = aligned && mode != 0 && mode != 2;
-  const bool use_staged = !use_tma && mode != 0;
+  const bool use_tma = aligned && mode != 0;
 
   // Split of the launch's block rows [r0, r1) x all grid columns:
   //   A  blocks whose 4x4 window lies inside the image, if they span at least one tile each way
-  //      ............................................. tile kernel    rows [r0, a_r1) x cols [0, a_c1)
+  //      ............................................. TMA kernel     rows [r0, a_r1) x cols [0, a_c1)
   //   B  right of A, same rows ....................... generic kernel rows [r0, a_r1) x cols [a_c1, grid_cols)
   //   C  everything below A .......................... generic kernel rows [a_r1, r1) x cols [0, grid_cols)
   // (B and C are the ragged image edge, whose windows clamp, and CompressAndPad's pad region.)
   using Shape = icb::TileShape<kNcomp>;
   uint32_t a_r1 = r0, a_c1 = 0;
-  if (use_tma || use_staged) {
+  if (use_tma) {
     const uint32_t full_rows = p.height / 4, full_cols = p.width / 4;  // blocks that need no clamping
     const uint32_t top = r1 < full_rows ? r1 : full_rows;
-    // RGB888 through TMA: a tile must start on a 16-byte boundary of its row (TMA faults otherwise), i.e. on a multiple
-    // of four blocks; the last, shifted tile starts at a_c1 - kBlocksX, so a_c1 is rounded down accordingly.  The
-    // staged driver has no such restriction.
-    const uint32_t usable_cols = (kNcomp == 3 && use_tma) ? full_cols & ~3u : full_cols;
+    // RGB888: a tile must start on a 16-byte boundary of its row (TMA faults otherwise), i.e. on a multiple of
+    // four blocks; the last, shifted tile starts at a_c1 - kBlocksX, so a_c1 is rounded down accordingly.
+    const uint32_t usable_cols = kNcomp == 3 ? full_cols & ~3u : full_cols;
     if (top >= r0 + Shape::kBlocksY && usable_cols >= Shape::kBlocksX) {
       a_r1 = top;
       a_c1 = usable_cols;
@@ -294,7 +264,7 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
   }
   if (a_r1 > r0) {
     p.row0 = r0; p.row1 = a_r1; p.col0 = 0; p.col1 = a_c1;
-    if (int s = use_tma ? launch_tma<kCodec, kNcomp>(p, info.sm_count, stream) : launch_staged<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
+    if (int s = launch_tma<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
     if (a_c1 < grid_cols) {
       p.col0 = a_c1; p.col1 = grid_cols;
       if (int s = launch_generic<kCodec, kNcomp>(p, info.sm_count, stream)) return s;
@@ -794,7 +764,7 @@ int icb_device_count(void) {
 
 uint64_t icb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int icb_set_tma_mode(int mode) { return g_tma_mode.exchange(mode < 0 ? -1 : (mode > 2 ? 1 : mode)); }
+int icb_set_tma_mode(int mode) { return g_tma_mode.exchange(mode < 0 ? -1 : (mode ? 1 : 0)); }
 
 size_t icb_compressed_size(int codec, uint32_t coded_height, uint32_t coded_width) {
   if (coded_height == 0 || coded_width == 0) return 0;

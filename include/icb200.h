@@ -292,9 +292,7 @@ ICB_API int icb_fill_synthetic(void *d_dst, size_t bytes, uint64_t seed, uint64_
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 ICB_API uint64_t icb_launch_count(void);
 
-/* Tile-driver selection for testing: 1 forces the TMA driver (ICB_ERR_INVALID for sources it cannot describe), 2 forces
- * the staged driver (the one unaligned sources get), 0 forbids both (everything through the generic per-block
- * kernel), -1 restores automatic selection.  Returns the previous setting. */
+/* Force (1) or forbid (0) the TMA fast path for testing; -1 restores automatic selection.  Returns previous. */
 ICB_API int icb_set_tma_mode(int mode);
 
 #ifdef __cplusplus
