@@ -54,6 +54,8 @@ PROTOTYPES = {
     "icb_ipc_close": (C.c_int, [C.c_void_p]),
     "icb_host_alloc": (C.c_void_p, [C.c_size_t]),
     "icb_host_free": (None, [C.c_void_p]),
+    "icb_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "icb_host_unregister": (C.c_int, [C.c_void_p]),
     "icb_fill_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "icb_launch_count": (C.c_uint64, []),
     "icb_set_tma_mode": (C.c_int, [C.c_int]),

@@ -832,18 +832,24 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   cfg.gridDim = dim3((lw * p.morph_rows + 127) / 128);
   cfg.blockDim = dim3(128);
   cudaError_t e = cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p);
-  if (e == cudaSuccess) {
+  const bool fused = icb::pvrtc_use_fused(h, w, whole) && !getenv("ICB_PVRTC_UNFUSED");
+  if (e == cudaSuccess && fused) {  // Modulate + Pack in one kernel, one CTA per 32 x 8-block tile
+    cfg.gridDim = dim3(lw / icb::kFusedBx, (h / 4) / icb::kFusedBy);
+    cfg.blockDim = dim3(icb::kFusedThreads);
+    e = cudaLaunchKernelEx(&cfg, icb::pvrtc_modpack_kernel, p);
+  }
+  if (e == cudaSuccess && !fused) {
     cfg.gridDim = dim3((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads);
     cfg.blockDim = dim3(icb::kModThreads);
     e = cudaLaunchKernelEx(&cfg, icb::pvrtc_modulate_kernel, p);
   }
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !fused) {
     cfg.gridDim = dim3((lw * p.pack_rows + 127) / 128);
     cfg.blockDim = dim3(128);
     e = cudaLaunchKernelEx(&cfg, icb::pvrtc_pack_kernel, p);
   }
   if (e == cudaSuccess) {
-    g_launches.fetch_add(3, std::memory_order_relaxed);
+    g_launches.fetch_add(fused ? 2 : 3, std::memory_order_relaxed);
     e = cudaGetLastError();
   }
   // the library's own scratch goes back to the pool on every path (stream-ordered: after whatever did launch)
@@ -1168,6 +1174,18 @@ void *icb_host_alloc(size_t bytes) {
 
 void icb_host_free(void *p) {
   if (p) cudaFreeHost(p);
+}
+
+int icb_host_register(void *p, size_t bytes) {
+  if (!p || bytes == 0) return fail(ICB_ERR_INVALID, "null pointer or zero size");
+  ICB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return ICB_OK;
+}
+
+int icb_host_unregister(void *p) {
+  if (!p) return ICB_OK;
+  ICB_CUDA(cudaHostUnregister(p));
+  return ICB_OK;
 }
 
 // ---- peer-mapped output (multi-GPU stripe path) -----------------------------------------------------------

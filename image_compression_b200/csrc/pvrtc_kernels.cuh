@@ -2,7 +2,9 @@
 // /root/reference/image_compression/internal/pvrtc_compressor.cc:586-597 = Morph :506-521, Modulate :527-540,
 // Encode :551-580).
 //
-// Three kernels, all coalesced and small enough to stay in the instruction cache:
+// Whole images of 256 x 32 pixels and more run TWO kernels: pvrtc_morph_kernel and pvrtc_modpack_kernel (Modulate and
+// Pack fused through shared memory, end of this file).  Small images and the row-stripe form keep the three-kernel
+// pipeline below, all coalesced and small enough to stay in the instruction cache:
 //   pvrtc_morph_kernel     one thread per 8x4 block -> bit-reduced A and B colours (one (A, B) pair per block: the
 //                          reference's two w/8 x h/4 images, interleaved, in scratch)
 //   pvrtc_modulate_kernel  one thread per 8-pixel segment of kModRows consecutive rows: bilinear upscale of A and B
@@ -143,13 +145,12 @@ __global__ void __launch_bounds__(128, 8) pvrtc_morph_kernel(const PvrtcParams p
 #else
 #define ICB_PVRTC_MOD_BOUNDS __launch_bounds__(kModThreads)
 #endif
-__global__ void ICB_PVRTC_MOD_BOUNDS pvrtc_modulate_kernel(const PvrtcParams p) {
-  pv_launch_dependents();
-  pv_wait_for_previous();  // Morph's A/B colours
+// One Modulate unit: pixels 8*bx .. 8*bx+7 of rows y0 .. y0+kModRows-1 (y0 = 4g+2, so all of them interpolate between
+// low-resolution rows g and g+1).  `wanted(r)` says whether row y0+r is needed at all; `store(r, y, bits)` receives the
+// eight 2-bit modulation values of row y = y0+r (mod height).
+template <typename Wanted, typename Store>
+__device__ __forceinline__ void pv_modulate_unit(const PvrtcParams &p, uint32_t bx, uint32_t y0, Wanted wanted, Store store) {
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= lw * p.mod_units) return;
-  const uint32_t bx = t & (lw - 1u), y0 = (2u + kModRows * (p.mod_unit0 + (t >> p.lw_shift))) & (p.height - 1u);
   // Low-resolution rows/columns these pixel rows interpolate between, wrapped (pvrtc_compressor.cc:216-223).
   const uint32_t top = ((y0 - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
   const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
@@ -161,6 +162,7 @@ __global__ void ICB_PVRTC_MOD_BOUNDS pvrtc_modulate_kernel(const PvrtcParams p) 
   }
 #pragma unroll
   for (uint32_t r = 0; r < kModRows; ++r) {
+    if (!wanted(r)) continue;
     const uint32_t y = (y0 + r) & (p.height - 1u);  // (only the unit that straddles the bottom edge wraps)
     const uint32_t fy = (y + 2u) & 3u;
     PvLanes va[3], vb[3];  // vertical blend, shared by the whole row: (4-fy)*top + fy*bottom, not yet divided
@@ -184,8 +186,37 @@ __global__ void ICB_PVRTC_MOD_BOUNDS pvrtc_modulate_kernel(const PvrtcParams p) 
       const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
       bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
     }
-    p.mod[y * lw + bx] = static_cast<uint16_t>(bits);
+    store(r, y, bits);
   }
+}
+
+// The modulation value of ONE pixel (x, y): what pv_modulate_unit computes for pixel 0 of segment x/8 (x % 8 == 0).
+__device__ __forceinline__ uint32_t pv_modulate_first_pixel_of_segment(const PvrtcParams &p, uint32_t bx, uint32_t y) {
+  const uint32_t lw = p.width >> 3, lh = p.height >> 2;
+  const uint32_t top = ((y - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
+  const uint32_t cl = (bx + lw - 1u) & (lw - 1u);
+  const uint32_t fy = (y + 2u) & 3u;
+  const uint2 tl = p.low[top * lw + cl], tr = p.low[top * lw + bx], bl = p.low[bottom * lw + cl], br = p.low[bottom * lw + bx];
+  auto vblend = [&](uint32_t t, uint32_t b) {
+    const PvLanes lt = pv_split(t), lb = pv_split(b);
+    return PvLanes{lt.rb * (4u - fy) + lb.rb * fy, lt.ga * (4u - fy) + lb.ga * fy};
+  };
+  // pixel 0 of a segment: fx = 4, between columns (bx-1, bx)
+  const uint32_t ca = pv_blend256(vblend(tl.x, bl.x), 32u, vblend(tr.x, br.x), 32u);
+  const uint32_t cb = pv_blend256(vblend(tl.y, bl.y), 32u, vblend(tr.y, br.y), 32u);
+  return pv_pick_modulation(pv_src_row(p, y)[bx * 8], ca, cb);
+}
+
+__global__ void ICB_PVRTC_MOD_BOUNDS pvrtc_modulate_kernel(const PvrtcParams p) {
+  pv_launch_dependents();
+  pv_wait_for_previous();  // Morph's A/B colours
+  const uint32_t lw = p.width >> 3;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lw * p.mod_units) return;
+  const uint32_t bx = t & (lw - 1u), y0 = (2u + kModRows * (p.mod_unit0 + (t >> p.lw_shift))) & (p.height - 1u);
+  pv_modulate_unit(
+      p, bx, y0, [](uint32_t) { return true; },
+      [&](uint32_t, uint32_t y, uint32_t bits) { p.mod[y * lw + bx] = static_cast<uint16_t>(bits); });
 }
 
 __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
@@ -209,5 +240,75 @@ __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
   const uint32_t colours = pv_pack_colours(ab.x, ab.y, one_bpp);
   p.dst[pv_z_index(bx, by)] = make_uint2(mod_bits, colours);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Modulate + Pack in one kernel (whole images of at least 256 x 32 pixels)
+// ---------------------------------------------------------------------------------------------------------
+//
+// A CTA owns a tile of kFusedBx x kFusedBy blocks (256 x 32 pixels).  Pack needs the modulation values of the tile's
+// pixel rows plus the row below and the pixel column to the right (pvrtc_compressor.cc:417-424), so phase 1 computes
+// modulation rows 4*by0 .. 4*by0 + 32 for the tile's 32 segments -- warp w takes Modulate unit g = by0 - 1 + w, the
+// first and the last warp only the rows that fall into the range -- plus the first pixel of the segment to the right
+// for the tile's 32 rows (four lanes of each warp, one row each), all into shared memory; after one __syncthreads
+// phase 2 packs the tile's 256 blocks from there.  The reference's byte-per-pixel modulation image never exists, not
+// even as 2-bit words in L2, and the third kernel with its launch and tail is gone.
+constexpr uint32_t kFusedBx = 32, kFusedBy = 8;
+constexpr uint32_t kFusedWarps = kFusedBy + 1, kFusedThreads = 32 * kFusedWarps;
+struct PvTileMods {
+  uint16_t rows[4 * kFusedBy + 1][kFusedBx];  // eight 2-bit values per word: row (y - 4*by0), segment (bx - bx0)
+  uint8_t right[4 * kFusedBy];                // value of the pixel right of the tile, rows 4*by0 .. 4*by0 + 31
+};
+
+__device__ __forceinline__ void pv_fused_phase1(const PvrtcParams &p, PvTileMods &tile, uint32_t tile_bx0, uint32_t tile_by0,
+                                                uint32_t thread) {
+  const uint32_t lw = p.width >> 3, lh = p.height >> 2;
+  const uint32_t warp = thread >> 5, lane = thread & 31u;
+  const uint32_t g = (tile_by0 + lh - 1u + warp) & (lh - 1u);  // Modulate unit: rows 4g+2 .. 4g+5
+  const uint32_t y0 = (4u * g + 2u) & (p.height - 1u);
+  // tile-relative index of the unit's first row: -2, 2, 6, ...; rows outside [0, 32] are not needed
+  const int rel0 = static_cast<int>(4u * warp) - 2;
+  auto wanted = [&](uint32_t r) { return rel0 + static_cast<int>(r) >= 0 && rel0 + static_cast<int>(r) <= static_cast<int>(4u * kFusedBy); };
+  pv_modulate_unit(p, tile_bx0 + lane, y0, wanted,
+                   [&](uint32_t r, uint32_t, uint32_t bits) { tile.rows[rel0 + static_cast<int>(r)][lane] = static_cast<uint16_t>(bits); });
+  // the column right of the tile (wrapped): lane r of this warp takes row r of the unit
+  const int rel = rel0 + static_cast<int>(lane);
+  if (lane < 4u && rel >= 0 && rel < static_cast<int>(4u * kFusedBy)) {
+    const uint32_t y = (y0 + lane) & (p.height - 1u);
+    tile.right[rel] = static_cast<uint8_t>(pv_modulate_first_pixel_of_segment(p, (tile_bx0 + kFusedBx) & (lw - 1u), y));
+  }
+}
+
+__device__ __forceinline__ void pv_fused_phase2(const PvrtcParams &p, const PvTileMods &tile, uint32_t tile_bx0,
+                                                uint32_t tile_by0, uint32_t thread) {
+  if (thread >= kFusedBx * kFusedBy) return;
+  const uint32_t lw = p.width >> 3;
+  const uint32_t lbx = thread & (kFusedBx - 1u), lby = thread / kFusedBx;
+  uint32_t row[5], right[4];
+#pragma unroll
+  for (int y = 0; y < 5; ++y) {
+    row[y] = tile.rows[4u * lby + y][lbx];
+    if (y < 4) right[y] = lbx + 1u < kFusedBx ? (tile.rows[4u * lby + y][lbx + 1u] & 3u) : tile.right[4u * lby + y];
+  }
+  bool one_bpp;
+  const uint32_t mod_bits = pv_pack_modulation(row, right, &one_bpp);
+  const uint32_t bx = tile_bx0 + lbx, by = tile_by0 + lby;
+  const uint2 ab = p.low[by * lw + bx];
+  p.dst[pv_z_index(bx, by)] = make_uint2(mod_bits, pv_pack_colours(ab.x, ab.y, one_bpp));
+}
+
+#ifndef ICB_HOST_EMULATION  // (tests/hostemu runs the two phases itself, thread by thread, around its own "barrier")
+__global__ void __launch_bounds__(kFusedThreads) pvrtc_modpack_kernel(const PvrtcParams p) {
+  __shared__ PvTileMods tile;
+  pv_launch_dependents();
+  pv_wait_for_previous();  // Morph's A/B colours
+  const uint32_t tile_bx0 = blockIdx.x * kFusedBx, tile_by0 = blockIdx.y * kFusedBy;
+  pv_fused_phase1(p, tile, tile_bx0, tile_by0, threadIdx.x);
+  __syncthreads();
+  pv_fused_phase2(p, tile, tile_bx0, tile_by0, threadIdx.x);
+}
+#endif
+
+// True when the fused kernel covers this launch: whole image, at least one full tile each way.
+inline bool pvrtc_use_fused(uint32_t h, uint32_t w, bool whole) { return whole && (w / 8) >= kFusedBx && (h / 4) >= kFusedBy; }
 
 }  // namespace icb

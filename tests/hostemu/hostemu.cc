@@ -48,6 +48,10 @@ extern "C" {
 
 // What the other lanes of the (emulated) warp answer to a vote: 0 = like this lane, 1 = "no", 2 = "no" to the
 // thread's first vote only (cuda_emulation.h).
+// 1: whole images keep the three-kernel PVRTC pipeline (Modulate and Pack as separate kernels) even where the library
+// would run the fused one, so that both are checked on the same inputs.
+bool g_emu_pvrtc_unfused = false;
+void emu_set_pvrtc_unfused(int on) { g_emu_pvrtc_unfused = on != 0; }
 void emu_set_vote(int vote) {
   g_emu_vote = vote == 2 ? kEmuVoteFirstNo : (vote ? kEmuVoteNo : kEmuVoteAgree);
   g_emu_votes_cast = 0;
@@ -149,6 +153,17 @@ int emu_pvrtc2(const uint8_t *src, uint32_t h, uint32_t w, uint32_t nstripes, ui
   std::vector<uint8_t> scratch(static_cast<size_t>(lw) * lh * 8 + static_cast<size_t>(lw) * h * 2);
   auto run = [&](const icb::PvrtcParams &p) {
     launch((lw * p.morph_rows + 127) / 128, 1, 128, [&] { icb::pvrtc_morph_kernel(p); });
+    if (icb::pvrtc_use_fused(h, w, p.morph_rows == lh && p.src_row0 == 0 && p.pack_rows == lh) && !g_emu_pvrtc_unfused) {
+      // the fused Modulate + Pack kernel, one "CTA" at a time: phase 1 for every thread, the barrier, phase 2
+      for (uint32_t cy = 0; cy < lh / icb::kFusedBy; ++cy)
+        for (uint32_t cx = 0; cx < lw / icb::kFusedBx; ++cx) {
+          icb::PvTileMods tile;
+          std::memset(&tile, 0xEE, sizeof(tile));
+          for (uint32_t t = 0; t < icb::kFusedThreads; ++t) icb::pv_fused_phase1(p, tile, cx * icb::kFusedBx, cy * icb::kFusedBy, t);
+          for (uint32_t t = 0; t < icb::kFusedThreads; ++t) icb::pv_fused_phase2(p, tile, cx * icb::kFusedBx, cy * icb::kFusedBy, t);
+        }
+      return;
+    }
     launch((lw * p.mod_units + icb::kModThreads - 1) / icb::kModThreads, 1, icb::kModThreads, [&] { icb::pvrtc_modulate_kernel(p); });
     launch((lw * p.pack_rows + 127) / 128, 1, 128, [&] { icb::pvrtc_pack_kernel(p); });
   };

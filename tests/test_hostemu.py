@@ -187,6 +187,25 @@ def test_pvrtc_vs_oracle_whole_and_striped(emu):
                     assert np.array_equal(pvrtc(emu, img.ravel(), n, parts), want), (n, kind, parts)
 
 
+def test_pvrtc_fused_modulate_pack_kernel(emu):
+    """Whole images of 256 x 256 and more run Morph + the fused Modulate/Pack kernel (one CTA per 32 x 8-block tile,
+    modulation values through shared memory, the tile's right-hand pixel column and the row below included): its two
+    phases, emulated CTA by CTA, give the oracle's bytes -- and the same bytes as the three-kernel pipeline, which
+    stays in use for small images and stripes -- on every kind of content, tile seams and the toroidal wrap included."""
+    emu.emu_set_pvrtc_unfused.argtypes = [C.c_int]
+    try:
+        for n in (256, 512):
+            for kind in imagegen.KINDS:
+                img = imagegen.make(kind, n, n, 4, seed=n + 7)
+                want = ck.oracle_pvrtc(img.ravel(), n, n)
+                emu.emu_set_pvrtc_unfused(0)
+                assert np.array_equal(pvrtc(emu, img.ravel(), n), want), (n, kind, "fused")
+                emu.emu_set_pvrtc_unfused(1)
+                assert np.array_equal(pvrtc(emu, img.ravel(), n), want), (n, kind, "three kernels")
+    finally:
+        emu.emu_set_pvrtc_unfused(0)
+
+
 def test_decoders_every_kind_of_block(emu):
     """Random bit patterns (blocks no encoder produces included) and encoder output, whole and cropped images."""
     rng = np.random.default_rng(9)

@@ -531,3 +531,56 @@ def test_unaligned_full_size_rgb888_width_not_multiple_of_16(icb):
     got = icb.encode_device(0, ck.RGB, src, h, w).cpu().numpy()
     bad = np.flatnonzero(got != want)
     assert bad.size == 0, "%d bytes differ from the CPU %s, first at %d" % (bad.size, kind, bad[0])
+
+
+def test_registered_caller_buffers_take_the_pinned_path(icb):
+    """icb_host_register: a buffer the caller already owns (numpy memory here) becomes page-locked; the host path then
+    DMAs it directly instead of staging it, with the same bytes out; unregistering puts it back on the staged path."""
+    L = icb.lib()
+    h = w = 2048
+    img = ck.synthetic(h * w * 4, 31)
+    out = np.zeros(icb.compressed_size(icb.CODEC_DXT5, h, w), np.uint8)
+    want = ck.oracle_dxt(ck.RGBA, img, h, w)
+    assert L.icb_host_register(img.ctypes.data, img.size) == 0 and L.icb_host_register(out.ctypes.data, out.size) == 0
+    try:
+        icb.compress_host(icb.CODEC_DXT5, icb.RGBA, img, h, w, out=out)
+        assert np.array_equal(out, want)
+    finally:
+        assert L.icb_host_unregister(img.ctypes.data) == 0 and L.icb_host_unregister(out.ctypes.data) == 0
+    out[:] = 0
+    icb.compress_host(icb.CODEC_DXT5, icb.RGBA, img, h, w, out=out)
+    assert np.array_equal(out, want)
+    assert L.icb_host_register(None, 16) == -1
+
+
+def test_pvrtc_fused_kernel_equals_three_kernel_pipeline_and_oracle(icb):
+    """Whole images >= 256 x 256 run Morph + the fused Modulate/Pack kernel; ICB_PVRTC_UNFUSED=1 keeps the three-kernel
+    pipeline.  Both must give the oracle's bytes (256 .. 1024, every content kind) and each other's at 2048."""
+    import os
+    for n in (256, 512, 1024):
+        for kind in imagegen.KINDS if n < 1024 else ("random", "alpha_extremes"):
+            img = imagegen.make(kind, n, n, 4, seed=n + 3)
+            want = ck.oracle_pvrtc(img.ravel(), n, n)
+            d = dev(img.ravel())
+            before = icb.launch_count()
+            got = icb.pvrtc_encode_device(d, n, n).cpu().numpy()
+            assert icb.launch_count() - before == 2          # Morph + Modulate/Pack
+            assert np.array_equal(got, want), (n, kind, "fused")
+            os.environ["ICB_PVRTC_UNFUSED"] = "1"
+            try:
+                before = icb.launch_count()
+                got3 = icb.pvrtc_encode_device(d, n, n).cpu().numpy()
+                assert icb.launch_count() - before == 3
+            finally:
+                del os.environ["ICB_PVRTC_UNFUSED"]
+            assert np.array_equal(got3, want), (n, kind, "three kernels")
+    n = 2048
+    src = torch.empty(n * n * 4, dtype=torch.uint8, device="cuda")
+    icb.fill_synthetic(src, 12)
+    a = icb.pvrtc_encode_device(src, n, n)
+    os.environ["ICB_PVRTC_UNFUSED"] = "1"
+    try:
+        b = icb.pvrtc_encode_device(src, n, n)
+    finally:
+        del os.environ["ICB_PVRTC_UNFUSED"]
+    assert torch.equal(a, b)
