@@ -832,8 +832,12 @@ int pvrtc_launch(const void *d_src, const void *d_first_pixel, uint32_t h, uint3
   cfg.gridDim = dim3((lw * p.morph_rows + 127) / 128);
   cfg.blockDim = dim3(128);
   cudaError_t e = cudaLaunchKernelEx(&cfg, icb::pvrtc_morph_kernel, p);
-  const bool fused = icb::pvrtc_use_fused(h, w, whole) && !getenv("ICB_PVRTC_UNFUSED");
-  if (e == cudaSuccess && fused) {  // Modulate + Pack in one kernel, one CTA per 32 x 8-block tile
+  // Modulate + Pack fused through shared memory exists and is bit-exact (tests), but measured SLOWER than the two
+  // separate kernels on B200 (4096^2: 50.4 vs 48.5 us; both are instruction-issue bound and the tile's extra row,
+  // extra column and partial warps add 10 % instructions, more than the third launch costs under programmatic
+  // dependent launch), so it is opt-in: ICB_PVRTC_FUSED=1.
+  const bool fused = icb::pvrtc_use_fused(h, w, whole) && getenv("ICB_PVRTC_FUSED") != nullptr;
+  if (e == cudaSuccess && fused) {  // one CTA per 32 x 8-block tile
     cfg.gridDim = dim3(lw / icb::kFusedBx, (h / 4) / icb::kFusedBy);
     cfg.blockDim = dim3(icb::kFusedThreads);
     e = cudaLaunchKernelEx(&cfg, icb::pvrtc_modpack_kernel, p);

@@ -2,9 +2,8 @@
 // /root/reference/image_compression/internal/pvrtc_compressor.cc:586-597 = Morph :506-521, Modulate :527-540,
 // Encode :551-580).
 //
-// Whole images of 256 x 32 pixels and more run TWO kernels: pvrtc_morph_kernel and pvrtc_modpack_kernel (Modulate and
-// Pack fused through shared memory, end of this file).  Small images and the row-stripe form keep the three-kernel
-// pipeline below, all coalesced and small enough to stay in the instruction cache:
+// Three kernels, all coalesced and small enough to stay in the instruction cache (a two-kernel form with Modulate and
+// Pack fused through shared memory is at the end of this file: bit-exact, but slower on B200, so opt-in):
 //   pvrtc_morph_kernel     one thread per 8x4 block -> bit-reduced A and B colours (one (A, B) pair per block: the
 //                          reference's two w/8 x h/4 images, interleaved, in scratch)
 //   pvrtc_modulate_kernel  one thread per 8-pixel segment of kModRows consecutive rows: bilinear upscale of A and B
@@ -251,7 +250,10 @@ __global__ void __launch_bounds__(128) pvrtc_pack_kernel(const PvrtcParams p) {
 // first and the last warp only the rows that fall into the range -- plus the first pixel of the segment to the right
 // for the tile's 32 rows (four lanes of each warp, one row each), all into shared memory; after one __syncthreads
 // phase 2 packs the tile's 256 blocks from there.  The reference's byte-per-pixel modulation image never exists, not
-// even as 2-bit words in L2, and the third kernel with its launch and tail is gone.
+// even as 2-bit words in L2, and the third kernel with its launch and tail is gone -- at the price of ~10 % more
+// instructions (the extra row and column, two partly idle warps per CTA) in a pipeline that is instruction-issue
+// bound: measured 50.4 us against 48.5 us for the three kernels at 4096^2, so the launcher uses it only on request
+// (ICB_PVRTC_FUSED=1).
 constexpr uint32_t kFusedBx = 32, kFusedBy = 8;
 constexpr uint32_t kFusedWarps = kFusedBy + 1, kFusedThreads = 32 * kFusedWarps;
 struct PvTileMods {

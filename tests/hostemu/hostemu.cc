@@ -48,8 +48,8 @@ extern "C" {
 
 // What the other lanes of the (emulated) warp answer to a vote: 0 = like this lane, 1 = "no", 2 = "no" to the
 // thread's first vote only (cuda_emulation.h).
-// 1: whole images keep the three-kernel PVRTC pipeline (Modulate and Pack as separate kernels) even where the library
-// would run the fused one, so that both are checked on the same inputs.
+// 1: whole images keep the three-kernel PVRTC pipeline (Modulate and Pack as separate kernels, the library's default)
+// where the fused Modulate/Pack kernel could run, so that both are checked on the same inputs.
 bool g_emu_pvrtc_unfused = false;
 void emu_set_pvrtc_unfused(int on) { g_emu_pvrtc_unfused = on != 0; }
 void emu_set_vote(int vote) {
