@@ -184,6 +184,9 @@ ICB_API size_t icb_idle_pipes(void);
  *                       single-GPU encoders.  The caller's current device is unchanged on return.
  * icb_ctx_compress_host icb_compress_host over exactly the context's devices (each uploads, encodes and downloads its
  *                       own chunks over its own PCIe link; nothing is gathered).
+ * Threading: icb_encode_sharded orders its devices through events owned by the context, so calls on ONE context must
+ * not overlap (use one context per calling thread; contexts are cheap); icb_ctx_compress_host leases its streams from
+ * the process-wide pool and may be called concurrently.
  */
 typedef struct icb_ctx icb_ctx;
 ICB_API int icb_ctx_create(int n_dev, const int *dev_ids, icb_ctx **ctx);
