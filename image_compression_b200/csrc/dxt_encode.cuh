@@ -238,7 +238,7 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     // index.  Crossing points h1 <= h2 <= h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
     // index bit is set exactly between the outer crossings and the low bit flips at the middle one:
     //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 16]
-    //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(+-v -+ h2 ...)
+    //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(v - h2 + 1), flipped at the end when falling
     // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
     // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
     const uint32_t a0 = up ? lum0 : lum1, a1 = up ? lum2 : lum3, a2 = up ? lum3 : lum2, a3 = up ? lum1 : lum0;
@@ -269,14 +269,16 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 16u) >> 1));
     // R + 1 = (h3 - h1 - 16) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -7: never set
     const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388615.0f;
-    const float sgn = up ? 1.0f : -1.0f;
-    const float k2 = __uint_as_float(up ? 0xcb000000u + h2 - 1u : kDxtLumBias + h2);
+    // The low bit is computed as [v >= h2] for both directions -- one two-operand FADD.SAT per pixel, where a per-block
+    // sign would need the three-register FFMA form, which issues at half the rate of the two-operand and immediate
+    // forms -- and flipped for all sixteen pixels at the end when the sequence falls (bit0 = [v < h2] there).
+    const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 16*l >= h2
     float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float v = __uint_as_float(kf[i]);
       const float u = __saturatef(rp1 - fabsf(v - mid));
-      const float t = __saturatef(fmaf(v, sgn, k2));
+      const float t = __saturatef(v + k2);
       const float z = fmaf(u, 2.0f, t);
       const float scale = static_cast<float>(1u << (2 * (i & 7)));
       if (i < 8)
@@ -284,7 +286,7 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
       else
         acc_hi = fmaf(z, scale, acc_hi);
     }
-    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410);
+    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410) ^ (up ? 0u : 0x55555555u);
   } else {
     float acc0, cross[3], step[3];
     {
