@@ -184,17 +184,19 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
   uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
   release();
-  uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1
+  const uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;      // 16 * luminance of p0 / p1: lum0 <= lum1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
-  uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
+  const uint32_t q0 = dxt_to_565(p0, w_red, w_blue), q1 = dxt_to_565(p1, w_red, w_blue);
   // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
   // where the warp has not yet diverged on "is this block constant".
-  const bool constant = c0 == c1;
-  if (c0 < c1) {
-    uint32_t t = p0; p0 = p1; p1 = t;
-    t = c0; c0 = c1; c1 = t;
-    t = lum0; lum0 = lum1; lum1 = t;
-  }
+  const bool constant = q0 == q1;
+  // The reference swaps the two base colours (565 and 8-bit alike) when c0 < c1, so that c0 > c1 (four-colour mode).
+  // Nothing is swapped here: with p0 the darker base colour always, the candidates in luminance order are
+  // (p0, (2 p0 + p1)/3, (p0 + 2 p1)/3, p1) either way -- the interpolants of the swapped pair are the same two colours
+  // in the other order -- and the swap only renames the indices, 0 <-> 1 and 2 <-> 3: the low bit of every index
+  // flips (one XOR at the end) and ties go to the OTHER candidate of the middle pair (one selected constant).
+  const bool swapped = q0 < q1;
+  uint32_t c0 = max(q0, q1), c1 = min(q0, q1);
   // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
   // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
   const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
@@ -202,27 +204,26 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
   constexpr uint32_t kThird = 683u << 21;
   const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
-                        16u * __umulhi(2u * b0 + b1, kThird);
+                        16u * __umulhi(2u * b0 + b1, kThird);   // the interpolant next to p0
   const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
-                        16u * __umulhi(b0 + 2u * b1, kThird);
+                        16u * __umulhi(b0 + 2u * b1, kThird);   // the interpolant next to p1
   // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
-  // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
-  // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
-  // midpoints have to be computed.  (Constant blocks vote yes: they take neither path, and a no would send the
-  // warp's other blocks down the slower general path -- flat image regions would pay for it.)
-  const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
-  const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
+  // base colours, i.e. the candidates are ordered along the luminance line with no two equal.  Then the crossing
+  // order, the tie rules and the index changes are fixed and only the three midpoints have to be computed.
+  // (Constant blocks vote yes: they take neither path, and a no would send the warp's other blocks down the slower
+  // general path -- flat image regions would pay for it.)
+  const bool strictly = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
   const uint32_t vote_mask = kFullWarp ? 0xffffffffu : __activemask();
-  const bool all_regular = __all_sync(vote_mask, constant || rising || falling);
+  const bool all_regular = __all_sync(vote_mask, constant || strictly);
   // Second chance for the line search, again decided once per warp: blocks whose interpolants are only WEAKLY between
   // the base colours (equal luminances: narrow-range blocks in flat, dark or slowly varying image regions -- most of a
   // real texture).  Candidates that tie with a lower index never win ("first strict minimum"), so they drop out of the
-  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0) along the line and the same two band tests classify
-  // it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
-  const bool up = lum0 < lum1;
+  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0 when swapped) along the line and the same two band tests
+  // classify it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
+  const bool up = !swapped;  // reference indices along the ascending line: (0,2,3,1) unswapped, (1,3,2,0) swapped
   bool all_monotone = all_regular;
-  if (!all_regular) {  // (uniform branch: the usual warp does not pay for the six extra comparisons)
-    const bool weakly = up ? (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) : (lum0 > lum1 && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1);
+  if (!all_regular) {  // (uniform branch: the usual warp does not pay for the extra comparisons)
+    const bool weakly = lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1;  // (lum0 < lum1 whenever the block is not constant)
     all_monotone = __all_sync(vote_mask, constant || weakly);
   }
   uint32_t bits;
@@ -241,7 +242,7 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(v - h2 + 1), flipped at the end when falling
     // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
     // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
-    const uint32_t a0 = up ? lum0 : lum1, a1 = up ? lum2 : lum3, a2 = up ? lum3 : lum2, a3 = up ? lum1 : lum0;
+    const uint32_t a0 = lum0, a1 = lum2, a2 = lum3, a3 = lum1;  // ascending
     uint32_t h1, h2, h3;
     if (all_regular) {
       h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
@@ -271,7 +272,7 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388615.0f;
     // The low bit is computed as [v >= h2] for both directions -- one two-operand FADD.SAT per pixel, where a per-block
     // sign would need the three-register FFMA form, which issues at half the rate of the two-operand and immediate
-    // forms -- and flipped for all sixteen pixels at the end when the sequence falls (bit0 = [v < h2] there).
+    // forms -- and flipped for all sixteen pixels at the end when the base colours were swapped (indices 2k <-> 2k+1).
     const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 16*l >= h2
     float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
 #pragma unroll
@@ -286,12 +287,13 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
       else
         acc_hi = fmaf(z, scale, acc_hi);
     }
-    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410) ^ (up ? 0u : 0x55555555u);
+    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410) ^ (swapped ? 0x55555555u : 0u);
   } else {
     float acc0, cross[3], step[3];
     {
-      // General case (flat blocks, crossed or equal candidates): sort the candidates as keys 16*L_c + c.
-      uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
+      // General case (crossed candidates): sort the candidates as keys 16*L_c + c, c = the reference's index.
+      uint32_t s0 = swapped ? lum1 : lum0, s1 = (swapped ? lum0 : lum1) + 1u, s2 = (swapped ? lum3 : lum2) + 2u,
+               s3 = (swapped ? lum2 : lum3) + 3u;
       sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
       const uint32_t sorted[4] = {s0, s1, s2, s3};
       uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
