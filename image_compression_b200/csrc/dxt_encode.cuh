@@ -164,7 +164,13 @@ struct NoRelease {
   __device__ __forceinline__ void operator()() const {}
 };
 
-template <bool kFullWarp, typename Fetch, typename Release = NoRelease>
+// kSwapBases: how the reference's "swap the base colours when c0 < c1" is realised.  false: nothing is swapped, the
+// indices are renamed at the end (fewer instructions: -35 per block; DXT5 87.0 vs 88.4 us, DXT1 from RGB888 51.6 vs
+// 55.0 us).  true: the two base colours, their 565 words and luminances are physically exchanged first, as in round 1
+// -- kept for DXT1 from RGBA8 only, whose TMA kernel runs 1.4 % FASTER with the longer code (51.1-51.8 vs 52.0-52.4 us
+// in three same-box A/B pairs: that kernel is bound by the hand-over between tiles, not by instruction issue, and
+// earlier slot release or shorter consumers both slow it down).  Both forms are checked against the oracle.
+template <bool kFullWarp, bool kSwapBases = false, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch,
                                                        Release release = Release()) {
   // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
@@ -184,19 +190,23 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
   uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
   release();
-  const uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;      // 16 * luminance of p0 / p1: lum0 <= lum1
+  uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1: lum0 <= lum1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   const uint32_t q0 = dxt_to_565(p0, w_red, w_blue), q1 = dxt_to_565(p1, w_red, w_blue);
   // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
   // where the warp has not yet diverged on "is this block constant".
   const bool constant = q0 == q1;
   // The reference swaps the two base colours (565 and 8-bit alike) when c0 < c1, so that c0 > c1 (four-colour mode).
-  // Nothing is swapped here: with p0 the darker base colour always, the candidates in luminance order are
-  // (p0, (2 p0 + p1)/3, (p0 + 2 p1)/3, p1) either way -- the interpolants of the swapped pair are the same two colours
-  // in the other order -- and the swap only renames the indices, 0 <-> 1 and 2 <-> 3: the low bit of every index
-  // flips (one XOR at the end) and ties go to the OTHER candidate of the middle pair (one selected constant).
+  // With kSwapBases == false nothing is swapped: with p0 the darker base colour always, the candidates in luminance
+  // order are (p0, (2 p0 + p1)/3, (p0 + 2 p1)/3, p1) either way -- the interpolants of the swapped pair are the same
+  // two colours in the other order -- and the swap only renames the indices, 0 <-> 1 and 2 <-> 3: the low bit of every
+  // index flips (one XOR at the end) and ties go to the OTHER candidate of the middle pair (one selected constant).
   const bool swapped = q0 < q1;
   uint32_t c0 = max(q0, q1), c1 = min(q0, q1);
+  if (kSwapBases && swapped) {
+    uint32_t t = p0; p0 = p1; p1 = t;
+    t = lum0; lum0 = lum1; lum1 = t;
+  }
   // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
   // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
   const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
@@ -212,7 +222,8 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // order, the tie rules and the index changes are fixed and only the three midpoints have to be computed.
   // (Constant blocks vote yes: they take neither path, and a no would send the warp's other blocks down the slower
   // general path -- flat image regions would pay for it.)
-  const bool strictly = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
+  // (kSwapBases: after a swap lum0 > lum1 and "between" runs the other way)
+  const bool strictly = (lum0 < lum2 && lum2 < lum3 && lum3 < lum1) || (kSwapBases && lum0 > lum2 && lum2 > lum3 && lum3 > lum1);
   const uint32_t vote_mask = kFullWarp ? 0xffffffffu : __activemask();
   const bool all_regular = __all_sync(vote_mask, constant || strictly);
   // Second chance for the line search, again decided once per warp: blocks whose interpolants are only WEAKLY between
@@ -223,7 +234,8 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   const bool up = !swapped;  // reference indices along the ascending line: (0,2,3,1) unswapped, (1,3,2,0) swapped
   bool all_monotone = all_regular;
   if (!all_regular) {  // (uniform branch: the usual warp does not pay for the extra comparisons)
-    const bool weakly = lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1;  // (lum0 < lum1 whenever the block is not constant)
+    // (the two base luminances differ whenever the block is not constant)
+    const bool weakly = (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) || (kSwapBases && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1 && lum0 > lum1);
     all_monotone = __all_sync(vote_mask, constant || weakly);
   }
   uint32_t bits;
@@ -242,7 +254,9 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(v - h2 + 1), flipped at the end when falling
     // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
     // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
-    const uint32_t a0 = lum0, a1 = lum2, a2 = lum3, a3 = lum1;  // ascending
+    // ascending luminances (kSwapBases: after a swap the four run the other way)
+    const bool flip = kSwapBases && swapped;
+    const uint32_t a0 = flip ? lum1 : lum0, a1 = flip ? lum3 : lum2, a2 = flip ? lum2 : lum3, a3 = flip ? lum0 : lum1;
     uint32_t h1, h2, h3;
     if (all_regular) {
       h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
@@ -292,8 +306,9 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     float acc0, cross[3], step[3];
     {
       // General case (crossed candidates): sort the candidates as keys 16*L_c + c, c = the reference's index.
-      uint32_t s0 = swapped ? lum1 : lum0, s1 = (swapped ? lum0 : lum1) + 1u, s2 = (swapped ? lum3 : lum2) + 2u,
-               s3 = (swapped ? lum2 : lum3) + 3u;
+      const bool rename = swapped && !kSwapBases;  // (kSwapBases: lum0..lum3 already belong to the reference's indices)
+      uint32_t s0 = rename ? lum1 : lum0, s1 = (rename ? lum0 : lum1) + 1u, s2 = (rename ? lum3 : lum2) + 2u,
+               s3 = (rename ? lum2 : lum3) + 3u;
       sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
       const uint32_t sorted[4] = {s0, s1, s2, s3};
       uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
@@ -324,14 +339,14 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
 }
 
 // Keys from 16 packed pixels (bytes c0,c1,c2,x in memory order; x ignored).
-template <bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
+template <bool kFullWarp = false, bool kSwapBases = false, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch,
                                                    Release release = Release()) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
   uint32_t kf[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
-  return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
+  return dxt1_encode_from_keys<kFullWarp, kSwapBases>(kf, swap_rb, always4, fetch, release);
 }
 
 // Keys straight from four rows of packed RGB888 (three 32-bit words = four pixels per row): the byte weights of
