@@ -92,17 +92,30 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   return policy;
 }
 
-// Tile geometry.  A tile is kTileBlocksX x kTileBlocksY blocks; the TMA box is (kTileBlocksX*4*kNcomp/4) 32-bit
-// words wide (the image row is described to TMA as 32-bit words so that RGB888 rows fit the 256-element box
-// limit) and kTileBlocksY*4 rows tall.
-template <int kNcomp>
+// Tile geometry.  A tile is kBlocksX x kBlocksY blocks; the TMA box is (kBlocksX*4*kNcomp/4) 32-bit words wide (the
+// image row is described to TMA as 32-bit words so that RGB888 rows fit the 256-element box limit) and kBlocksY*4
+// rows tall.  One consumer thread per block of the tile.
+// Tile height per codec, measured on B200 (profiles/r02_tile_shapes.txt, 8192^2, us per launch):
+//   DXT1   64 x 8 blocks (32 KB tiles, 16 consumer warps, 2 CTAs per SM): 50.2 (RGBA8) / 49.6 (RGB888) against 51.6 / 51.7
+//          with 64 x 4 and 52.2 / 56.6 with 64 x 2 -- fewer, larger hand-overs suit the kernel that is bound by them;
+//   DXT5   64 x 4 (110.9 us with 64 x 8, 91.8 with 64 x 2 against 87.2);  ETC1  64 x 4 (register budget).
+// ICB_DXT1_TILE_BLOCKS_Y overrides DXT1's for A/B builds (tools/build_variants.sh).
+#ifndef ICB_DXT1_TILE_BLOCKS_Y
+#define ICB_DXT1_TILE_BLOCKS_Y 8
+#endif
+template <int kCodec>
+constexpr int tile_blocks_y() { return kCodec == kCodecDxt1 ? ICB_DXT1_TILE_BLOCKS_Y : 4; }
+
+template <int kCodec, int kNcomp>
 struct TileShape {
   static constexpr int kBlocksX = 64;                       // 256 pixels
-  static constexpr int kBlocksY = 4;                        // 16 pixel rows
+  static constexpr int kBlocksY = tile_blocks_y<kCodec>();  // 16 or 32 pixel rows
   static constexpr int kRowWords = kBlocksX * kNcomp;       // 32-bit words per tile row (256 or 192)
   static constexpr int kRows = kBlocksY * 4;
-  static constexpr int kBytes = kRowWords * 4 * kRows;      // 16384 or 12288
+  static constexpr int kBytes = kRowWords * 4 * kRows;      // 16384 / 12288 (x2 for DXT1)
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
+  // resident CTAs per SM the kernels are compiled for (register budget = 65536 / threads / CTAs)
+  static constexpr int kProducerMinCtas = kCodec == kCodecDxt1 ? (kBlocksY >= 8 ? 2 : 4) : 3;
 };
 
 // Shared-memory loads by 32-bit shared-window address (no generic pointers: the tile base stays one register and the
@@ -129,10 +142,10 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // and the last tile of a row / column is shifted back so that it ends exactly at col1 / row1 -- the blocks it
 // shares with its neighbour are simply encoded twice, to the same bytes.
 template <int kCodec, int kNcomp, int kTmaStages>
-__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads + 32, kCodec == kCodecDxt1 ? 4 : 3)
+__global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 32, TileShape<kCodec, kNcomp>::kProducerMinCtas)
     encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                          uint32_t num_tiles) {
-  using Shape = TileShape<kNcomp>;
+  using Shape = TileShape<kCodec, kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // layout: kTmaStages tiles, then kTmaStages "full" barriers, then kTmaStages "empty" barriers
   // (kTmaStages trades bytes in flight per CTA against resident CTAs per SM; the launcher picks)
@@ -310,11 +323,11 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t addr, uint3
 #endif
 
 template <int kCodec, int kNcomp, int kTmaStages>
-__global__ void __launch_bounds__(TileShape<kNcomp>::kConsumerThreads,
-                                  kCodec == kCodecEtc1 ? 3 : (kCodec == kCodecDxt5 ? ICB_DXT5_RING_MIN_CTAS : 4))
+__global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
+                                  kCodec == kCodecEtc1 ? 3 : (kCodec == kCodecDxt5 ? ICB_DXT5_RING_MIN_CTAS : TileShape<kCodec, kNcomp>::kProducerMinCtas))
     encode4x4_ring_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                           uint32_t num_tiles) {
-  using Shape = TileShape<kNcomp>;
+  using Shape = TileShape<kCodec, kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), then per stage a done-counter (8 bytes)
   uint32_t tiles_s;

@@ -140,7 +140,7 @@ int launch_generic(const Encode4x4Params &p, int sm_count, cudaStream_t stream) 
 
 template <int kCodec, int kNcomp>
 int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
-  using Shape = icb::TileShape<kNcomp>;
+  using Shape = icb::TileShape<kCodec, kNcomp>;
   if (static_cast<uint64_t>(p.grid_cols) * icb::CodecTraits<kCodec>::kBlockBytes > 0xffffffffull)
     return fail(ICB_ERR_INVALID, "image too wide");
   EncodeTiledFn encode = encode_tiled_fn();
@@ -249,7 +249,7 @@ int encode4x4_typed(Encode4x4Params p, uint32_t coded_h, uint32_t coded_w, uint3
   //   B  right of A, same rows ....................... generic kernel rows [r0, a_r1) x cols [a_c1, grid_cols)
   //   C  everything below A .......................... generic kernel rows [a_r1, r1) x cols [0, grid_cols)
   // (B and C are the ragged image edge, whose windows clamp, and CompressAndPad's pad region.)
-  using Shape = icb::TileShape<kNcomp>;
+  using Shape = icb::TileShape<kCodec, kNcomp>;
   uint32_t a_r1 = r0, a_c1 = 0;
   if (use_tma) {
     const uint32_t full_rows = p.height / 4, full_cols = p.width / 4;  // blocks that need no clamping
@@ -1290,8 +1290,9 @@ static int compress_host_impl(const int *ctx_devs, int ctx_ndev, int codec, int 
   if (chunks < 1) chunks = 1;
   if (chunks > HostPipe::kMaxChunks) chunks = HostPipe::kMaxChunks;
   if (chunks > grid_rows) chunks = grid_rows;
-  // whole tile rows per chunk (4 block rows), so that only the last chunk can leave rows to the generic kernel
-  const uint32_t rows_per_chunk = ((grid_rows + chunks - 1) / chunks + 3) / 4 * 4;
+  // whole tile rows per chunk (8 block rows: the tallest tile), so that only the last chunk can leave rows to the
+  // generic kernel
+  const uint32_t rows_per_chunk = ((grid_rows + chunks - 1) / chunks + 7) / 8 * 8;
   const uint32_t num_chunks = (grid_rows + rows_per_chunk - 1) / rows_per_chunk;
 
   // Devices: chunk c goes to device c % ndev (ICB_HOST_DEVICES, default one), each over its own PCIe link; every
