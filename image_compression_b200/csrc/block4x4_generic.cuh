@@ -62,10 +62,7 @@ __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch
     release();
     *reinterpret_cast<uint2 *>(out) = make_uint2(a, b);
 #else
-#ifndef ICB_DXT1_RGBA_SWAP
-#define ICB_DXT1_RGBA_SWAP 1  // (build macro for A/B runs; see dxt1_encode_from_keys_swapping)
-#endif
-    const uint2 c = dxt1_encode_block<kFullWarp, /*kSwapBases=*/ICB_DXT1_RGBA_SWAP != 0>(px, swap_rb != 0, false, fetch, release);
+    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, false, fetch, release);
     *reinterpret_cast<uint2 *>(out) = c;
 #endif
   } else if constexpr (kCodec == kCodecDxt5) {

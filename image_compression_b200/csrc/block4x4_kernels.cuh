@@ -115,7 +115,7 @@ struct TileShape {
   static constexpr int kBytes = kRowWords * 4 * kRows;      // 16384 / 12288 (x2 for DXT1)
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
   // resident CTAs per SM the kernels are compiled for (register budget = 65536 / threads / CTAs)
-  static constexpr int kProducerMinCtas = kCodec == kCodecDxt1 ? (kBlocksY >= 8 ? 2 : 4) : 3;
+  static constexpr int kProducerMinCtas = kCodec == kCodecDxt1 ? (kBlocksY >= 16 ? 1 : (kBlocksY >= 8 ? 2 : 4)) : 3;
 };
 
 // Shared-memory loads by 32-bit shared-window address (no generic pointers: the tile base stays one register and the

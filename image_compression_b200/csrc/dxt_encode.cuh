@@ -323,180 +323,14 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   return make_uint2(c0 | (c1 << 16), bits);
 }
 
-// Round 1's form of the same function, kept VERBATIM for one caller: it physically exchanges the two base colours,
-// their 565 words and luminances when c0 < c1 (as the reference does) instead of renaming indices at the end, which
-// costs ~35 instructions per block more -- and DXT1 from RGBA8, whose TMA kernel is bound by the hand-over between
-// tiles rather than by instruction issue, runs 1.4-2 % FASTER with it (51.1-51.8 us against 52.0-52.4 us for the shorter
-// code in five same-box A/B pairs on B200, profiles/r02_dxt1_rgba8_colour_variants.txt; releasing ring slots earlier
-// slows that kernel down as well).  The kernel's timing follows ptxas's schedule of this exact source, so it is not
-// merged with the function above.  Everything else (DXT5, DXT1 from RGB888) uses the shorter form: 87.0 vs 88.4 us and
-// 51.5 vs 55.0 us.  Both are checked against the oracle on the CPU (tests/hostemu) and on the GPU.
-template <bool kFullWarp, typename Fetch, typename Release = NoRelease>
-__device__ __forceinline__ uint2 dxt1_encode_from_keys_swapping(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch,
-                                                       Release release = Release()) {
-  // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
-  // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
-  // folds two more registers (four pixels) per instruction.
-  uint32_t pk[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) pk[k] = __byte_perm(kf[2 * k], kf[2 * k + 1], 0x5410) + ((2u * k) | ((2u * k + 1u) << 16));
-  uint32_t mn = __vimin3_u16x2(pk[0], pk[1], pk[2]);
-  mn = __vimin3_u16x2(mn, pk[3], pk[4]);
-  mn = __vimin3_u16x2(mn, pk[5], pk[6]);
-  mn = __vminu2(mn, pk[7]);
-  uint32_t mx = __vimax3_u16x2(pk[0] ^ 0x000f000fu, pk[1] ^ 0x000f000fu, pk[2] ^ 0x000f000fu);
-  mx = __vimax3_u16x2(mx, pk[3] ^ 0x000f000fu, pk[4] ^ 0x000f000fu);
-  mx = __vimax3_u16x2(mx, pk[5] ^ 0x000f000fu, pk[6] ^ 0x000f000fu);
-  mx = __vmaxu2(mx, pk[7] ^ 0x000f000fu);
-  const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
-  uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
-  release();
-  uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;            // 16 * luminance of p0 / p1
-  const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
-  uint32_t c0 = dxt_to_565(p0, w_red, w_blue), c1 = dxt_to_565(p1, w_red, w_blue);
-  // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
-  // where the warp has not yet diverged on "is this block constant".
-  const bool constant = c0 == c1;
-  if (c0 < c1) {
-    uint32_t t = p0; p0 = p1; p1 = t;
-    t = c0; c0 = c1; c1 = t;
-    t = lum0; lum0 = lum1; lum1 = t;
-  }
-  // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
-  // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
-  const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
-  const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
-  const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
-  constexpr uint32_t kThird = 683u << 21;
-  const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
-                        16u * __umulhi(2u * b0 + b1, kThird);
-  const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
-                        16u * __umulhi(b0 + 2u * b1, kThird);
-  // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
-  // base colours, i.e. the candidates are already ordered 0,2,3,1 (or 1,3,2,0) along the luminance line with no
-  // two equal.  Then the crossing order, the tie rules and the index changes are fixed and only the three
-  // midpoints have to be computed.  (Constant blocks vote yes: they take neither path, and a no would send the
-  // warp's other blocks down the slower general path -- flat image regions would pay for it.)
-  const bool rising = lum0 < lum2 && lum2 < lum3 && lum3 < lum1;
-  const bool falling = lum0 > lum2 && lum2 > lum3 && lum3 > lum1;
-  const uint32_t vote_mask = kFullWarp ? 0xffffffffu : __activemask();
-  const bool all_regular = __all_sync(vote_mask, constant || rising || falling);
-  // Second chance for the line search, again decided once per warp: blocks whose interpolants are only WEAKLY between
-  // the base colours (equal luminances: narrow-range blocks in flat, dark or slowly varying image regions -- most of a
-  // real texture).  Candidates that tie with a lower index never win ("first strict minimum"), so they drop out of the
-  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0) along the line and the same two band tests classify
-  // it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
-  const bool up = lum0 < lum1;
-  bool all_monotone = all_regular;
-  if (!all_regular) {  // (uniform branch: the usual warp does not pay for the six extra comparisons)
-    const bool weakly = up ? (lum0 <= lum2 && lum2 <= lum3 && lum3 <= lum1) : (lum0 > lum1 && lum0 >= lum2 && lum2 >= lum3 && lum3 >= lum1);
-    all_monotone = __all_sync(vote_mask, constant || weakly);
-  }
-  uint32_t bits;
-  if (constant) {
-    // The reference swaps red and blue a second time here (dxtc_compressor.cc:360), i.e. it looks up the
-    // memory-order colour.
-    const uint64_t packed = dxt_const_colour(p0, always4);
-    c0 = static_cast<uint32_t>(packed) & 0xffffu;
-    c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
-    bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
-  } else if (all_monotone) {
-    // Ascending index sequence along the luminance line: rising 0,2,3,1, falling 1,3,2,0; a tie goes to the smaller
-    // index.  Crossing points h1 <= h2 <= h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
-    // index bit is set exactly between the outer crossings and the low bit flips at the middle one:
-    //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 16]
-    //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(v - h2 + 1), flipped at the end when falling
-    // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
-    // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
-    const uint32_t a0 = up ? lum0 : lum1, a1 = up ? lum2 : lum3, a2 = up ? lum3 : lum2, a3 = up ? lum1 : lum0;
-    uint32_t h1, h2, h3;
-    if (all_regular) {
-      h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
-      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;        // 2->3 stays on tie, 3->2 moves
-      h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
-    } else {
-      // Which of the two inner candidates survive.  Ascending order carries indices (0,2,3,1) when rising and (1,3,2,0)
-      // when falling; a candidate is dead when an equal luminance exists under a smaller index.
-      const bool inner_tie = a1 == a2;
-      const bool dead1 = a1 == a0 || a1 == a3 || (!up && inner_tie);   // index 2 (rising) / 3 (falling)
-      const bool dead2 = a2 == a0 || a2 == a3 || (up && inner_tie);    // index 3 (rising) / 2 (falling)
-      const uint32_t first_above = !dead1 ? a1 : (!dead2 ? a2 : a3);   // first live candidate above a0
-      const uint32_t last_below = !dead2 ? a2 : (!dead1 ? a1 : a0);    // last live candidate below a3
-      h1 = ((a0 + first_above + 32u) >> 1) & ~15u;            // into a larger index: a tie stays
-      h3 = ((last_below + a3 + 16u) >> 1) & ~15u;             // into a smaller index: a tie moves
-      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;
-      if (dead1 && dead2) {                                   // only the base colours are left: one crossing, 0->1 / 1->0
-        h1 = up ? h1 : h3;
-        h3 = h1;
-      }
-      // The low bit is set for indices 3 and 1: it flips at the inner crossing; without the second inner candidate
-      // (index 3 rising, 2 falling) it flips with the band's far edge, without the first one with its near edge.
-      if (dead1 || dead2) h2 = dead2 ? h3 : h1;
-    }
-    const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 16u) >> 1));
-    // R + 1 = (h3 - h1 - 16) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -7: never set
-    const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388615.0f;
-    // The low bit is computed as [v >= h2] for both directions -- one two-operand FADD.SAT per pixel, where a per-block
-    // sign would need the three-register FFMA form, which issues at half the rate of the two-operand and immediate
-    // forms -- and flipped for all sixteen pixels at the end when the sequence falls (bit0 = [v < h2] there).
-    const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 16*l >= h2
-    float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float v = __uint_as_float(kf[i]);
-      const float u = __saturatef(rp1 - fabsf(v - mid));
-      const float t = __saturatef(v + k2);
-      const float z = fmaf(u, 2.0f, t);
-      const float scale = static_cast<float>(1u << (2 * (i & 7)));
-      if (i < 8)
-        acc_lo = fmaf(z, scale, acc_lo);
-      else
-        acc_hi = fmaf(z, scale, acc_hi);
-    }
-    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410) ^ (up ? 0u : 0x55555555u);
-  } else {
-    float acc0, cross[3], step[3];
-    {
-      // General case (flat blocks, crossed or equal candidates): sort the candidates as keys 16*L_c + c.
-      uint32_t s0 = lum0, s1 = lum1 + 1u, s2 = lum2 + 2u, s3 = lum3 + 3u;
-      sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
-      const uint32_t sorted[4] = {s0, s1, s2, s3};
-      uint32_t rep = s0;                                  // lowest-index candidate of the current luminance
-      acc0 = __uint_as_float(kDxtLumBias + (s0 & 3u));    // 2^23 + index of the lowest candidate
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const uint32_t b = sorted[j + 1];
-        const bool same_lum = (b - rep) < 4u;             // keys differ only in the index bits
-        const uint32_t cb = b & 3u, cr = rep & 3u;
-        // pixel key v = 16*l crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
-        const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
-        cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : kDxtLumBias + h - 1u);
-        step[j] = static_cast<float>((cb - cr) & 3u);  // irrelevant when same_lum: that crossing never fires
-        rep = same_lum ? rep : b;
-      }
-    }
-    bits = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float v = __uint_as_float(kf[i]);
-      float acc = fmaf(__saturatef(v - cross[0]), step[0], acc0);
-      acc = fmaf(__saturatef(v - cross[1]), step[1], acc);
-      acc = fmaf(__saturatef(v - cross[2]), step[2], acc);
-      bits = __funnelshift_r(bits, __float_as_uint(acc), 2);  // low two mantissa bits = chosen index (mod 4)
-    }
-  }
-  return make_uint2(c0 | (c1 << 16), bits);
-}
-
 // Keys from 16 packed pixels (bytes c0,c1,c2,x in memory order; x ignored).
-template <bool kFullWarp = false, bool kSwapBases = false, typename Fetch, typename Release = NoRelease>
+template <bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch,
                                                    Release release = Release()) {
   const uint32_t w16 = dxt_lum_weights(swap_rb);
   uint32_t kf[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
-  if constexpr (kSwapBases) return dxt1_encode_from_keys_swapping<kFullWarp>(kf, swap_rb, always4, fetch, release);
   return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
 }
 
