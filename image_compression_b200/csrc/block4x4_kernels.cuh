@@ -103,6 +103,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 #ifndef ICB_DXT1_TILE_BLOCKS_Y
 #define ICB_DXT1_TILE_BLOCKS_Y 8
 #endif
+// Producer-warp kernel: 1 = consumers hand a ring slot back from inside the encoder (after the last read of the staged
+// pixels) instead of after the block is stored.  A/B knob.
+#ifndef ICB_TMA_EARLY_RELEASE
+#define ICB_TMA_EARLY_RELEASE 0
+#endif
 template <int kCodec>
 constexpr int tile_blocks_y() { return kCodec == kCodecDxt1 ? ICB_DXT1_TILE_BLOCKS_Y : 4; }
 
@@ -130,6 +135,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -141,18 +152,25 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // [row0,row1) x columns [col0,col1), each extent at least one tile; tiles are numbered row-major, tiles_x per row,
 // and the last tile of a row / column is shifted back so that it ends exactly at col1 / row1 -- the blocks it
 // shares with its neighbour are simply encoded twice, to the same bytes.
-template <int kCodec, int kNcomp, int kTmaStages>
+// kSwapRb: red and blue exchanged (kBGR / kBGRA sources) as a COMPILE-TIME constant -- the luminance, quantiser and
+// channel-extraction weights of the DXT encoders depend on it, and as a run-time parameter it cost about ten
+// uniform-datapath selects per block, which share the warp's issue slots (ETC1 does not look at it).
+template <int kCodec, int kNcomp, int kTmaStages, bool kSwapRb>
 __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 32, TileShape<kCodec, kNcomp>::kProducerMinCtas)
     encode4x4_tma_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                          uint32_t num_tiles) {
   using Shape = TileShape<kCodec, kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // layout: kTmaStages tiles, then kTmaStages "full" barriers, then kTmaStages "empty" barriers
+  // layout: kTmaStages tiles, then kTmaStages "full" barriers, kTmaStages "empty" barriers, kTmaStages tile origins
   // (kTmaStages trades bytes in flight per CTA against resident CTAs per SM; the launcher picks)
   // (volatile: keeps the shared-window base in a register instead of re-deriving it from SR_CgaCtaId per tile)
   uint32_t tiles_s;
   asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
   const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, empty_s = full_s + kTmaStages * 8;
+  // ... then per stage the byte offset of the tile's first block in the output (8 bytes): whoever loads a tile works
+  // its position out ONCE and leaves it here; the consumers pick it up with one 64-bit shared load instead of each
+  // thread tracking (tx, ty), clamping and multiplying on its own (about fifteen instructions per block).
+  const uint32_t origin_s = empty_s + kTmaStages * 8;
   constexpr uint32_t kConsumerWarps = Shape::kConsumerThreads / 32;
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
@@ -170,9 +188,11 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
   const uint64_t policy = is_producer ? l2_evict_first_policy() : 0ull;  // the source is read exactly once
   auto produce_one = [&]() {
     mbar_wait_relaxed(empty_s + 8 * p_stage, p_phase ^ 1u);  // passes at once on the first trip round the ring
-    mbar_arrive_expect_tx(full_s + 8 * p_stage, Shape::kBytes);
     const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, p.col1 - Shape::kBlocksX);
     const uint32_t br = min(p.row0 + ty * Shape::kBlocksY, p.row1 - Shape::kBlocksY);
+    // (ordered before the consumers' reads by the arrive below and the tile's completion on the same barrier)
+    sts_u64(origin_s + 8 * p_stage, (static_cast<uint64_t>(br) * p.grid_cols + bc) * kBlockBytes);
+    mbar_arrive_expect_tx(full_s + 8 * p_stage, Shape::kBytes);
     tma_load_2d(tiles_s + p_stage * Shape::kBytes, &src_map, full_s + 8 * p_stage, static_cast<int32_t>(bc * kNcomp),
                 static_cast<int32_t>(br * 4u), policy);
     if (++p_stage == kTmaStages) {
@@ -216,9 +236,7 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
   const uint32_t win0 = tiles_s + (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;
   // This thread's block in a tile whose first block is (0,0); the launcher checks that a row of blocks fits 32 bits.
   uint8_t *const out_origin = p.dst + (static_cast<size_t>(lby) * p.grid_cols + lbx) * kBlockBytes;
-  const uint32_t out_row_bytes = p.grid_cols * kBlockBytes;
-  const uint32_t last_bc = p.col1 - Shape::kBlocksX, last_br = p.row1 - Shape::kBlocksY;
-  const bool swap_rb = p.swap_rb != 0;
+  constexpr bool swap_rb = kSwapRb;
   // The ring is walked with the stage as a compile-time constant (barrier and tile addresses become immediates)
   // where the encoder is small; ETC1's exhaustive search is ~5000 instructions, three copies of which would not
   // fit the instruction cache, so it keeps a run-time stage.
@@ -241,9 +259,14 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
           return lds_u8(q) | (lds_u8(q + 1) << 8) | (lds_u8(q + 2) << 16);
         }
       };
-      const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
-      uint8_t *out = out_origin + static_cast<size_t>(br) * out_row_bytes + bc * kBlockBytes;
       mbar_wait(full_s + 8 * stage, phase);
+      uint8_t *out = out_origin + lds_u64(origin_s + 8 * stage);
+      // Hands the slot back to the producer: either from inside the encoder, as soon as it has read its last pixel
+      // from the tile (ICB_TMA_EARLY_RELEASE), or after the block has been stored.
+      auto release = [&]() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
+      };
 
       if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
         // RGB888 -> DXT1 never needs the unpacked pixels: luminance keys come straight from the row words
@@ -254,7 +277,11 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
           rows[y][1] = lds_u32(win + y * kRowBytes + 4);
           rows[y][2] = lds_u32(win + y * kRowBytes + 8);
         }
+#if ICB_TMA_EARLY_RELEASE
+        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch, release);
+#else
         *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch);
+#endif
       } else {
         uint32_t px[16];
 #pragma unroll
@@ -271,17 +298,16 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
             px[4 * y + 3] = w2 >> 8;
           }
         }
-        encode_and_store<kCodec, true>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out);
+#if ICB_TMA_EARLY_RELEASE
+        encode_and_store<kCodec, true>(px, fetch, false, swap_rb ? 1 : 0, p.etc_strategy, alpha_table, out, release);
+#else
+        encode_and_store<kCodec, true>(px, fetch, false, swap_rb ? 1 : 0, p.etc_strategy, alpha_table, out);
+#endif
       }
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
+#if !ICB_TMA_EARLY_RELEASE
+      release();
+#endif
       tile += gridDim.x;
-      tx += step_x;
-      ty += step_y;
-      if (tx >= tiles_x) {
-        tx -= tiles_x;
-        ++ty;
-      }
       if constexpr (kUnroll == 1) {
         if (++rt_stage == kTmaStages) {
           rt_stage = 0;
@@ -322,22 +348,23 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t addr, uint3
 #define ICB_DXT5_RING_MIN_CTAS 4
 #endif
 
-template <int kCodec, int kNcomp, int kTmaStages>
+template <int kCodec, int kNcomp, int kTmaStages, bool kSwapRb>
 __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
                                   kCodec == kCodecEtc1 ? 3 : (kCodec == kCodecDxt5 ? ICB_DXT5_RING_MIN_CTAS : TileShape<kCodec, kNcomp>::kProducerMinCtas))
     encode4x4_ring_kernel(const __grid_constant__ CUtensorMap src_map, const Encode4x4Params p, uint32_t tiles_x,
                           uint32_t num_tiles) {
   using Shape = TileShape<kCodec, kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), then per stage a done-counter (8 bytes)
+  // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), a done-counter (8 bytes), a tile origin (8 bytes)
   uint32_t tiles_s;
   asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
+  // ... then per stage the byte offset of the tile's first block in the output (see encode4x4_tma_kernel)
   const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, count_s = full_s + kTmaStages * 8;
+  const uint32_t origin_s = count_s + kTmaStages * 8;
   constexpr uint32_t kWarps = Shape::kConsumerThreads / 32;
   static_assert((kWarps & (kWarps - 1)) == 0, "the done-counter is tested modulo the warp count");
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
-  const uint32_t step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
   // DXT5's 32 KB crossing table is read from global memory (four 16-byte loads per block, L1-resident): a
   // shared-memory copy would cost resident CTAs.
   const uint4 *alpha_table = reinterpret_cast<const uint4 *>(g_dxt5_alpha_table);
@@ -348,6 +375,8 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
   auto load_tile = [&](uint32_t t, uint32_t stage) {
     const uint32_t ty = t / tiles_x, tx = t - ty * tiles_x;
     const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
+    // (every warp reads the slot's previous origin before it counts itself off, i.e. before the refill that calls this)
+    sts_u64(origin_s + 8 * stage, (static_cast<uint64_t>(br) * p.grid_cols + bc) * kBlockBytes);
     mbar_arrive_expect_tx(full_s + 8 * stage, Shape::kBytes);
     tma_load_2d(tiles_s + stage * Shape::kBytes, &src_map, full_s + 8 * stage, static_cast<int32_t>(bc * kNcomp),
                 static_cast<int32_t>(br * 4u), l2_evict_first_policy());  // the source is read exactly once
@@ -374,10 +403,8 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
   const uint32_t lbx = threadIdx.x % Shape::kBlocksX, lby = threadIdx.x / Shape::kBlocksX;
   const uint32_t win0 = tiles_s + (lby * 4u * Shape::kRowWords + lbx * kNcomp) * 4u;
   uint8_t *const out_origin = p.dst + (static_cast<size_t>(lby) * p.grid_cols + lbx) * kBlockBytes;
-  const uint32_t out_row_bytes = p.grid_cols * kBlockBytes;
-  const bool swap_rb = p.swap_rb != 0;
+  constexpr bool swap_rb = kSwapRb;
   const uint32_t refill_stride = kTmaStages * gridDim.x;
-  uint32_t ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;  // this CTA's current tile
   constexpr int kUnroll = kCodec == kCodecEtc1 ? 1 : kTmaStages;  // see encode4x4_tma_kernel
   uint32_t phase = 0, tile = blockIdx.x, rt_stage = 0;
   while (true) {
@@ -395,8 +422,6 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
           return lds_u8(q) | (lds_u8(q + 1) << 8) | (lds_u8(q + 2) << 16);
         }
       };
-      const uint32_t bc = min(p.col0 + tx * Shape::kBlocksX, last_bc), br = min(p.row0 + ty * Shape::kBlocksY, last_br);
-      uint8_t *out = out_origin + static_cast<size_t>(br) * out_row_bytes + bc * kBlockBytes;
       // Done with this slot (called by the encoder as soon as it has read its last pixel from the tile): count this
       // warp off; the last warp to do so refills the slot.  The acq_rel atomic (MEMBAR.CTA + ATOMS) completes this
       // warp's shared-memory reads before the count and makes every warp's reads happen-before the refill.
@@ -417,6 +442,7 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
       if ((((threadIdx.x >> 5) * 3u + tile) & 7u) == 1u) __nanosleep(5000);  // ... and some arrive late at the next tile
 #endif
       mbar_wait(full_s + 8 * stage, phase);
+      uint8_t *out = out_origin + lds_u64(origin_s + 8 * stage);  // before release(): the refill overwrites it
 
       if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
         uint32_t rows[4][3];
@@ -443,15 +469,9 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
             px[4 * y + 3] = w2 >> 8;
           }
         }
-        encode_and_store<kCodec, true>(px, fetch, false, p.swap_rb, p.etc_strategy, alpha_table, out, release);
+        encode_and_store<kCodec, true>(px, fetch, false, swap_rb ? 1 : 0, p.etc_strategy, alpha_table, out, release);
       }
       tile += gridDim.x;
-      tx += step_x;
-      ty += step_y;
-      if (tx >= tiles_x) {
-        tx -= tiles_x;
-        ++ty;
-      }
       if constexpr (kUnroll == 1) {
         if (++rt_stage == kTmaStages) {
           rt_stage = 0;

@@ -121,8 +121,10 @@ __device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
   return c0 | (c1 << 16) | (static_cast<uint64_t>(which) << 32);
 }
 
-// Weights for IDP.4A: 16*(4,8,1) on the logical (r,g,b); the alpha byte always gets weight 0.
-__device__ __forceinline__ uint32_t dxt_lum_weights(bool swap_rb) { return swap_rb ? 0x00408010u : 0x00108040u; }
+// Weights for IDP.4A: 8*(4,8,1) on the logical (r,g,b); the alpha byte always gets weight 0.  (Scale 8, not 16: the
+// keys 8*lum + index stay below 2^15 -- lum <= 3315 -- so they are also valid SIGNED 16-bit lanes, which the
+// index search's VIADDMNMX.S16x2 needs; half-integer crossing points only need a scale of 2.)
+__device__ __forceinline__ uint32_t dxt_lum_weights(bool swap_rb) { return swap_rb ? 0x00204008u : 0x00084020u; }
 
 // 565 quantisation straight from a packed pixel.  round(v*31/255) == (v*249 + 1024) >> 11 and
 // round(v*63/255) == (v*253 + 512) >> 10 for every 8-bit v (checked exhaustively in tests/test_host_math.py), so
@@ -146,17 +148,30 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 // Index search.  The reference scores pixel luminance l against the four candidate luminances L_c with
 // (L_c - l)^2 and keeps the first strict minimum (dxtc_compressor.cc:334-345).  On a line that is a nearest-
 // neighbour search, so the answer only changes where l crosses the midpoint of two neighbouring candidates:
-//   * sort the candidates by (L_c, c) once per block (five min/max pairs);
 //   * walking upwards, candidate b replaces the current one a iff 2l > L_a + L_b, or 2l == L_a + L_b and b has the
 //     smaller index (that is what "first strict minimum" does with a tie); candidates with equal luminance are
 //     represented by their smallest index;
-//   * per pixel, each of the three crossings is one saturating float add (1.0 if crossed, else 0.0) and one
-//     float multiply-add that accumulates the index change -- exact, since every value is an integer below 2^24,
-//     and it runs on the FMA pipes while the integer pipe, which bounds this kernel, only does the final bit
-//     insert.  The pixel value 2^23 + 16*l is produced directly in float format by the IDP.4A that computes the
-//     luminance (accumulator 0x4B000000), so no int->float conversion is needed.
-// kf[i] = 0x4B000000 + 16*lum(pixel i): read as a float it is 2^23 + 16*lum, which the index search consumes as is.
+//   * a pixel's index is the start index plus the index changes of the crossings it has passed.
+// Keys.  kf[i] = 0x4B000000 + 8*lum(pixel i) + seed(i): produced by the IDP.4A that computes the luminance, with the
+// constant in its accumulator.  The low half is the 16-bit key 8*lum + index-within-lane (< 2^15: also a valid SIGNED
+// lane); read as a float the word is 2^23 + key, exact, which the fp32 form of the search consumes as is.
+// Pixel pair (k, k+8) shares one register, pixel k in the low lane: the low lane of an accumulator then collects the
+// index bits of pixels 0..7 and the high lane those of pixels 8..15, i.e. the finished 32-bit index word.
 constexpr uint32_t kDxtLumBias = 0x4b000000u;
+constexpr uint32_t kDxtKeyStep = 8u;  // key units per unit of luminance
+
+// Which pixel pairs (bit k = pair (k, k+8)) run the usual-case index search on 16-bit integer lanes -- per pair three
+// VIADDMNMX.S16x2.RELU (integer pipe) + three IMAD with immediate steps (FMA pipe): 3 instructions per pixel -- and
+// which on fp32 -- five FADD/FFMA per pixel, nothing on the integer pipe.  The split balances the two pipes; A/B knob
+// (tools/build_variants.sh), measured values in DESIGN.md section 4.2.
+#ifndef ICB_DXT_INT_PAIRS
+#define ICB_DXT_INT_PAIRS 0xff
+#endif
+constexpr uint32_t kDxtIntPairs = ICB_DXT_INT_PAIRS;
+constexpr __host__ __device__ bool dxt_int_pair(int k) { return ((kDxtIntPairs >> (k & 7)) & 1u) != 0u; }
+// The accumulator of pixel i's key IDP: integer pairs get their lane index for free here; fp32 pairs must not carry
+// one (their band test is symmetric about a midpoint), it is added when the 16-bit keys are packed.
+constexpr __host__ __device__ uint32_t dxt_key_seed(int i) { return kDxtLumBias + (dxt_int_pair(i) ? static_cast<uint32_t>(i & 7) : 0u); }
 
 // A caller that stages pixels in a buffer it wants back early passes `release`; it is called once, right after the
 // two base colours have been re-read through `fetch` (nothing reads the staged pixels after that).
@@ -167,24 +182,32 @@ struct NoRelease {
 template <bool kFullWarp, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16], bool swap_rb, bool always4, Fetch fetch,
                                                        Release release = Release()) {
-  // First minimum / first maximum in raster order: 16-bit keys 16*lum + i (lum <= 3315), two pixels per register;
-  // the maximum uses the index field reversed (^15) so that ties resolve to the lowest index.  VIMNMX3.U16x2
-  // folds two more registers (four pixels) per instruction.
+  // First minimum / first maximum in raster order: 16-bit keys 8*lum + k, pixel k in the low lane and pixel k + 8 in
+  // the high lane of register k; the maximum uses the index field reversed (^7) so that ties resolve to the lowest
+  // index.  VIMNMX3.U16x2 folds two more registers (four pixels) per instruction.
   uint32_t pk[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) pk[k] = __byte_perm(kf[2 * k], kf[2 * k + 1], 0x5410) + ((2u * k) | ((2u * k + 1u) << 16));
+  for (int k = 0; k < 8; ++k) {
+    pk[k] = __byte_perm(kf[k], kf[k + 8], 0x5410);
+    if (!dxt_int_pair(k)) pk[k] += static_cast<uint32_t>(k) * 0x10001u;
+  }
   uint32_t mn = __vimin3_u16x2(pk[0], pk[1], pk[2]);
   mn = __vimin3_u16x2(mn, pk[3], pk[4]);
   mn = __vimin3_u16x2(mn, pk[5], pk[6]);
   mn = __vminu2(mn, pk[7]);
-  uint32_t mx = __vimax3_u16x2(pk[0] ^ 0x000f000fu, pk[1] ^ 0x000f000fu, pk[2] ^ 0x000f000fu);
-  mx = __vimax3_u16x2(mx, pk[3] ^ 0x000f000fu, pk[4] ^ 0x000f000fu);
-  mx = __vimax3_u16x2(mx, pk[5] ^ 0x000f000fu, pk[6] ^ 0x000f000fu);
-  mx = __vmaxu2(mx, pk[7] ^ 0x000f000fu);
-  const uint32_t kmin = min(mn & 0xffffu, mn >> 16), kmax = max(mx & 0xffffu, mx >> 16);
-  uint32_t p0 = fetch(kmin & 15u), p1 = fetch((kmax & 15u) ^ 15u);  // base colours, memory byte order
+  uint32_t mx = __vimax3_u16x2(pk[0] ^ 0x00070007u, pk[1] ^ 0x00070007u, pk[2] ^ 0x00070007u);
+  mx = __vimax3_u16x2(mx, pk[3] ^ 0x00070007u, pk[4] ^ 0x00070007u);
+  mx = __vimax3_u16x2(mx, pk[5] ^ 0x00070007u, pk[6] ^ 0x00070007u);
+  mx = __vmaxu2(mx, pk[7] ^ 0x00070007u);
+  // Between the lanes: every pixel of the low lane precedes every pixel of the high lane, so the low lane wins ties
+  // of luminance whatever the index fields say.
+  const uint32_t mn_lo = mn & 0xffffu, mn_hi = mn >> 16, mx_lo = mx & 0xffffu, mx_hi = mx >> 16;
+  const bool min_in_lo = mn_lo <= (mn_hi | 7u), max_in_lo = (mx_lo | 7u) >= mx_hi;
+  const uint32_t kmin = min_in_lo ? mn_lo : mn_hi, kmax = max_in_lo ? mx_lo : mx_hi;
+  const uint32_t imin = (kmin & 7u) + (min_in_lo ? 0u : 8u), imax = ((kmax & 7u) ^ 7u) + (max_in_lo ? 0u : 8u);
+  uint32_t p0 = fetch(imin), p1 = fetch(imax);  // base colours, memory byte order
   release();
-  const uint32_t lum0 = kmin & 0xfff0u, lum1 = kmax & 0xfff0u;      // 16 * luminance of p0 / p1: lum0 <= lum1
+  const uint32_t lum0 = kmin & 0xfff8u, lum1 = kmax & 0xfff8u;      // 8 * luminance of p0 / p1: lum0 <= lum1
   const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
   const uint32_t q0 = dxt_to_565(p0, w_red, w_blue), q1 = dxt_to_565(p1, w_red, w_blue);
   // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
@@ -203,10 +226,10 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
   const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
   constexpr uint32_t kThird = 683u << 21;
-  const uint32_t lum2 = 64u * __umulhi(2u * r0 + r1, kThird) + 128u * __umulhi(2u * g0 + g1, kThird) +
-                        16u * __umulhi(2u * b0 + b1, kThird);   // the interpolant next to p0
-  const uint32_t lum3 = 64u * __umulhi(r0 + 2u * r1, kThird) + 128u * __umulhi(g0 + 2u * g1, kThird) +
-                        16u * __umulhi(b0 + 2u * b1, kThird);   // the interpolant next to p1
+  const uint32_t lum2 = 32u * __umulhi(2u * r0 + r1, kThird) + 64u * __umulhi(2u * g0 + g1, kThird) +
+                        8u * __umulhi(2u * b0 + b1, kThird);    // the interpolant next to p0
+  const uint32_t lum3 = 32u * __umulhi(r0 + 2u * r1, kThird) + 64u * __umulhi(g0 + 2u * g1, kThird) +
+                        8u * __umulhi(b0 + 2u * b1, kThird);    // the interpolant next to p1
   // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
   // base colours, i.e. the candidates are ordered along the luminance line with no two equal.  Then the crossing
   // order, the tie rules and the index changes are fixed and only the three midpoints have to be computed.
@@ -218,8 +241,8 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // Second chance for the line search, again decided once per warp: blocks whose interpolants are only WEAKLY between
   // the base colours (equal luminances: narrow-range blocks in flat, dark or slowly varying image regions -- most of a
   // real texture).  Candidates that tie with a lower index never win ("first strict minimum"), so they drop out of the
-  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0 when swapped) along the line and the same two band tests
-  // classify it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
+  // sequence; what is left is still 0,[2],[3],1 (or 1,[3],[2],0 when swapped) along the line and the same three
+  // crossings classify it once the crossings of the missing candidates are collapsed onto their neighbours' (below).
   const bool up = !swapped;  // reference indices along the ascending line: (0,2,3,1) unswapped, (1,3,2,0) swapped
   bool all_monotone = all_regular;
   if (!all_regular) {  // (uniform branch: the usual warp does not pay for the extra comparisons)
@@ -235,19 +258,16 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     c1 = (static_cast<uint32_t>(packed) >> 16) & 0xffffu;
     bits = static_cast<uint32_t>(packed >> 32) * 0x55555555u;
   } else if (all_monotone) {
-    // Ascending index sequence along the luminance line: rising 0,2,3,1, falling 1,3,2,0; a tie goes to the smaller
-    // index.  Crossing points h1 <= h2 <= h3 (multiples of 16, "crossed iff 16*l >= h").  In both sequences the high
-    // index bit is set exactly between the outer crossings and the low bit flips at the middle one:
-    //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 16]
-    //   bit0 = [v >= h2] (rising) / [v < h2] (falling) = sat(v - h2 + 1), flipped at the end when falling
-    // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position, eight pixels per accumulator:
-    // five exact FADD/FFMA per pixel on the FMA pipes and no per-pixel work on the integer pipe.
+    // Ascending index sequence along the luminance line: rising 0,2,3,1, falling 1,3,2,0 = the rising one with the low
+    // bit of every index flipped (one XOR of the finished word); a tie goes to the smaller index.  Crossing points
+    // h1 <= h2 <= h3 (multiples of 8, "crossed iff 8*l >= h"), index changes +2, +1, -2:
+    //   index = 2*[v >= h1] + [v >= h2] - 2*[v >= h3]
     const uint32_t a0 = lum0, a1 = lum2, a2 = lum3, a3 = lum1;  // ascending
     uint32_t h1, h2, h3;
     if (all_regular) {
-      h1 = ((a0 + a1 + 32u) >> 1) & ~15u;                     // 0->2 / 1->3: larger index, tie stays
-      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;        // 2->3 stays on tie, 3->2 moves
-      h3 = ((a2 + a3 + 16u) >> 1) & ~15u;                     // 3->1 / 2->0: smaller index, tie moves
+      h1 = ((a0 + a1 + 16u) >> 1) & ~7u;                      // 0->2 / 1->3: larger index, tie stays
+      h2 = ((a1 + a2 + (up ? 16u : 8u)) >> 1) & ~7u;          // 2->3 stays on tie, 3->2 moves
+      h3 = ((a2 + a3 + 8u) >> 1) & ~7u;                       // 3->1 / 2->0: smaller index, tie moves
     } else {
       // Which of the two inner candidates survive.  Ascending order carries indices (0,2,3,1) when rising and (1,3,2,0)
       // when falling; a candidate is dead when an equal luminance exists under a smaller index.
@@ -256,9 +276,9 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
       const bool dead2 = a2 == a0 || a2 == a3 || (up && inner_tie);    // index 3 (rising) / 2 (falling)
       const uint32_t first_above = !dead1 ? a1 : (!dead2 ? a2 : a3);   // first live candidate above a0
       const uint32_t last_below = !dead2 ? a2 : (!dead1 ? a1 : a0);    // last live candidate below a3
-      h1 = ((a0 + first_above + 32u) >> 1) & ~15u;            // into a larger index: a tie stays
-      h3 = ((last_below + a3 + 16u) >> 1) & ~15u;             // into a smaller index: a tie moves
-      h2 = ((a1 + a2 + (up ? 32u : 16u)) >> 1) & ~15u;
+      h1 = ((a0 + first_above + 16u) >> 1) & ~7u;             // into a larger index: a tie stays
+      h3 = ((last_below + a3 + 8u) >> 1) & ~7u;               // into a smaller index: a tie moves
+      h2 = ((a1 + a2 + (up ? 16u : 8u)) >> 1) & ~7u;
       if (dead1 && dead2) {                                   // only the base colours are left: one crossing, 0->1 / 1->0
         h1 = up ? h1 : h3;
         h3 = h1;
@@ -267,31 +287,53 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
       // (index 3 rising, 2 falling) it flips with the band's far edge, without the first one with its near edge.
       if (dead1 || dead2) h2 = dead2 ? h3 : h1;
     }
-    const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 16u) >> 1));
-    // R + 1 = (h3 - h1 - 16) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -7: never set
-    const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388615.0f;
-    // The low bit is computed as [v >= h2] for both directions -- one two-operand FADD.SAT per pixel, where a per-block
-    // sign would need the three-register FFMA form, which issues at half the rate of the two-operand and immediate
-    // forms -- and flipped for all sixteen pixels at the end when the base colours were swapped (indices 2k <-> 2k+1).
-    const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 16*l >= h2
-    float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
+    // Integer pairs: t = relu(min(key + (1 - h), 1)) is 1 once the pixel has passed crossing h -- the key's index field
+    // (< 8) cannot carry it over a multiple of 8 -- for both pixels of the pair in one VIADDMNMX.S16x2.RELU, and
+    // t * (step << 2k) drops the index change at the pair's bit position of both lanes in one IMAD with an immediate
+    // multiplier.  All arithmetic is modulo 2^32 and the final fields are indices 0..3, so the order of the additions
+    // does not matter.
+    const uint32_t m1 = 1u - h1, m2 = 1u - h2, m3 = 1u - h3;
+    const uint32_t n1 = __byte_perm(m1, m1, 0x1010), n2 = __byte_perm(m2, m2, 0x1010), n3 = __byte_perm(m3, m3, 0x1010);
+    uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float v = __uint_as_float(kf[i]);
-      const float u = __saturatef(rp1 - fabsf(v - mid));
-      const float t = __saturatef(v + k2);
-      const float z = fmaf(u, 2.0f, t);
-      const float scale = static_cast<float>(1u << (2 * (i & 7)));
-      if (i < 8)
-        acc_lo = fmaf(z, scale, acc_lo);
-      else
-        acc_hi = fmaf(z, scale, acc_hi);
+    for (int k = 0; k < 8; ++k) {
+      if (!dxt_int_pair(k)) continue;
+      acc += __viaddmin_s16x2_relu(pk[k], n1, 0x00010001u) * (2u << (2 * k));
+      acc += __viaddmin_s16x2_relu(pk[k], n2, 0x00010001u) * (1u << (2 * k));
+      acc -= __viaddmin_s16x2_relu(pk[k], n3, 0x00010001u) * (2u << (2 * k));
     }
-    bits = __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410) ^ (swapped ? 0x55555555u : 0u);
+    if constexpr (kDxtIntPairs != 0xffu) {
+      // fp32 pairs: the high index bit is set exactly between the outer crossings and the low bit flips at the middle one:
+      //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 8]
+      //   bit0 = [v >= h2] = sat(v - h2 + 1)
+      // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position: five exact FADD/FFMA per pixel.
+      const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 8u) >> 1));
+      // R + 1 = (h3 - h1 - 8) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -3: never set
+      const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388611.0f;
+      const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 8*l >= h2
+      float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (dxt_int_pair(i)) continue;
+        const float v = __uint_as_float(kf[i]);
+        const float u = __saturatef(rp1 - fabsf(v - mid));
+        const float t = __saturatef(v + k2);
+        const float z = fmaf(u, 2.0f, t);
+        const float scale = static_cast<float>(1u << (2 * (i & 7)));
+        if (i < 8)
+          acc_lo = fmaf(z, scale, acc_lo);
+        else
+          acc_hi = fmaf(z, scale, acc_hi);
+      }
+      acc += __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410);
+    }
+    bits = acc ^ (swapped ? 0x55555555u : 0u);
   } else {
     float acc0, cross[3], step[3];
     {
-      // General case (crossed candidates): sort the candidates as keys 16*L_c + c, c = the reference's index.
+      // General case (crossed candidates): sort the candidates as keys 8*L_c + c, c = the reference's index; per pixel,
+      // each of the three crossings is one saturating float add (1.0 if crossed, else 0.0) and one float multiply-add
+      // that accumulates the index change -- exact, since every value is an integer below 2^24.
       uint32_t s0 = swapped ? lum1 : lum0, s1 = (swapped ? lum0 : lum1) + 1u, s2 = (swapped ? lum3 : lum2) + 2u,
                s3 = (swapped ? lum2 : lum3) + 3u;
       sort2(s0, s1); sort2(s2, s3); sort2(s0, s2); sort2(s1, s3); sort2(s1, s2);
@@ -303,8 +345,8 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
         const uint32_t b = sorted[j + 1];
         const bool same_lum = (b - rep) < 4u;             // keys differ only in the index bits
         const uint32_t cb = b & 3u, cr = rep & 3u;
-        // pixel key v = 16*l crosses iff v >= h, h = 16 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
-        const uint32_t h = ((rep + b + (cb < cr ? 16u : 32u)) >> 1) & ~15u;
+        // pixel key v = 8*l (+ lane index < 8) crosses iff v >= h, h = 8 * ceil((L_a + L_b + (cb < cr ? 0 : 1)) / 2)
+        const uint32_t h = ((rep + b + (cb < cr ? 8u : 16u)) >> 1) & ~7u;
         cross[j] = __uint_as_float(same_lum ? 0x4b7fffffu : kDxtLumBias + h - 1u);
         step[j] = static_cast<float>((cb - cr) & 3u);  // irrelevant when same_lum: that crossing never fires
         rep = same_lum ? rep : b;
@@ -313,7 +355,9 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
     bits = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float v = __uint_as_float(kf[i]);
+      // 2^23 + key of pixel i, rebuilt from the packed 16-bit keys (one byte permute) so that the sixteen key words need
+      // not stay in registers across the vote just for this path
+      const float v = __uint_as_float(__byte_perm(pk[i & 7], kDxtLumBias, i < 8 ? 0x7610 : 0x7632));
       float acc = fmaf(__saturatef(v - cross[0]), step[0], acc0);
       acc = fmaf(__saturatef(v - cross[1]), step[1], acc);
       acc = fmaf(__saturatef(v - cross[2]), step[2], acc);
@@ -327,10 +371,10 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
 template <bool kFullWarp = false, typename Fetch, typename Release = NoRelease>
 __device__ __forceinline__ uint2 dxt1_encode_block(const uint32_t (&px)[16], bool swap_rb, bool always4, Fetch fetch,
                                                    Release release = Release()) {
-  const uint32_t w16 = dxt_lum_weights(swap_rb);
+  const uint32_t w8 = dxt_lum_weights(swap_rb);
   uint32_t kf[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w16, kDxtLumBias);
+  for (int i = 0; i < 16; ++i) kf[i] = __dp4a(px[i], w8, dxt_key_seed(i));
   return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
 }
 
@@ -348,10 +392,10 @@ __device__ __forceinline__ uint2 dxt1_encode_rgb888_rows(const uint32_t (&rows)[
   uint32_t kf[16];
 #pragma unroll
   for (int y = 0; y < 4; ++y) {
-    kf[4 * y + 0] = __dp4a(rows[y][0], wa, kDxtLumBias);
-    kf[4 * y + 1] = __dp4a(rows[y][1], wb_hi, __dp4a(rows[y][0], wb_lo, kDxtLumBias));
-    kf[4 * y + 2] = __dp4a(rows[y][2], wc_hi, __dp4a(rows[y][1], wc_lo, kDxtLumBias));
-    kf[4 * y + 3] = __dp4a(rows[y][2], wd, kDxtLumBias);
+    kf[4 * y + 0] = __dp4a(rows[y][0], wa, dxt_key_seed(4 * y + 0));
+    kf[4 * y + 1] = __dp4a(rows[y][1], wb_hi, __dp4a(rows[y][0], wb_lo, dxt_key_seed(4 * y + 1)));
+    kf[4 * y + 2] = __dp4a(rows[y][2], wc_hi, __dp4a(rows[y][1], wc_lo, dxt_key_seed(4 * y + 2)));
+    kf[4 * y + 3] = __dp4a(rows[y][2], wd, dxt_key_seed(4 * y + 3));
   }
   return dxt1_encode_from_keys<kFullWarp>(kf, swap_rb, always4, fetch, release);
 }
@@ -385,11 +429,13 @@ constexpr int kDxt5AlphaTableBytes = 512 * 64;
 // Round 1 ran this on packed fp16 (HFMA2.SAT + HFMA2 per crossing, both on the half-rate FMA pipe, 322 instructions
 // per block); this form needs about 240 and splits them between the two pipes.
 // Part 1: the two endpoint alphas, packed a0 | a1 << 8 (ComputeBaseAlphas).
-__device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&px)[16]) {
-  uint32_t x[8];
+// The sixteen alphas as eight lane pairs: x[i] = (alpha of pixel i + 8) << 16 | alpha of pixel i.
+__device__ __forceinline__ void dxt5_alpha_lanes(const uint32_t (&px)[16], uint32_t (&x)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = __byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu;
+}
 
+__device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&x)[8]) {
   // ---- statistics
   uint32_t fk[8], gk[8], zeros255 = 0, not255 = 0;
 #pragma unroll
@@ -428,11 +474,48 @@ __device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&px)[16
 }
 
 // Part 2: the sixteen 3-bit indices for endpoints a0 | a1 << 8 (ComputeAlphaBits).  Returns the 8 output bytes.
-__device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&px)[16], uint32_t endpoints, const uint4 *table) {
+// ICB_DXT5_PLAIN8: 1 = warps whose 32 blocks are all in 8-alpha mode with eight distinct candidates (a0 - a1 >= 7: every
+// block of an image with varied alpha) take a form of the walk whose index changes are compile-time constants; 0 = always
+// the table-driven walk.  A/B knob.
+#ifndef ICB_DXT5_PLAIN8
+#define ICB_DXT5_PLAIN8 1
+#endif
+
+template <bool kFullWarp = false>
+__device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&x)[8], uint32_t endpoints, const uint4 *table) {
   const uint32_t a0 = endpoints & 255u, a1 = endpoints >> 8;
-  uint32_t x[8];
+#if ICB_DXT5_PLAIN8
+  // Usual case, decided once per warp (uniform branch): 8-alpha mode and no two candidates equal.  Ascending from a1 the
+  // line then carries the indices 1,7,6,5,4,3,2,0 -- start 1, index changes +6, -1 x5, -2 (tools/gen_dxt5_alpha_table.py
+  // derives them; tests/test_host_math.py checks that every table entry with D >= 7 says the same) -- so only the seven
+  // thresholds come from the table (two of the entry's four 16-byte words), the five -1 crossings are summed with two
+  // three-input adds before they meet the accumulator, and the field position of a pixel pair is part of the immediate
+  // multiplier: 13 instructions per pixel pair instead of 15.5, no 6-alpha patch-up, no step words.
+  if (__all_sync(kFullWarp ? 0xffffffffu : __activemask(), a0 >= a1 + 7u)) {
+    const uint4 *e = table + 4u * (256u + a0 - a1);
+    const uint4 e0 = e[0], e1 = e[1];
+    const uint32_t minus_a0 = ((0u - a0) & 0xffffu) * 0x10001u;
+    uint32_t acc_a = 0x02490249u, acc_b = 0x02490249u;  // index 1 in four 3-bit fields of both lanes
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = __byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu;
+    for (int p = 0; p < 8; ++p) {
+      const uint32_t d = __vadd2(x[p], minus_a0);  // alpha - a0, two's complement per lane
+      const uint32_t t0 = __viaddmin_s16x2_relu(d, e0.x, 0x00010001u), t1 = __viaddmin_s16x2_relu(d, e0.y, 0x00010001u),
+                     t2 = __viaddmin_s16x2_relu(d, e0.z, 0x00010001u), t3 = __viaddmin_s16x2_relu(d, e0.w, 0x00010001u),
+                     t4 = __viaddmin_s16x2_relu(d, e1.x, 0x00010001u), t5 = __viaddmin_s16x2_relu(d, e1.y, 0x00010001u),
+                     t6 = __viaddmin_s16x2_relu(d, e1.z, 0x00010001u);
+      const uint32_t ones = t1 + t2 + t3 + t4 + t5;  // crossings that lower the index by one
+      const uint32_t f = 1u << (3 * (p & 3));        // this pair's field in both lanes
+      uint32_t &acc = p < 4 ? acc_a : acc_b;
+      // (modulo 2^32; the finished fields are indices 0..7, so intermediate borrows between fields cancel)
+      acc += t0 * (6u * f);
+      acc -= ones * f;
+      acc -= t6 * (2u * f);
+    }
+    const uint32_t word0 = a0 | (a1 << 8) | ((acc_a & 0xfffu) << 16) | (acc_b << 28);
+    const uint32_t word1 = ((acc_b & 0xfffu) >> 4) | ((acc_a >> 16) << 8) | ((acc_b >> 16) << 20);
+    return make_uint2(word0, word1);
+  }
+#endif
 
   // ---- crossings for this (mode, |a0 - a1|)
   const bool six = a0 <= a1;  // 6-alpha mode: candidates 0 and 255 are explicit
@@ -478,12 +561,22 @@ __device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&px)[16], ui
   return make_uint2(word0, word1);
 }
 
-__device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], bool one_pixel, const uint4 *table) {
-  if (one_pixel) {  // window entirely outside the image: both endpoints = that alpha, all indices 0
-    const uint32_t a = px[0] >> 24;
+template <bool kFullWarp = false>
+__device__ __forceinline__ uint2 dxt5_encode_alpha_lanes(const uint32_t (&x)[8], bool one_pixel, const uint4 *table) {
+  // A window entirely outside the image (generic driver only): both endpoints = that alpha, all indices 0.  It still goes
+  // through the search below, whose warp vote every lane must reach.
+  const uint2 r = dxt5_alpha_indices<kFullWarp>(x, dxt5_alpha_endpoints(x), table);
+  if (one_pixel) {
+    const uint32_t a = x[0] & 255u;
     return make_uint2(a | (a << 8), 0u);
   }
-  return dxt5_alpha_indices(px, dxt5_alpha_endpoints(px), table);
+  return r;
+}
+template <bool kFullWarp = false>
+__device__ __forceinline__ uint2 dxt5_encode_alpha(const uint32_t (&px)[16], bool one_pixel, const uint4 *table) {
+  uint32_t x[8];
+  dxt5_alpha_lanes(px, x);
+  return dxt5_encode_alpha_lanes<kFullWarp>(x, one_pixel, table);
 }
 
 }  // namespace icb

@@ -138,8 +138,8 @@ int launch_generic(const Encode4x4Params &p, int sm_count, cudaStream_t stream) 
   return ICB_OK;
 }
 
-template <int kCodec, int kNcomp>
-int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
+template <int kCodec, int kNcomp, bool kSwapRb>
+int launch_tma_typed(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   using Shape = icb::TileShape<kCodec, kNcomp>;
   if (static_cast<uint64_t>(p.grid_cols) * icb::CodecTraits<kCodec>::kBlockBytes > 0xffffffffull)
     return fail(ICB_ERR_INVALID, "image too wide");
@@ -156,8 +156,10 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ICB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
 
-  // Driver and ring depth.  DXT5 runs the producer-less ring kernel with two stages (four CTAs per SM, see
-  // block4x4_kernels.cuh); DXT1 and ETC1 run the producer-warp kernel with 3 or 4 stages, whichever gives the most
+  // Driver and ring depth.  DXT5 and DXT1 from four-byte pixels run the producer-less ring kernel with two stages (see
+  // block4x4_kernels.cuh; for DXT1 from RGBA8 it took over from the producer-warp kernel once the integer-lane index
+  // search had shortened the encoder: 48.8-49.1 us against 50.9-51.2 at 8192^2, profiles/r02b_driver_ab.txt); DXT1 from
+  // RGB888 (43.0-44.8 against 46.6) and ETC1 run the producer-warp kernel with 3 or 4 stages, whichever gives the most
   // resident CTAs (ties -> deeper ring).  ICB_DRIVER=ring|producer and ICB_TMA_STAGES=2|3|4 override for experiments.
   struct Config {
     void (*kernel)(const CUtensorMap, const Encode4x4Params, uint32_t, uint32_t);
@@ -169,18 +171,18 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   int dev = 0;
   ICB_CUDA(cudaGetDevice(&dev));
   if (chosen[dev].kernel == nullptr) {
-    constexpr size_t kStage = Shape::kBytes + 16;  // tile + its barrier / counter words
+    constexpr size_t kStage = Shape::kBytes + 24;  // tile + its barrier / counter words + its output origin
     constexpr size_t kTable = 0;  // (round 1 kept DXT5's crossing table behind the ring; it is read through L1 now)
     const char *driver = getenv("ICB_DRIVER"), *force = getenv("ICB_TMA_STAGES");
-    const bool ring = driver ? strcmp(driver, "ring") == 0 : kCodec == icb::kCodecDxt5;
+    const bool ring = driver ? strcmp(driver, "ring") == 0 : (kCodec == icb::kCodecDxt5 || (kCodec == icb::kCodecDxt1 && kNcomp == 4));
     Config cand[3];
     int n = 0;
     if (ring) {
-      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 2>, 2 * kStage, 0, Shape::kConsumerThreads};
-      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 3>, 3 * kStage, 0, Shape::kConsumerThreads};
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 2, kSwapRb>, 2 * kStage, 0, Shape::kConsumerThreads};
+      cand[n++] = {icb::encode4x4_ring_kernel<kCodec, kNcomp, 3, kSwapRb>, 3 * kStage, 0, Shape::kConsumerThreads};
     } else {
-      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 4>, 4 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
-      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3>, 3 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 4, kSwapRb>, 4 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
+      cand[n++] = {icb::encode4x4_tma_kernel<kCodec, kNcomp, 3, kSwapRb>, 3 * kStage + kTable, 0, Shape::kConsumerThreads + 32};
     }
     int best = -1;
     for (int c = 0; c < n; ++c) {
@@ -224,6 +226,13 @@ int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
   ICB_CUDA(cudaLaunchKernelEx(&launch, cfg.kernel, map, p, tiles_x, num_tiles));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ICB_OK;
+}
+
+// The red/blue exchange of kBGR / kBGRA sources is a template parameter of the tile kernels (ETC1 ignores it).
+template <int kCodec, int kNcomp>
+int launch_tma(const Encode4x4Params &p, int sm_count, cudaStream_t stream) {
+  if (kCodec != icb::kCodecEtc1 && p.swap_rb) return launch_tma_typed<kCodec, kNcomp, kCodec != icb::kCodecEtc1>(p, sm_count, stream);
+  return launch_tma_typed<kCodec, kNcomp, false>(p, sm_count, stream);
 }
 
 template <int kCodec, int kNcomp>

@@ -30,18 +30,63 @@ def direct_first_min(cands, l):
 
 
 def line_search(cands, l, i):
-    """The crossing-point formulation used in dxt_encode.cuh, in integers."""
-    keys = sorted(16 * L + c for c, L in enumerate(cands))
-    rep, acc, v = keys[0], keys[0] & 3, 16 * l + i
+    """The crossing-point formulation used in dxt_encode.cuh (general path), in integers: keys 8*L + c for the
+    candidates, 8*l + (lane index < 8) for the pixel."""
+    keys = sorted(8 * L + c for c, L in enumerate(cands))
+    rep, acc, v = keys[0], keys[0] & 3, 8 * l + (i & 7)
     for b in keys[1:]:
         same = (b - rep) < 4
         cb, cr = b & 3, rep & 3
-        h = ((rep + b + (16 if cb < cr else 32)) >> 1) & ~15
+        h = ((rep + b + (8 if cb < cr else 16)) >> 1) & ~7
         if not same:
             if v >= h:
                 acc += (cb - cr) & 3
             rep = b
     return acc & 3
+
+
+def monotone_search(cands, l, i):
+    """The usual-case form (dxt_encode.cuh, all_regular): candidates (L0, L2, L3, L1) strictly ascending along the line,
+    three crossings with index changes +2, +1, -2 on signed 16-bit lanes."""
+    a0, a1, a2, a3 = (8 * L for L in (cands[0], cands[2], cands[3], cands[1]))
+    h1 = ((a0 + a1 + 16) >> 1) & ~7
+    h2 = ((a1 + a2 + 16) >> 1) & ~7
+    h3 = ((a2 + a3 + 8) >> 1) & ~7
+    key = 8 * l + (i & 7)
+    assert key < 1 << 15
+    t = [max(min(key + 1 - h, 1), 0) for h in (h1, h2, h3)]
+    return 2 * t[0] + t[1] - 2 * t[2]
+
+
+def test_monotone_search_equals_first_strict_minimum():
+    import random
+    rng = random.Random(11)
+    for _ in range(60000):
+        L0 = rng.randint(0, 3300)
+        L = sorted({L0, L0 + rng.randint(1, 40), L0 + rng.randint(1, 900), rng.randint(L0, 3315)})
+        if len(L) < 4:
+            continue
+        cands = [L[0], L[3], L[1], L[2]]  # reference order: base0, base1, interpolant next to base0, next to base1
+        l = rng.randint(max(0, L[0] - 3), min(3315, L[3] + 3))
+        assert monotone_search(cands, l, rng.randint(0, 15)) == direct_first_min(cands, l), (cands, l)
+
+
+def test_dxt5_plain8_steps_are_constants():
+    """dxt5_alpha_indices' warp-uniform form hard-codes what the crossing table says for every 8-alpha entry with
+    eight distinct candidates (D = a0 - a1 >= 7): start index 1, index changes +6, -1, -1, -1, -1, -1, -2."""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "image_compression_b200", "csrc", "dxt5_alpha_table.inc")
+    rows = {}
+    for line in open(path):
+        m = re.match(r"/\*\s*(\d+)\*/ (.*),$", line.strip())
+        if m:
+            rows[int(m.group(1))] = [int(x.rstrip("u"), 16) for x in m.group(2).split(", ")]
+    assert len(rows) == 512
+    for D in range(7, 256):
+        e = rows[256 + D]
+        steps = [v - (1 << 32) if v & 0x80000000 else v for v in e[8:15]]
+        assert steps == [6, -1, -1, -1, -1, -1, -2] and e[7] == 1, D
 
 
 def test_line_search_equals_first_strict_minimum():
