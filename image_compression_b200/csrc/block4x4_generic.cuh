@@ -12,11 +12,6 @@
 
 namespace icb {
 
-// DXT5: 1 = extract the alphas before the colour half (register pressure); A/B knob.
-#ifndef ICB_DXT5_ALPHA_LANES_FIRST
-#define ICB_DXT5_ALPHA_LANES_FIRST 0
-#endif
-
 enum Codec4x4 : int { kCodecDxt1 = 0, kCodecDxt5 = 1, kCodecEtc1 = 2 };
 
 struct Encode4x4Params {
@@ -76,22 +71,10 @@ __device__ __forceinline__ void encode_and_store(const uint32_t (&px)[16], Fetch
     // warp doubled the kernel time, 90 -> 189 us; the row loads hit L1 99 % of the time anyway.  Also tried: half of the
     // CTA's warps running the alpha half BEFORE the colour half, to stagger the integer-heavy and FP32-heavy phases
     // across a scheduler's warps -- 88 -> 104 us, the late release of the staged pixels starves the two-stage ring.)
-#if ICB_DXT5_ALPHA_LANES_FIRST
-    // The alphas leave the pixel words BEFORE the colour half: it then keeps eight lane-pair registers alive for the
-    // alpha half instead of the sixteen pixel words.  (The empty asm keeps the compiler from sinking the extraction
-    // back below the colour half: volatile asm statements -- the shared loads and the release -- keep their order.)
-    uint32_t x[8];
-    dxt5_alpha_lanes(px, x);
-#ifndef ICB_HOST_EMULATION
-#pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("" : "+r"(x[i]));
-#endif
-    const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch, release);
-    const uint2 a = dxt5_encode_alpha_lanes<kFullWarp>(x, one_pixel, alpha_table);
-#else
+    // (Tried in round 2, second half: extracting the eight alpha lane pairs BEFORE the colour half, so that it keeps
+    // eight registers alive instead of the sixteen pixel words -- 83.4 against 82.6 us, with or without a fifth CTA.)
     const uint2 c = dxt1_encode_block<kFullWarp>(px, swap_rb != 0, true, fetch, release);
     const uint2 a = dxt5_encode_alpha<kFullWarp>(px, one_pixel, alpha_table);
-#endif
     *reinterpret_cast<uint4 *>(out) = make_uint4(a.x, a.y, c.x, c.y);
   } else {
     release();  // every pixel is already in registers

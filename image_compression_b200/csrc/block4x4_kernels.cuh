@@ -103,11 +103,6 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 #ifndef ICB_DXT1_TILE_BLOCKS_Y
 #define ICB_DXT1_TILE_BLOCKS_Y 8
 #endif
-// Producer-warp kernel: 1 = consumers hand a ring slot back from inside the encoder (after the last read of the staged
-// pixels) instead of after the block is stored.  A/B knob.
-#ifndef ICB_TMA_EARLY_RELEASE
-#define ICB_TMA_EARLY_RELEASE 0
-#endif
 template <int kCodec>
 constexpr int tile_blocks_y() { return kCodec == kCodecDxt1 ? ICB_DXT1_TILE_BLOCKS_Y : 4; }
 
@@ -261,12 +256,6 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
       };
       mbar_wait(full_s + 8 * stage, phase);
       uint8_t *out = out_origin + lds_u64(origin_s + 8 * stage);
-      // Hands the slot back to the producer: either from inside the encoder, as soon as it has read its last pixel
-      // from the tile (ICB_TMA_EARLY_RELEASE), or after the block has been stored.
-      auto release = [&]() {
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
-      };
 
       if constexpr (kCodec == kCodecDxt1 && kNcomp == 3) {
         // RGB888 -> DXT1 never needs the unpacked pixels: luminance keys come straight from the row words
@@ -277,11 +266,7 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
           rows[y][1] = lds_u32(win + y * kRowBytes + 4);
           rows[y][2] = lds_u32(win + y * kRowBytes + 8);
         }
-#if ICB_TMA_EARLY_RELEASE
-        *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch, release);
-#else
         *reinterpret_cast<uint2 *>(out) = dxt1_encode_rgb888_rows<true>(rows, swap_rb, false, fetch);
-#endif
       } else {
         uint32_t px[16];
 #pragma unroll
@@ -298,15 +283,12 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
             px[4 * y + 3] = w2 >> 8;
           }
         }
-#if ICB_TMA_EARLY_RELEASE
-        encode_and_store<kCodec, true>(px, fetch, false, swap_rb ? 1 : 0, p.etc_strategy, alpha_table, out, release);
-#else
         encode_and_store<kCodec, true>(px, fetch, false, swap_rb ? 1 : 0, p.etc_strategy, alpha_table, out);
-#endif
       }
-#if !ICB_TMA_EARLY_RELEASE
-      release();
-#endif
+      // Hands the slot back to the producer.  (Handing it back from inside the encoder, right after its last read of the
+      // staged pixels, measured the same: 43.6 against 43.0-44.8 us for RGB888, 51.6 against 50.9 for RGBA8.)
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty_s + 8 * stage);
       tile += gridDim.x;
       if constexpr (kUnroll == 1) {
         if (++rt_stage == kTmaStages) {
@@ -324,26 +306,42 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads + 
 // ---------------------------------------------------------------------------------------------------------
 //
 // Same tiles, ring and consumer code as encode4x4_tma_kernel, but nobody polls for free ring slots: every warp
-// counts itself off a per-stage counter as soon as it has read its last pixel from a tile (one shared-memory atomic
-// per warp per tile, issued from inside the encoder through the `release` hook), and the warp that counts last
-// refills the slot on the spot -- expect_tx + one TMA load of tile (current + stages * grid).  Dropping the producer
-// warp frees its register share (256 instead of 288 threads per CTA: 64 registers per thread at four CTAs per SM),
-// which is what DXT5 needs: with the producer warp it is limited to three CTAs per SM (72 registers), here it runs
-// four, with a two-stage ring (early release makes two stages enough) and its crossing table read through L1.
-// Measured on B200 (8192^2): DXT5 103.5 -> 94.2 us.  DXT1 does not gain (51.6 us with the producer warp, 52.8-54.0
-// here: its polling warp fills otherwise idle issue slots and the 56-register code is a little tighter), so the
-// launcher keeps the producer-warp kernel for DXT1 and ETC1 (ICB_DRIVER=ring|producer overrides for experiments).
+// counts itself off a per-stage "released" mbarrier as soon as it has read its last pixel from a tile (one arrive per
+// warp per tile, issued from inside the encoder through the `release` hook), and the warp whose arrival completes the
+// barrier's phase refills the slot on the spot -- expect_tx + one TMA load of tile (current + stages * grid).  Dropping
+// the producer warp frees its register share (256 instead of 288 threads per CTA: 64 registers per thread at four CTAs
+// per SM), which is what DXT5 needs: with the producer warp it is limited to three CTAs per SM (72 registers), here it
+// runs four, with a two-stage ring (early release makes two stages enough) and its crossing table read through L1.
+// Measured on B200 (8192^2): DXT5 103.5 -> 94.2 us in round 1.  DXT1 from RGBA8 moved here in round 2, once the
+// integer-lane index search had shortened its encoder (48.8-49.1 us against 50.9-51.2 with the producer warp; ncu times
+// the kernel alone at 46.6 us, the rest is the gap between back-to-back launches); DXT1 from RGB888 (43.0-44.8 against
+// 46.6) and ETC1 stay with the producer warp (ICB_DRIVER=ring|producer overrides for experiments).
+// Until the second half of round 2 the warps counted off with an acq_rel atomic add on a counter word, which ptxas
+// expands into its warp-aggregated form (vote, FLO, POPC, MEMBAR, ATOMS, SHFL: eighteen instructions in lane 0's path);
+// the mbarrier form is six (DXT5 78.3 -> 77.6 us).
 
-__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t addr, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-  return old;
+// Arrives on an mbarrier and returns the number of arrivals its phase was still waiting for BEFORE this one
+// (mbarrier.pending_count of the state the arrive returns; tools/microbench/mbar_pending.cu prints 4 3 2 1 4 3 2 1 4 for
+// a barrier of four): 1 = this arrival completed the phase.
+__device__ __forceinline__ uint32_t mbar_arrive_pending(uint32_t bar) {
+  uint32_t pending;
+  asm volatile(
+      "{\n"
+      ".reg .b64 st;\n"
+      "mbarrier.arrive.shared::cta.b64 st, [%1];\n"
+      "mbarrier.pending_count.b64 %0, st;\n"
+      "}\n"
+      : "=r"(pending)
+      : "r"(bar)
+      : "memory");
+  return pending;
 }
 
 // Resident CTAs per SM the DXT5 build of the ring kernel is compiled for.  4 = 64 registers (the measured default).
-// Experiment prepared for the next GPU visit (tools/build_variants.sh dxt5x5 "-DICB_DXT5_RING_MIN_CTAS=5"): 5 = 48
-// registers, which ptxas reaches with 8 bytes of spill and 16 more instructions (2040 instead of 2024 static); the
-// launcher's occupancy query then runs 40 warps per SM instead of 32 for a kernel that leaves 25 % of its issue slots empty.
+// 5 = 48 registers: no faster (79.5 against 79.0 us) and, with CUDA 12.9's ptxas, WRONG -- in that build the first
+// statistics key of the alpha half, __vadd2(x0, 0xffffffff), comes out as VIADD.16x2 R8,R4,0x0 / VIADD.16x2 R5,R4,
+// 0xffffffff / PRMT R14,R8,0x7610,R5, i.e. the low lane keeps alpha instead of alpha - 1; the bench's in-run parity
+// flag caught it (profiles/r02b_driver_ab.txt).  Kept as a knob only so that the finding can be reproduced.
 #ifndef ICB_DXT5_RING_MIN_CTAS
 #define ICB_DXT5_RING_MIN_CTAS 4
 #endif
@@ -355,14 +353,14 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
                           uint32_t num_tiles) {
   using Shape = TileShape<kCodec, kNcomp>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), a done-counter (8 bytes), a tile origin (8 bytes)
+  // layout: kTmaStages tiles, then per stage a "full" barrier (8 bytes), a "released" barrier of kWarps arrivals
+  // (8 bytes), a tile origin (8 bytes)
   uint32_t tiles_s;
   asm volatile("mov.u32 %0, %1;" : "=r"(tiles_s) : "r"(smem_u32(smem_raw)));
   // ... then per stage the byte offset of the tile's first block in the output (see encode4x4_tma_kernel)
   const uint32_t full_s = tiles_s + kTmaStages * Shape::kBytes, count_s = full_s + kTmaStages * 8;
   const uint32_t origin_s = count_s + kTmaStages * 8;
   constexpr uint32_t kWarps = Shape::kConsumerThreads / 32;
-  static_assert((kWarps & (kWarps - 1)) == 0, "the done-counter is tested modulo the warp count");
   constexpr uint32_t kBlockBytes = CodecTraits<kCodec>::kBlockBytes;
   constexpr uint32_t kRowBytes = Shape::kRowWords * 4;
   // DXT5's 32 KB crossing table is read from global memory (four 16-byte loads per block, L1-resident): a
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
     asm volatile("prefetch.tensormap [%0];" ::"l"(&src_map) : "memory");
     for (int s = 0; s < kTmaStages; ++s) {
       mbar_init(full_s + 8 * s, 1);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_s + 8 * s), "r"(0u) : "memory");
+      mbar_init(count_s + 8 * s, kWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -423,8 +421,7 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
         }
       };
       // Done with this slot (called by the encoder as soon as it has read its last pixel from the tile): count this
-      // warp off; the last warp to do so refills the slot.  The acq_rel atomic (MEMBAR.CTA + ATOMS) completes this
-      // warp's shared-memory reads before the count and makes every warp's reads happen-before the refill.
+      // warp off; the last warp to do so refills the slot.
       auto release = [&]() {
 #ifdef ICB_RING_SKEW_TEST
         // Test builds only (tools/build_variants.sh skew "-DICB_RING_SKEW_TEST"): some warps hand their slot back
@@ -433,8 +430,12 @@ __global__ void __launch_bounds__(TileShape<kCodec, kNcomp>::kConsumerThreads,
 #endif
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
-          const uint32_t old = atom_add_acq_rel_shared(count_s + 8 * stage, 1u);
-          if ((old & (kWarps - 1)) == kWarps - 1 && tile + refill_stride < num_tiles) load_tile(tile + refill_stride, stage);
+          // The arrive releases this warp's reads of the slot; the warp that completes the phase acquires everybody's
+          // (a wait on the phase it has just completed: passes at once) before it lets TMA overwrite the slot.
+          if (mbar_arrive_pending(count_s + 8 * stage) == 1u && tile + refill_stride < num_tiles) {
+            mbar_wait(count_s + 8 * stage, phase);
+            load_tile(tile + refill_stride, stage);
+          }
         }
         __syncwarp();
       };

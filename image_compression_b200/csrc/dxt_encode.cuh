@@ -126,15 +126,6 @@ __device__ __noinline__ uint64_t dxt_const_colour(uint32_t t, bool always4) {
 // index search's VIADDMNMX.S16x2 needs; half-integer crossing points only need a scale of 2.)
 __device__ __forceinline__ uint32_t dxt_lum_weights(bool swap_rb) { return swap_rb ? 0x00204008u : 0x00084020u; }
 
-// 565 quantisation straight from a packed pixel.  round(v*31/255) == (v*249 + 1024) >> 11 and
-// round(v*63/255) == (v*253 + 512) >> 10 for every 8-bit v (checked exhaustively in tests/test_host_math.py), so
-// one IDP.4A per channel -- weight in the byte that holds the channel, rounding term in the accumulator --
-// replaces byte extraction, multiply and the two-step Blinn rounding.
-__device__ __forceinline__ uint32_t dxt_to_565(uint32_t p, uint32_t w_red, uint32_t w_blue) {
-  const uint32_t xr = __dp4a(p, w_red, 1024u), xg = __dp4a(p, 0x0000fd00u, 512u), xb = __dp4a(p, w_blue, 1024u);
-  return (xr & 0xf800u) | ((xg >> 5) & 0x07e0u) | (xb >> 11);
-}
-
 __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
   const uint32_t lo = min(a, b), hi = max(a, b);
   a = lo;
@@ -152,26 +143,21 @@ __device__ __forceinline__ void sort2(uint32_t &a, uint32_t &b) {
 //     smaller index (that is what "first strict minimum" does with a tie); candidates with equal luminance are
 //     represented by their smallest index;
 //   * a pixel's index is the start index plus the index changes of the crossings it has passed.
-// Keys.  kf[i] = 0x4B000000 + 8*lum(pixel i) + seed(i): produced by the IDP.4A that computes the luminance, with the
-// constant in its accumulator.  The low half is the 16-bit key 8*lum + index-within-lane (< 2^15: also a valid SIGNED
-// lane); read as a float the word is 2^23 + key, exact, which the fp32 form of the search consumes as is.
+// Keys.  kf[i] = 8*lum(pixel i) + (i & 7): produced by the IDP.4A that computes the luminance, with the lane index in
+// its accumulator -- a 16-bit key below 2^15, i.e. also a valid SIGNED lane.  (The rare general path reads a key as the
+// float 2^23 + key: one byte permute with the exponent word.)
 // Pixel pair (k, k+8) shares one register, pixel k in the low lane: the low lane of an accumulator then collects the
 // index bits of pixels 0..7 and the high lane those of pixels 8..15, i.e. the finished 32-bit index word.
 constexpr uint32_t kDxtLumBias = 0x4b000000u;
 constexpr uint32_t kDxtKeyStep = 8u;  // key units per unit of luminance
 
-// Which pixel pairs (bit k = pair (k, k+8)) run the usual-case index search on 16-bit integer lanes -- per pair three
-// VIADDMNMX.S16x2.RELU (integer pipe) + three IMAD with immediate steps (FMA pipe): 3 instructions per pixel -- and
-// which on fp32 -- five FADD/FFMA per pixel, nothing on the integer pipe.  The split balances the two pipes; A/B knob
-// (tools/build_variants.sh), measured values in DESIGN.md section 4.2.
-#ifndef ICB_DXT_INT_PAIRS
-#define ICB_DXT_INT_PAIRS 0xff
-#endif
-constexpr uint32_t kDxtIntPairs = ICB_DXT_INT_PAIRS;
-constexpr __host__ __device__ bool dxt_int_pair(int k) { return ((kDxtIntPairs >> (k & 7)) & 1u) != 0u; }
-// The accumulator of pixel i's key IDP: integer pairs get their lane index for free here; fp32 pairs must not carry
-// one (their band test is symmetric about a midpoint), it is added when the 16-bit keys are packed.
-constexpr __host__ __device__ uint32_t dxt_key_seed(int i) { return kDxtLumBias + (dxt_int_pair(i) ? static_cast<uint32_t>(i & 7) : 0u); }
+// Round 2 measured the alternatives on B200 (profiles/r02b_driver_ab.txt): the same search on fp32 (five FADD/FFMA per
+// pixel, nothing on the integer pipe -- the round-1 form) for all, half or every other pixel pair is slower for every
+// DXT kernel (DXT5 87.4 / 83.9 / 83.9 us against 82.7; RGB888 48.3 / 45.1 / 47.3 against 43.0), and so are forms that move
+// the key packing and the reversed index to the FMA pipe behind an opaque multiplier: these kernels are bound by the
+// NUMBER of instructions issued, not by one pipe.
+// The accumulator of pixel i's key IDP: its lane index (pixel i sits in lane i / 8 of register i % 8).
+constexpr __host__ __device__ uint32_t dxt_key_seed(int i) { return static_cast<uint32_t>(i & 7); }
 
 // A caller that stages pixels in a buffer it wants back early passes `release`; it is called once, right after the
 // two base colours have been re-read through `fetch` (nothing reads the staged pixels after that).
@@ -185,20 +171,23 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // First minimum / first maximum in raster order: 16-bit keys 8*lum + k, pixel k in the low lane and pixel k + 8 in
   // the high lane of register k; the maximum uses the index field reversed (^7) so that ties resolve to the lowest
   // index.  VIMNMX3.U16x2 folds two more registers (four pixels) per instruction.
-  uint32_t pk[8];
+  uint32_t pk[8], xk[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    pk[k] = __byte_perm(kf[k], kf[k + 8], 0x5410);
-    if (!dxt_int_pair(k)) pk[k] += static_cast<uint32_t>(k) * 0x10001u;
+    pk[k] = kf[k + 8] * 65536u + kf[k];  // bare keys < 2^15: one IMAD joins the pair
+    // Index field reversed for the maximum: the field of register k holds exactly k in both lanes, so k ^ 7 = 7 - k is
+    // the addition of 7 - 2k to each lane, and since no lane goes negative (key >= k) the two lane additions are one
+    // 32-bit addition.
+    xk[k] = pk[k] + static_cast<uint32_t>(7 - 2 * k) * 0x10001u;
   }
   uint32_t mn = __vimin3_u16x2(pk[0], pk[1], pk[2]);
   mn = __vimin3_u16x2(mn, pk[3], pk[4]);
   mn = __vimin3_u16x2(mn, pk[5], pk[6]);
   mn = __vminu2(mn, pk[7]);
-  uint32_t mx = __vimax3_u16x2(pk[0] ^ 0x00070007u, pk[1] ^ 0x00070007u, pk[2] ^ 0x00070007u);
-  mx = __vimax3_u16x2(mx, pk[3] ^ 0x00070007u, pk[4] ^ 0x00070007u);
-  mx = __vimax3_u16x2(mx, pk[5] ^ 0x00070007u, pk[6] ^ 0x00070007u);
-  mx = __vmaxu2(mx, pk[7] ^ 0x00070007u);
+  uint32_t mx = __vimax3_u16x2(xk[0], xk[1], xk[2]);
+  mx = __vimax3_u16x2(mx, xk[3], xk[4]);
+  mx = __vimax3_u16x2(mx, xk[5], xk[6]);
+  mx = __vmaxu2(mx, xk[7]);
   // Between the lanes: every pixel of the low lane precedes every pixel of the high lane, so the low lane wins ties
   // of luminance whatever the index fields say.
   const uint32_t mn_lo = mn & 0xffffu, mn_hi = mn >> 16, mx_lo = mx & 0xffffu, mx_hi = mx >> 16;
@@ -208,8 +197,20 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   uint32_t p0 = fetch(imin), p1 = fetch(imax);  // base colours, memory byte order
   release();
   const uint32_t lum0 = kmin & 0xfff8u, lum1 = kmax & 0xfff8u;      // 8 * luminance of p0 / p1: lum0 <= lum1
-  const uint32_t w_red = swap_rb ? 0x00f90000u : 0x000000f9u, w_blue = swap_rb ? 0x000000f9u : 0x00f90000u;
-  const uint32_t q0 = dxt_to_565(p0, w_red, w_blue), q1 = dxt_to_565(p1, w_red, w_blue);
+  // The base colours' channels on lanes: memory bytes 0 and 2 (red and blue, or blue and red when swap_rb) side by side
+  // in the 16-bit lanes of one register, byte 1 (green) alone in another.  Quantisation and interpolation then cost one
+  // multiply-add for two channels, with immediate multipliers -- the per-channel IDP.4A form needed six weight
+  // constants in uniform registers, which ptxas re-materialises for every block.
+  const uint32_t rb0 = p0 & 0x00ff00ffu, rb1 = p1 & 0x00ff00ffu;
+  const uint32_t g0 = __byte_perm(p0, 0u, 0x4441), g1 = __byte_perm(p1, 0u, 0x4441);
+  // 565 quantisation: round(v*31/255) == (v*249 + 1024) >> 11, round(v*63/255) == (v*253 + 512) >> 10 for every 8-bit v
+  // (tests/test_host_math.py); v*249 + 1024 < 2^16, so the two lanes do not meet.
+  const uint32_t x0 = rb0 * 249u + 0x04000400u, x1 = rb1 * 249u + 0x04000400u;
+  const uint32_t y0 = g0 * 253u + 512u, y1 = g1 * 253u + 512u;
+  const uint32_t q0 = swap_rb ? (((x0 >> 16) & 0xf800u) | ((y0 >> 5) & 0x07e0u) | ((x0 >> 11) & 0x1fu))
+                              : ((x0 & 0xf800u) | ((y0 >> 5) & 0x07e0u) | (x0 >> 27));
+  const uint32_t q1 = swap_rb ? (((x1 >> 16) & 0xf800u) | ((y1 >> 5) & 0x07e0u) | ((x1 >> 11) & 0x1fu))
+                              : ((x1 & 0xf800u) | ((y1 >> 5) & 0x07e0u) | (x1 >> 27));
   // Everything up to the warp vote below is computed for constant blocks too (and ignored): the vote has to sit
   // where the warp has not yet diverged on "is this block constant".
   const bool constant = q0 == q1;
@@ -220,16 +221,16 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
   // flips (one XOR at the end) and ties go to the OTHER candidate of the middle pair (one selected constant).
   const bool swapped = q0 < q1;
   uint32_t c0 = max(q0, q1), c1 = min(q0, q1);
-  // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation:
-  // floor((2a+b)/3) = umulhi(2a+b, 683 << 21) for 2a+b <= 765.
-  const uint32_t s_red = swap_rb ? 0x00010000u : 0x00000001u, s_blue = swap_rb ? 0x00000001u : 0x00010000u;
-  const uint32_t r0 = __dp4a(p0, s_red, 0u), g0 = __dp4a(p0, 0x00000100u, 0u), b0 = __dp4a(p0, s_blue, 0u);
-  const uint32_t r1 = __dp4a(p1, s_red, 0u), g1 = __dp4a(p1, 0x00000100u, 0u), b1 = __dp4a(p1, s_blue, 0u);
-  constexpr uint32_t kThird = 683u << 21;
-  const uint32_t lum2 = 32u * __umulhi(2u * r0 + r1, kThird) + 64u * __umulhi(2u * g0 + g1, kThird) +
-                        8u * __umulhi(2u * b0 + b1, kThird);    // the interpolant next to p0
-  const uint32_t lum3 = 32u * __umulhi(r0 + 2u * r1, kThird) + 64u * __umulhi(g0 + 2u * g1, kThird) +
-                        8u * __umulhi(b0 + 2u * b1, kThird);    // the interpolant next to p1
+  // Interpolants come from the UNQUANTISED base colours, channel by channel with truncation.  floor(x / 3) =
+  // umulhi(x, 683 << 21) for x <= 765; for the channel in the HIGH lane of a sum word s = lo + 65536 * hi the shift is
+  // part of the multiplier: umulhi(s, 683 << 5) = floor(hi * 683 / 2048 + lo * 683 / 2^27) = floor(hi / 3), because the
+  // two error terms add up to less than 0.13 (tests/test_host_math.py runs every lo, hi).
+  constexpr uint32_t kThird = 683u << 21, kThirdOfHighLane = 683u << 5;
+  const uint32_t s_rb = 2u * rb0 + rb1, s_g = 2u * g0 + g1;    // the interpolant next to p0
+  const uint32_t t_rb = rb0 + 2u * rb1, t_g = g0 + 2u * g1;    // the interpolant next to p1
+  const uint32_t w_lo = swap_rb ? 8u : 32u, w_hi = swap_rb ? 32u : 8u;  // 8 * (4, 8, 1) on (red, green, blue)
+  const uint32_t lum2 = w_lo * __umulhi(s_rb & 0xffffu, kThird) + 64u * __umulhi(s_g, kThird) + w_hi * __umulhi(s_rb, kThirdOfHighLane);
+  const uint32_t lum3 = w_lo * __umulhi(t_rb & 0xffffu, kThird) + 64u * __umulhi(t_g, kThird) + w_hi * __umulhi(t_rb, kThirdOfHighLane);
   // Usual case, decided once per warp so the branch never diverges: the interpolants lie strictly between the
   // base colours, i.e. the candidates are ordered along the luminance line with no two equal.  Then the crossing
   // order, the tie rules and the index changes are fixed and only the three midpoints have to be computed.
@@ -287,45 +288,19 @@ __device__ __forceinline__ uint2 dxt1_encode_from_keys(const uint32_t (&kf)[16],
       // (index 3 rising, 2 falling) it flips with the band's far edge, without the first one with its near edge.
       if (dead1 || dead2) h2 = dead2 ? h3 : h1;
     }
-    // Integer pairs: t = relu(min(key + (1 - h), 1)) is 1 once the pixel has passed crossing h -- the key's index field
-    // (< 8) cannot carry it over a multiple of 8 -- for both pixels of the pair in one VIADDMNMX.S16x2.RELU, and
-    // t * (step << 2k) drops the index change at the pair's bit position of both lanes in one IMAD with an immediate
-    // multiplier.  All arithmetic is modulo 2^32 and the final fields are indices 0..3, so the order of the additions
-    // does not matter.
-    const uint32_t m1 = 1u - h1, m2 = 1u - h2, m3 = 1u - h3;
-    const uint32_t n1 = __byte_perm(m1, m1, 0x1010), n2 = __byte_perm(m2, m2, 0x1010), n3 = __byte_perm(m3, m3, 0x1010);
+    // t = relu(min(key + (1 - h), 1)) is 1 once the pixel has passed crossing h -- the key's index field (< 8) cannot
+    // carry it over a multiple of 8 -- for both pixels of the pair in one VIADDMNMX.S16x2.RELU, and t * (step << 2k)
+    // drops the index change at the pair's bit position of both lanes in one IMAD with an immediate multiplier.  All
+    // arithmetic is modulo 2^32 and the final fields are indices 0..3, so the order of the additions does not matter.
+    // 1 - h in both lanes as ONE multiply-add: (65537 - h) * 65537 = 0x00020001 - h * 65537 (mod 2^32), and 65537 - h fits
+    // a lane because every crossing is at least 8 (h1, h3 round up from a sum >= 8; h2 is replaced when its candidates are dead).
+    const uint32_t n1 = h1 * 0xfffeffffu + 0x00020001u, n2 = h2 * 0xfffeffffu + 0x00020001u, n3 = h3 * 0xfffeffffu + 0x00020001u;
     uint32_t acc = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (!dxt_int_pair(k)) continue;
       acc += __viaddmin_s16x2_relu(pk[k], n1, 0x00010001u) * (2u << (2 * k));
       acc += __viaddmin_s16x2_relu(pk[k], n2, 0x00010001u) * (1u << (2 * k));
       acc -= __viaddmin_s16x2_relu(pk[k], n3, 0x00010001u) * (2u << (2 * k));
-    }
-    if constexpr (kDxtIntPairs != 0xffu) {
-      // fp32 pairs: the high index bit is set exactly between the outer crossings and the low bit flips at the middle one:
-      //   bit1 = [h1 <= v < h3] = sat(R + 1 - |v - mid|)      mid, R = centre and half-width of [h1, h3 - 8]
-      //   bit0 = [v >= h2] = sat(v - h2 + 1)
-      // and 2*bit1 + bit0 is added into the mantissa of 2^23 at the pixel's position: five exact FADD/FFMA per pixel.
-      const float mid = __uint_as_float(kDxtLumBias + ((h1 + h3 - 8u) >> 1));
-      // R + 1 = (h3 - h1 - 8) / 2 + 1; an empty band (h1 == h3, possible only with dead candidates) gives -3: never set
-      const float rp1 = __uint_as_float(kDxtLumBias + ((h3 - h1) >> 1)) - 8388611.0f;
-      const float k2 = __uint_as_float(0xcb000000u + h2 - 1u);   // -(2^23 + h2 - 1): v + k2 >= 1 iff 8*l >= h2
-      float acc_lo = 8388608.0f, acc_hi = 8388608.0f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (dxt_int_pair(i)) continue;
-        const float v = __uint_as_float(kf[i]);
-        const float u = __saturatef(rp1 - fabsf(v - mid));
-        const float t = __saturatef(v + k2);
-        const float z = fmaf(u, 2.0f, t);
-        const float scale = static_cast<float>(1u << (2 * (i & 7)));
-        if (i < 8)
-          acc_lo = fmaf(z, scale, acc_lo);
-        else
-          acc_hi = fmaf(z, scale, acc_hi);
-      }
-      acc += __byte_perm(__float_as_uint(acc_lo), __float_as_uint(acc_hi), 0x5410);
     }
     bits = acc ^ (swapped ? 0x55555555u : 0u);
   } else {
@@ -474,17 +449,9 @@ __device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&x)[8])
 }
 
 // Part 2: the sixteen 3-bit indices for endpoints a0 | a1 << 8 (ComputeAlphaBits).  Returns the 8 output bytes.
-// ICB_DXT5_PLAIN8: 1 = warps whose 32 blocks are all in 8-alpha mode with eight distinct candidates (a0 - a1 >= 7: every
-// block of an image with varied alpha) take a form of the walk whose index changes are compile-time constants; 0 = always
-// the table-driven walk.  A/B knob.
-#ifndef ICB_DXT5_PLAIN8
-#define ICB_DXT5_PLAIN8 1
-#endif
-
 template <bool kFullWarp = false>
 __device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&x)[8], uint32_t endpoints, const uint4 *table) {
   const uint32_t a0 = endpoints & 255u, a1 = endpoints >> 8;
-#if ICB_DXT5_PLAIN8
   // Usual case, decided once per warp (uniform branch): 8-alpha mode and no two candidates equal.  Ascending from a1 the
   // line then carries the indices 1,7,6,5,4,3,2,0 -- start 1, index changes +6, -1 x5, -2 (tools/gen_dxt5_alpha_table.py
   // derives them; tests/test_host_math.py checks that every table entry with D >= 7 says the same) -- so only the seven
@@ -494,7 +461,8 @@ __device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&x)[8], uint
   if (__all_sync(kFullWarp ? 0xffffffffu : __activemask(), a0 >= a1 + 7u)) {
     const uint4 *e = table + 4u * (256u + a0 - a1);
     const uint4 e0 = e[0], e1 = e[1];
-    const uint32_t minus_a0 = ((0u - a0) & 0xffffu) * 0x10001u;
+    // -a0 in both lanes as one multiply-add: (65536 - a0) * 65537 = 0x00010000 - a0 * 65537 (mod 2^32); a0 >= 7 here
+    const uint32_t minus_a0 = a0 * 0xfffeffffu + 0x00010000u;
     uint32_t acc_a = 0x02490249u, acc_b = 0x02490249u;  // index 1 in four 3-bit fields of both lanes
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -515,7 +483,6 @@ __device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&x)[8], uint
     const uint32_t word1 = ((acc_b & 0xfffu) >> 4) | ((acc_a >> 16) << 8) | ((acc_b >> 16) << 20);
     return make_uint2(word0, word1);
   }
-#endif
 
   // ---- crossings for this (mode, |a0 - a1|)
   const bool six = a0 <= a1;  // 6-alpha mode: candidates 0 and 255 are explicit

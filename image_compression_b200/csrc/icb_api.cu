@@ -1577,8 +1577,8 @@ int icb_root_share_permille(int codec, int format_components, int n) {
   double t_kernel_per_out_byte;
   const double link_gbs = n == 2 ? 510.0 : (n == 3 ? 680.0 : 720.0), t_link_per_out_byte = 1.0 / (link_gbs * 1e9);
   switch (codec) {
-    case ICB_CODEC_DXT1: t_kernel_per_out_byte = (format_components == 4 ? 51.5e-6 : 53.0e-6) / 33554432.0; break;
-    case ICB_CODEC_DXT5: t_kernel_per_out_byte = 90e-6 / 67108864.0; break;
+    case ICB_CODEC_DXT1: t_kernel_per_out_byte = (format_components == 4 ? 49.0e-6 : 43.5e-6) / 33554432.0; break;
+    case ICB_CODEC_DXT5: t_kernel_per_out_byte = 78e-6 / 67108864.0; break;
     case ICB_CODEC_ETC1: t_kernel_per_out_byte = 156e-6 / 8388608.0; break;
     default: return -1;
   }

@@ -20,6 +20,20 @@ def test_division_by_three_forms():
         assert (x * (683 << 21)) >> 32 == x // 3
 
 
+def test_third_of_the_high_lane():
+    """dxt_encode.cuh: floor(hi / 3) of a word lo + 65536 * hi, lanes <= 765, as one multiply-high."""
+    for hi in range(766):
+        for lo in (0, 1, 2, 255, 509, 510, 763, 764, 765):
+            assert (((lo + 65536 * hi) * (683 << 5)) >> 32) == hi // 3, (lo, hi)
+    for lo in range(766):
+        for hi in (0, 1, 2, 3, 254, 255, 511, 764, 765):
+            assert (((lo + 65536 * hi) * (683 << 5)) >> 32) == hi // 3, (lo, hi)
+
+
+def test_quantiser_on_lanes_does_not_carry():
+    assert 255 * 249 + 1024 < 1 << 16 and 255 * 253 + 512 < 1 << 16
+
+
 def direct_first_min(cands, l):
     best, pick = None, 0
     for c, L in enumerate(cands):
