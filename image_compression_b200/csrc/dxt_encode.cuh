@@ -410,13 +410,25 @@ __device__ __forceinline__ void dxt5_alpha_lanes(const uint32_t (&px)[16], uint3
   for (int i = 0; i < 8; ++i) x[i] = __byte_perm(px[i], px[i + 8], 0x7733) & 0x00ff00ffu;
 }
 
+// The two lane-wise addends of the statistics keys live in constant memory, NOT in the instruction stream: with them as
+// immediates, CUDA 12.9's ptxas miscompiles one of the eight additions in some instantiations (the 48-register ring
+// build, the generic DXT5 kernel: "VIADD.16x2 R17,R4,0x0 / VIADD.16x2 R15,R4,0xff01ff01 / PRMT R19,R17,0x7610,R15" --
+// the low lane of one key loses its addend, and the block's alpha endpoint is off whenever that pixel holds the
+// extreme; found by the bench's parity flag and the GPU suite, profiles/r02b_driver_ab.txt).  Constant memory is
+// writable from the host, so ptxas cannot split these values into lanes.
+#ifdef ICB_HOST_EMULATION
+constexpr uint32_t c_dxt5_minus_one_lanes = 0xffffffffu, c_dxt5_plus_ff01_lanes = 0xff01ff01u;
+#else
+__constant__ uint32_t c_dxt5_minus_one_lanes = 0xffffffffu, c_dxt5_plus_ff01_lanes = 0xff01ff01u;
+#endif
+
 __device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&x)[8]) {
   // ---- statistics
   uint32_t fk[8], gk[8], zeros255 = 0, not255 = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    fk[i] = __vadd2(x[i], 0xffffffffu);              // a - 1; a == 0 -> 0xffff
-    gk[i] = __vadd2(x[i], 0xff01ff01u);              // a + 0xff01; a == 255 -> 0
+    fk[i] = __vadd2(x[i], c_dxt5_minus_one_lanes);   // a - 1; a == 0 -> 0xffff
+    gk[i] = __vadd2(x[i], c_dxt5_plus_ff01_lanes);   // a + 0xff01; a == 255 -> 0
     zeros255 = __dp4a(fk[i], 0x01000100u, zeros255);  // += high bytes: 255 per zero alpha
     not255 = __dp4a(gk[i], 0x01000100u, not255);      // += 255 per alpha that is not 255
   }

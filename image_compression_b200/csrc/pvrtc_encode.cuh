@@ -23,28 +23,24 @@ __device__ __forceinline__ uint32_t pv_l1(uint32_t p, uint32_t q) { return __vsa
 // pipe 10 %); a multiplier it cannot see stays an IMAD with a constant-bank operand.
 __device__ __forceinline__ uint32_t pv_key(uint32_t value, uint32_t key_scale, uint32_t index) { return value * key_scale + index; }
 
-// Keep the top n bits of an 8-bit value and replicate them downwards (ApplyBitDepthReduction).
-__device__ __forceinline__ uint32_t pv_keep_bits(uint32_t v, uint32_t n) {
-  const uint32_t kept = v & ((0xffu << (8u - n)) & 0xffu);
-  uint32_t out = kept | (kept >> n);
-  if (n <= 3u) out |= kept >> (2u * n);
-  return out;
-}
-
-// Colour as it will decode after being stored as the block's A (is_b=false) or B (is_b=true) colour.
+// Colour as it will decode after being stored as the block's A (is_b=false) or B (is_b=true) colour
+// (ApplyColorChannelReduction: opaque colours keep 5,5,4|5 bits of r,g,b; translucent ones 4,4,3|4 and 3 bits of alpha;
+// a channel keeps its top n bits and replicates them downwards, ApplyBitDepthReduction).  All four channels at once on the packed word: the kept bits are
+// one mask, and "replicate downwards" is the masked word shifted by the channel's bit count (a channel's shifted bits
+// are masked so that they do not run into its lower neighbour).  tests/test_host_math.py compares with the per-channel
+// form for every value of every channel.
 __device__ __forceinline__ uint32_t pv_reduce_colour(uint32_t c, bool is_b) {
-  uint32_t r = c & 255u, g = (c >> 8) & 255u, b = (c >> 16) & 255u, a = c >> 24;
-  if (a == 255u) {
-    r = pv_keep_bits(r, 5);
-    g = pv_keep_bits(g, 5);
-    b = pv_keep_bits(b, is_b ? 5 : 4);
+  uint32_t opaque, translucent;
+  if (is_b) {
+    opaque = (c & 0xfff8f8f8u) | ((c >> 5) & 0x00070707u);
+    const uint32_t t = c & 0xe0f0f0f0u;
+    translucent = t | ((t >> 4) & 0x000f0f0fu) | ((t >> 3) & 0x1c000000u) | ((t >> 6) & 0x03000000u);
   } else {
-    r = pv_keep_bits(r, 4);
-    g = pv_keep_bits(g, 4);
-    b = pv_keep_bits(b, is_b ? 4 : 3);
-    a = pv_keep_bits(a, 3);
+    opaque = (c & 0xfff0f8f8u) | ((c >> 5) & 0x00000707u) | ((c >> 4) & 0x000f0000u);
+    const uint32_t t = c & 0xe0e0f0f0u;
+    translucent = t | ((t >> 4) & 0x00000f0fu) | ((t >> 3) & 0x1c1c0000u) | ((t >> 6) & 0x03030000u);
   }
-  return r | (g << 8) | (b << 16) | (a << 24);
+  return c >= 0xff000000u ? opaque : translucent;
 }
 
 // The block's two extreme colours (GetExtremesFast + ApplyColorChannelReduction).  px[j], j = 8*y + x, are the
@@ -176,6 +172,10 @@ __device__ __forceinline__ uint32_t pv_high_bits(uint32_t row) {
   return (x | (x >> 4)) & 0xffu;
 }
 
+__device__ __noinline__ uint32_t pv_one_bpp_bits(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  return pv_high_bits(r0) | (pv_high_bits(r1) << 8) | (pv_high_bits(r2) << 16) | (pv_high_bits(r3) << 24);
+}
+
 // Modulation mode + data word for one block (CalculateBlockModulationMode / Data).  row[y], y = 0..3: the block's
 // rows, eight 2-bit values each (pixel x in bits 2x..2x+1); row[4]: the wrapped row below; right[y]: the 2-bit value
 // of the wrapped pixel to the right of row y.  Works on whole rows: value differences are summed four at a time
@@ -208,17 +208,15 @@ __device__ __forceinline__ uint32_t pv_pack_modulation(const uint32_t (&row)[5],
   else
     mode = kAverage4;
 
-  uint32_t bits;
-  if (mode == k1Bpp) {  // one bit per pixel: value / 2, raster order
-    bits = pv_high_bits(row[0]) | (pv_high_bits(row[1]) << 8) | (pv_high_bits(row[2]) << 16) | (pv_high_bits(row[3]) << 24);
-  } else {
-    // checkerboard (x ^ y even), two bits each in raster order: even rows keep fields 0,2,4,6, odd rows 1,3,5,7
-    bits = pv_even_fields(row[0]) | (pv_even_fields(row[1] >> 2) << 8) | (pv_even_fields(row[2]) << 16) |
-           (pv_even_fields(row[3] >> 2) << 24);
-    // the low bit of the entries at bit positions 0 and 20 carries the sub-mode instead of data
-    bits = (mode == kAverage4) ? (bits & ~1u) : (bits | 1u);
-    bits = (mode == kVertical) ? (bits | (1u << 20)) : (bits & ~(1u << 20));
-  }
+  // checkerboard (x ^ y even), two bits each in raster order: even rows keep fields 0,2,4,6, odd rows 1,3,5,7
+  uint32_t bits = pv_even_fields(row[0]) | (pv_even_fields(row[1] >> 2) << 8) | (pv_even_fields(row[2]) << 16) |
+                  (pv_even_fields(row[3] >> 2) << 24);
+  // the low bit of the entries at bit positions 0 and 20 carries the sub-mode instead of data
+  bits = (mode == kAverage4) ? (bits & ~1u) : (bits | 1u);
+  bits = (mode == kVertical) ? (bits | (1u << 20)) : (bits & ~(1u << 20));
+  // One bit per pixel (value / 2, raster order) for blocks that are nearly two-level: rare, and as a predicated tail of
+  // this function its 28 instructions were issued for every block -- a call is only taken by the blocks that need it.
+  if (mode == k1Bpp) bits = pv_one_bpp_bits(row[0], row[1], row[2], row[3]);
   *one_bpp = (mode == k1Bpp);
   return bits;
 }

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(128, 8) pvrtc_morph_kernel(const PvrtcParams p
     px[8 * y + 0] = u.x; px[8 * y + 1] = u.y; px[8 * y + 2] = u.z; px[8 * y + 3] = u.w;
     px[8 * y + 4] = v.x; px[8 * y + 5] = v.y; px[8 * y + 6] = v.z; px[8 * y + 7] = v.w;
   }
-  auto fetch = [&](uint32_t j) { return origin[static_cast<size_t>(j >> 3) * p.width + (j & 7u)]; };
+  // (32-bit offset: a block's four rows span less than 4 * width pixels, and one IMAD.WIDE then forms the address)
+  auto fetch = [&](uint32_t j) { return origin[(j >> 3) * p.width + (j & 7u)]; };
   uint32_t ca, cb;
   pv_block_extremes(px, *p.first_pixel, p.key_scale, fetch, &ca, &cb);
   p.low[by * lw + bx] = make_uint2(ca, cb);
@@ -153,24 +154,47 @@ __device__ __forceinline__ void pv_modulate_unit(const PvrtcParams &p, uint32_t 
   // Low-resolution rows/columns these pixel rows interpolate between, wrapped (pvrtc_compressor.cc:216-223).
   const uint32_t top = ((y0 - 2u) & (p.height - 1u)) >> 2, bottom = (top + 1u) & (lh - 1u);
   const uint32_t col[3] = {(bx + lw - 1u) & (lw - 1u), bx, (bx + 1u) & (lw - 1u)};
-  PvLanes at[3], ab[3], bt[3], bb[3];  // A and B colours of the top / bottom low-resolution row, three columns
+  // A and B colours of the top / bottom low-resolution row, three columns, as 16-bit lane pairs: index [c][k] =
+  // column c, lane pair k (0 = A's (r,b), 1 = A's (g,a), 2 = B's (r,b), 3 = B's (g,a)).
+  uint32_t top_c[3][4], bot_c[3][4];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const uint2 ct = p.low[top * lw + col[i]], cb = p.low[bottom * lw + col[i]];
-    at[i] = pv_split(ct.x); ab[i] = pv_split(cb.x); bt[i] = pv_split(ct.y); bb[i] = pv_split(cb.y);
+    const PvLanes at = pv_split(ct.x), bt = pv_split(ct.y), ab = pv_split(cb.x), bb = pv_split(cb.y);
+    top_c[i][0] = at.rb; top_c[i][1] = at.ga; top_c[i][2] = bt.rb; top_c[i][3] = bt.ga;
+    bot_c[i][0] = ab.rb; bot_c[i][1] = ab.ga; bot_c[i][2] = bb.rb; bot_c[i][3] = bb.ga;
   }
+  // Horizontal steps between neighbouring columns, as differences of the packed words: a word is the exact integer
+  // lane0 + 65536 * lane1, so the difference of two words is the exact integer of the lane differences, negative lanes
+  // and all, and everything below is linear in it modulo 2^32.
+  uint32_t top_d[2][4], bot_d[2][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      top_d[h][k] = top_c[h + 1][k] - top_c[h][k];
+      bot_d[h][k] = bot_c[h + 1][k] - bot_c[h][k];
+    }
 #pragma unroll
   for (uint32_t r = 0; r < kModRows; ++r) {
     if (!wanted(r)) continue;
     const uint32_t y = (y0 + r) & (p.height - 1u);  // (only the unit that straddles the bottom edge wraps)
-    const uint32_t fy = (y + 2u) & 3u;
-    PvLanes va[3], vb[3];  // vertical blend, shared by the whole row: (4-fy)*top + fy*bottom, not yet divided
+    // (y + 2) & 3; with four rows per unit (y0 = 4g + 2) that is r itself, a compile-time constant of the unrolled loop:
+    // the vertical weights become immediates and the bottom row drops out of the unit's first pixel row
+    const uint32_t fy = kModRows == 4 ? r : ((y + 2u) & 3u);
+    // The bilinear blend ((4-fy)(8-fx) c00 + (4-fy) fx c01 + fy (8-fx) c10 + fy fx c11) / 32 of a channel, scaled by 8 so
+    // that the divisor is 256 (every lane stays below 2^16: 255 * 4 * 64), is LINEAR in fx within a half segment:
+    //   word(fx) = 64 * V_left + fx * 8 * (V_right - V_left),   V = (4-fy) * top + fy * bottom  (vertical blend)
+    // so one multiply-add per lane pair and pixel walks along the row (two before: both columns weighted afresh for
+    // every pixel), after a per-row set-up of a start word and a step word per half and lane pair.  Pixels 0..3 have
+    // fx = 4..7 between columns (bx-1, bx), pixels 4..7 have fx = 0..3 between (bx, bx+1).
+    uint32_t start[2][4], step[2][4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      va[i].rb = at[i].rb * (4u - fy) + ab[i].rb * fy;
-      va[i].ga = at[i].ga * (4u - fy) + ab[i].ga * fy;
-      vb[i].rb = bt[i].rb * (4u - fy) + bb[i].rb * fy;
-      vb[i].ga = bt[i].ga * (4u - fy) + bb[i].ga * fy;
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) step[h][k] = top_d[h][k] * (8u * (4u - fy)) + bot_d[h][k] * (8u * fy);
+      start[0][k] = top_c[0][k] * (64u * (4u - fy)) + bot_c[0][k] * (64u * fy) + 4u * step[0][k];  // fx = 4 at pixel 0
+      start[1][k] = top_c[1][k] * (64u * (4u - fy)) + bot_c[1][k] * (64u * fy);                    // fx = 0 at pixel 4
     }
     const uint4 *row = reinterpret_cast<const uint4 *>(pv_src_row(p, y) + bx * 8);
     const uint4 u = row[0], v = row[1];
@@ -178,11 +202,11 @@ __device__ __forceinline__ void pv_modulate_unit(const PvrtcParams &p, uint32_t 
     uint32_t bits = 0;
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-      const int left = x < 4 ? 0 : 1;       // pixels 0..3 sit between columns (bx-1, bx), 4..7 between (bx, bx+1)
-      const uint32_t fx = (x + 4) & 7;
-      // ((8-fx)*V_left + fx*V_right) / 32, V <= 4*255: weights scaled by 8 so the divisor is 256 (lanes < 2^16)
-      const uint32_t ca = pv_blend256(va[left], 64u - 8u * fx, va[left + 1], 8u * fx);
-      const uint32_t cb = pv_blend256(vb[left], 64u - 8u * fx, vb[left + 1], 8u * fx);
+      const int h = x < 4 ? 0 : 1;
+      const uint32_t n = static_cast<uint32_t>(x & 3);
+      // the quotient by 256 is each lane's high byte: one byte permute divides and re-interleaves (r,g,b,a)
+      const uint32_t ca = __byte_perm(start[h][0] + n * step[h][0], start[h][1] + n * step[h][1], 0x7351);
+      const uint32_t cb = __byte_perm(start[h][2] + n * step[h][2], start[h][3] + n * step[h][3], 0x7351);
       bits |= pv_pick_modulation(px[x], ca, cb) << (2 * x);
     }
     store(r, y, bits);

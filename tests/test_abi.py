@@ -145,3 +145,28 @@ def test_host_emulation_macro_is_test_only():
                 if re.search(r"^\s*#\s*define\s+ICB_HOST_EMULATION", text, re.M):
                     definers.append(os.path.relpath(os.path.join(base, f), root))
     assert definers == ["tests/hostemu/cuda_emulation.h"], definers
+
+
+def test_library_sass_is_free_of_a_known_ptxas_miscompile():
+    """CUDA 12.9's ptxas has been seen to split a lane-wise add with an immediate addend (VIADD.16x2 R, R, imm) into
+    "VIADD.16x2 R17,R4,0x0 ; VIADD.16x2 R15,R4,imm ; PRMT R19,R17,0x7610,R15" -- one lane loses its addend -- in some
+    instantiations of the DXT5 alpha statistics (found on the GPU by the parity tests; profiles/r02b_driver_ab.txt).
+    The addends now live in constant memory; this scans every kernel of the shipped library for the signature, so that
+    the build container already refuses a library whose GPU results would be wrong."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from image_compression_b200 import binding
+    sass = subprocess.run([cuobjdump, "-sass", binding.lib_path()], capture_output=True, text=True, check=True).stdout
+    assert sass.count("Function :") > 20
+    bad, fn = [], None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif re.search(r"VIADD\.16x2 R\d+, R\d+(\.reuse)?, 0x0 ", line):
+            bad.append(fn)
+    assert not bad, bad

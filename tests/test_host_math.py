@@ -120,6 +120,48 @@ def test_line_search_equals_first_strict_minimum():
         assert line_search(L, l, rng.randint(0, 15)) == direct_first_min(L, l), (L, l)
 
 
+def test_pvrtc_colour_reduction_on_the_packed_word():
+    """pvrtc_encode.cuh:pv_reduce_colour works on the packed (r,g,b,a) word; this is the per-channel definition
+    (ApplyBitDepthReduction, pvrtc_compressor.cc:93-106, 337-349) against it for every value of every channel."""
+    def keep(v, n):
+        kept = v & ((0xff << (8 - n)) & 0xff)
+        out = kept | (kept >> n)
+        if n <= 3:
+            out |= kept >> (2 * n)
+        return out
+
+    def per_channel(c, is_b):
+        r, g, b, a = c & 255, (c >> 8) & 255, (c >> 16) & 255, c >> 24
+        if a == 255:
+            r, g, b = keep(r, 5), keep(g, 5), keep(b, 5 if is_b else 4)
+        else:
+            r, g, b, a = keep(r, 4), keep(g, 4), keep(b, 4 if is_b else 3), keep(a, 3)
+        return r | (g << 8) | (b << 16) | (a << 24)
+
+    def packed(c, is_b):
+        if is_b:
+            opaque = (c & 0xfff8f8f8) | ((c >> 5) & 0x00070707)
+            t = c & 0xe0f0f0f0
+            translucent = t | ((t >> 4) & 0x000f0f0f) | ((t >> 3) & 0x1c000000) | ((t >> 6) & 0x03000000)
+        else:
+            opaque = (c & 0xfff0f8f8) | ((c >> 5) & 0x00000707) | ((c >> 4) & 0x000f0000)
+            t = c & 0xe0e0f0f0
+            translucent = t | ((t >> 4) & 0x00000f0f) | ((t >> 3) & 0x1c1c0000) | ((t >> 6) & 0x03030000)
+        return opaque if c >= 0xff000000 else translucent
+
+    import random
+    rng = random.Random(5)
+    for is_b in (False, True):
+        for v in range(256):
+            for shift in (0, 8, 16, 24):
+                for others in (0x00000000, 0xffffffff, 0x5aa5c33c):
+                    c = (others & ~(0xff << shift)) | (v << shift)
+                    assert packed(c, is_b) == per_channel(c, is_b), (hex(c), is_b)
+        for _ in range(20000):
+            c = rng.getrandbits(32) | (0xff000000 if rng.random() < 0.3 else 0)
+            assert packed(c, is_b) == per_channel(c, is_b), (hex(c), is_b)
+
+
 # ---- addressing identities of the TMA drivers (block4x4_kernels.cuh); the host emulation does not run those kernels ----
 
 def test_tile_window_offset_trick():
