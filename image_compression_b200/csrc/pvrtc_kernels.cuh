@@ -110,7 +110,10 @@ __device__ __forceinline__ void pv_wait_for_previous() { asm volatile("griddepco
 // Eight CTAs per SM = 64 registers per thread: with that budget ptxas issues all eight 128-bit pixel loads before the
 // first use (63 registers); left to itself it settles on 32 registers and loads two rows at a time, and the kernel
 // waits on its loads (measured: 49.8 -> 48.7 us per encode).
-__global__ void __launch_bounds__(128, 8) pvrtc_morph_kernel(const PvrtcParams p) {
+#ifndef ICB_PVRTC_MORPH_MIN_CTAS
+#define ICB_PVRTC_MORPH_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, ICB_PVRTC_MORPH_MIN_CTAS) pvrtc_morph_kernel(const PvrtcParams p) {
   pv_launch_dependents();
   pv_wait_for_previous();  // whatever wrote the image; the previous encode's Pack (reads the colours written below)
   const uint32_t lw = p.width >> 3, lh = p.height >> 2;
