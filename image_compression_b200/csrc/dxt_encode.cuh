@@ -473,16 +473,20 @@ __device__ __forceinline__ uint2 dxt5_alpha_indices(const uint32_t (&x)[8], uint
   if (__all_sync(kFullWarp ? 0xffffffffu : __activemask(), a0 >= a1 + 7u)) {
     const uint4 *e = table + 4u * (256u + a0 - a1);
     const uint4 e0 = e[0], e1 = e[1];
-    // -a0 in both lanes as one multiply-add: (65536 - a0) * 65537 = 0x00010000 - a0 * 65537 (mod 2^32); a0 >= 7 here
+    // -a0 in both lanes as one multiply-add: (65536 - a0) * 65537 = 0x00010000 - a0 * 65537 (mod 2^32); a0 >= 7 here.
+    // It goes into the seven thresholds (relative to a0 in the table) rather than into the eight alpha lane pairs.
     const uint32_t minus_a0 = a0 * 0xfffeffffu + 0x00010000u;
+    const uint32_t c0 = __vadd2(e0.x, minus_a0), c1 = __vadd2(e0.y, minus_a0), c2 = __vadd2(e0.z, minus_a0),
+                   c3 = __vadd2(e0.w, minus_a0), c4 = __vadd2(e1.x, minus_a0), c5 = __vadd2(e1.y, minus_a0),
+                   c6 = __vadd2(e1.z, minus_a0);
     uint32_t acc_a = 0x02490249u, acc_b = 0x02490249u;  // index 1 in four 3-bit fields of both lanes
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-      const uint32_t d = __vadd2(x[p], minus_a0);  // alpha - a0, two's complement per lane
-      const uint32_t t0 = __viaddmin_s16x2_relu(d, e0.x, 0x00010001u), t1 = __viaddmin_s16x2_relu(d, e0.y, 0x00010001u),
-                     t2 = __viaddmin_s16x2_relu(d, e0.z, 0x00010001u), t3 = __viaddmin_s16x2_relu(d, e0.w, 0x00010001u),
-                     t4 = __viaddmin_s16x2_relu(d, e1.x, 0x00010001u), t5 = __viaddmin_s16x2_relu(d, e1.y, 0x00010001u),
-                     t6 = __viaddmin_s16x2_relu(d, e1.z, 0x00010001u);
+      const uint32_t d = x[p];
+      const uint32_t t0 = __viaddmin_s16x2_relu(d, c0, 0x00010001u), t1 = __viaddmin_s16x2_relu(d, c1, 0x00010001u),
+                     t2 = __viaddmin_s16x2_relu(d, c2, 0x00010001u), t3 = __viaddmin_s16x2_relu(d, c3, 0x00010001u),
+                     t4 = __viaddmin_s16x2_relu(d, c4, 0x00010001u), t5 = __viaddmin_s16x2_relu(d, c5, 0x00010001u),
+                     t6 = __viaddmin_s16x2_relu(d, c6, 0x00010001u);
       const uint32_t ones = t1 + t2 + t3 + t4 + t5;  // crossings that lower the index by one
       const uint32_t f = 1u << (3 * (p & 3));        // this pair's field in both lanes
       uint32_t &acc = p < 4 ? acc_a : acc_b;
