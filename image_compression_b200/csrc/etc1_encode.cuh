@@ -24,6 +24,31 @@ enum Etc1Strategy : int { kEtcSplitHorizontally = 0, kEtcSplitVertically = 1, kE
 __device__ __forceinline__ int etc_small(int cw) { return static_cast<int>(0x2f2118120d090502ull >> (8 * cw)) & 0xff; }
 __device__ __forceinline__ int etc_large(int cw) { return static_cast<int>(0xb76a503c2a1d1108ull >> (8 * cw)) & 0xff; }
 
+// What the rolled codeword loop needs per codeword, the same for every block: the four modifiers (+s, +l, -s, -l) in
+// both 16-bit lanes for the candidate builder, and -2s, -2l, 3s^2, 3l^2 for the line form.  Constant memory, indexed by
+// the (warp-uniform) loop counter: one LDC per value instead of a dozen shift / mask / negate / replicate
+// instructions per codeword, which is what made the rolled loop 4 % slower than the unrolled one.
+struct EtcCodewordConsts {
+  uint32_t m2[4];
+  int neg2s, neg2l, s3, l3;
+  int large, pad[3];
+};
+constexpr int etc_small_c(int cw) { return static_cast<int>(0x2f2118120d090502ull >> (8 * cw)) & 0xff; }
+constexpr int etc_large_c(int cw) { return static_cast<int>(0xb76a503c2a1d1108ull >> (8 * cw)) & 0xff; }
+constexpr uint32_t etc_lanes(int m) { return (static_cast<uint32_t>(m) & 0xffffu) * 0x10001u; }
+constexpr EtcCodewordConsts etc_codeword_consts(int cw) {
+  return EtcCodewordConsts{{etc_lanes(etc_small_c(cw)), etc_lanes(etc_large_c(cw)), etc_lanes(-etc_small_c(cw)), etc_lanes(-etc_large_c(cw))},
+                           -2 * etc_small_c(cw), -2 * etc_large_c(cw), 3 * etc_small_c(cw) * etc_small_c(cw),
+                           3 * etc_large_c(cw) * etc_large_c(cw), etc_large_c(cw), {0, 0, 0}};
+}
+#ifdef ICB_HOST_EMULATION
+static const EtcCodewordConsts
+#else
+__constant__ EtcCodewordConsts
+#endif
+    c_etc_codewords[8] = {etc_codeword_consts(0), etc_codeword_consts(1), etc_codeword_consts(2), etc_codeword_consts(3),
+                          etc_codeword_consts(4), etc_codeword_consts(5), etc_codeword_consts(6), etc_codeword_consts(7)};
+
 // clamp255(base + modifier) on each of three channels, packed as bytes (r,g,b,0).
 __device__ __forceinline__ uint32_t etc_candidate(int r, int g, int b, int modifier) {
   const uint32_t cr = static_cast<uint32_t>(__viaddmin_s32_relu(r, modifier, 255));
@@ -77,6 +102,65 @@ __device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[1
   return best;
 }
 
+// Codewords whose four candidates do not clamp lie ON the line base + m*(1,1,1), m = +s, +l, -s, -l, and the distance
+// of a pixel to such a candidate is |d|^2 - 2 m S + 3 m^2 with d = pixel - base, S = d_r + d_g + d_b: the nearest of the
+// four is decided by |S| alone,
+//     min_j |pixel - candidate_j|^2 = |d|^2 + min(3 s^2 - 2 s |S|, 3 l^2 - 2 l |S|)        (exact, no rounding anywhere)
+// -- two multiply-adds, a minimum and an addition per pixel and codeword where the general form needs four candidate
+// distances (VABSDIFF4 + IDP.4A each), two minima and an addition, plus the four clamped candidates per codeword.
+// |d|^2 and |S| do not depend on the codeword: they are computed once per sub-block.  A codeword qualifies when
+// l <= every base channel <= 255 - l, i.e. when l does not exceed the bases' margin (etc_noclamp_margin); the margin is
+// made warp-uniform (minimum over the lanes: one REDUX) so that the choice of form never diverges.  The large magnitudes
+// grow with the codeword: on uniform random bytes codewords 0 .. 2 or 3 of 8 qualify for a whole warp, on dark or
+// bright regions none or two, on mid-tone regions up to six.
+#ifndef ICB_ETC1_LINE_SHORTCUT
+#define ICB_ETC1_LINE_SHORTCUT 1
+#endif
+#ifndef ICB_ETC1_UNROLL_CODEWORDS
+#define ICB_ETC1_UNROLL_CODEWORDS 0
+#endif
+
+// The largest modifier magnitude that cannot clamp either of two base colours (bytes r,g,b,0), slightly conservative:
+// 127 - max |channel - 128| (a channel of exactly l would still be safe on the low side; losing that case costs nothing
+// but an unnecessary general-form evaluation).  Negative when a channel is 0 or 255.
+__device__ __forceinline__ int etc_noclamp_margin(uint32_t base1, uint32_t base2) {
+  const uint32_t a1 = __vabsdiffu4(base1, 0x00808080u), a2 = __vabsdiffu4(base2, 0x00808080u);  // the top bytes are zero
+  const uint32_t m1 = max(max(a1 & 255u, (a1 >> 8) & 255u), a1 >> 16), m2 = max(max(a2 & 255u, (a2 >> 8) & 255u), a2 >> 16);
+  return 127 - static_cast<int>(max(m1, m2));
+}
+
+// Sum of |d|^2 over the pixels selected by kMask (the part of the line form that does not depend on the codeword).
+template <uint32_t kMask>
+__device__ __forceinline__ uint32_t etc_line_d2(const uint32_t (&px)[16], uint32_t base) {
+  uint32_t d2 = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (kMask & (1u << i)) {
+      const uint32_t d = __vabsdiffu4(px[i], base);
+      d2 = __dp4a(d, d, d2);
+    }
+  }
+  return d2;
+}
+
+// Sum over a sub-block's pixels of min(3 s^2 - 2 s |S|, 3 l^2 - 2 l |S|) (signed; the caller adds the sum of |d|^2).
+// S is recomputed from the pixel for every codeword (one IDP.4A with -(b_r + b_g + b_b) in its accumulator, one IABS):
+// keeping the sixteen |S| of an orientation in registers across the loop made ptxas spill the loop's invariants, and
+// the GENERAL form paid for it (dark content, where no codeword qualifies: 158 -> 175 us).
+template <uint32_t kMask>
+__device__ __forceinline__ int etc_line_error(const uint32_t (&px)[16], uint32_t minus_sum, const EtcCodewordConsts &c) {
+  int total = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (kMask & (1u << i)) {
+      const int s = static_cast<int>(__dp4a(px[i], 0x00010101u, minus_sum));
+      const int u = s < 0 ? -s : s;
+      total += min(u * c.neg2s + c.s3, u * c.neg2l + c.l3);
+    }
+  }
+  return total;
+}
+
 // The same for BOTH sub-blocks of one orientation at once.  Building the clamped candidates is a quarter of the
 // integer-pipe work of the exhaustive search when done channel by channel (three VIADDMNMX + two packing operations
 // per candidate); the two sub-blocks meet the same modifier at the same time, so their channels ride in 16-bit lanes
@@ -88,13 +172,40 @@ __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16],
   const uint32_t rb1 = base1 & 0x00ff00ffu, rb2 = base2 & 0x00ff00ffu;
   const uint32_t g12 = __byte_perm(base1, base2, 0x3531);  // (g1, 0, g2, 0): the bases' top bytes are zero
   uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu;
+#if ICB_ETC1_LINE_SHORTCUT
+  // (REDUX.MIN on the margin + 128 >= 0, so that the unsigned minimum is the signed one)
+  const int line_margin = static_cast<int>(__reduce_min_sync(__activemask(), static_cast<uint32_t>(etc_noclamp_margin(base1, base2) + 128))) - 128;
+  uint32_t d2_1 = 0, d2_2 = 0;
+  if (line_margin >= etc_large_c(0)) {  // (warp-uniform: dark and bright regions do not pay for sums they cannot use)
+    d2_1 = etc_line_d2<kMask1>(px, base1);
+    d2_2 = etc_line_d2<kMask2>(px, base2);
+  }
+  const uint32_t minus_sum1 = 0u - __dp4a(base1, 0x00010101u, 0u), minus_sum2 = 0u - __dp4a(base2, 0x00010101u, 0u);
+#endif
+  // The codeword loop is NOT unrolled (ICB_ETC1_UNROLL_CODEWORDS=0): unrolled, the exhaustive search is ~5000
+  // instructions (80 KB) -- tolerable while every warp walks it in the same order, but with the two forms of a codeword
+  // the warps of an SM spread over a 105 KB body and stall on instruction fetch (measured: 17 % fewer instructions
+  // executed, 158 -> 180-218 us on structured content).  Rolled, both forms of both orientations are ~1000 instructions.
+#if ICB_ETC1_UNROLL_CODEWORDS
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int cw = 0; cw < 8; ++cw) {
+    const EtcCodewordConsts &cc = c_etc_codewords[cw];
+#if ICB_ETC1_LINE_SHORTCUT
+    if (cc.large <= line_margin) {  // warp-uniform
+      const uint32_t e1 = d2_1 + static_cast<uint32_t>(etc_line_error<kMask1>(px, minus_sum1, cc));
+      const uint32_t e2 = d2_2 + static_cast<uint32_t>(etc_line_error<kMask2>(px, minus_sum2, cc));
+      best1 = min(best1, e1 * 8u + static_cast<uint32_t>(cw));
+      best2 = min(best2, e2 * 8u + static_cast<uint32_t>(cw));
+      continue;
+    }
+#endif
     EtcCandidates k1, k2;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int mag = (j & 1) ? etc_large(cw) : etc_small(cw);
-      const uint32_t m2 = (static_cast<uint32_t>((j & 2) ? -mag : mag) & 0xffffu) * 0x10001u;
+      const uint32_t m2 = cc.m2[j];
       const uint32_t c_rb1 = __viaddmin_s16x2_relu(rb1, m2, 0x00ff00ffu);
       const uint32_t c_rb2 = __viaddmin_s16x2_relu(rb2, m2, 0x00ff00ffu);
       const uint32_t c_g12 = __viaddmin_s16x2_relu(g12, m2, 0x00ff00ffu);

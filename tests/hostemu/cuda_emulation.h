@@ -59,6 +59,11 @@ static inline bool __all_sync(uint32_t, bool pred) {
   return (nth & 1) ? pred : false;
 }
 
+// Warp-wide minimum (REDUX): like the votes, the harness decides what the other lanes contribute -- nothing that
+// lowers this lane's value (kEmuVoteAgree), or a zero (the other modes), which sends ETC1's codeword search (whose
+// operand is a margin + 128) down its general form for every codeword.
+static inline uint32_t __reduce_min_sync(uint32_t, uint32_t v) { return g_emu_vote == kEmuVoteAgree ? v : 0u; }
+
 // ---- scalar helpers
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }

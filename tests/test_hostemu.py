@@ -175,8 +175,10 @@ def test_etc1_vs_oracle(emu, strategy):
     for kind in imagegen.KINDS:
         for (h, w) in ((16, 32), (9, 14)):
             img = imagegen.make(kind, h, w, 3, seed=24)
-            got = encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy)
-            assert np.array_equal(got, ck.oracle_etc1(strategy, img.ravel(), h, w)), (kind, h, w)
+            want = ck.oracle_etc1(strategy, img.ravel(), h, w)
+            # vote 0: this lane's no-clamp codewords take the line form; vote 1: the general form for every codeword
+            for vote in (0, 1):
+                assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy, vote=vote), want), (kind, h, w, vote)
 
 
 def test_pvrtc_vs_oracle_whole_and_striped(emu):
@@ -375,7 +377,9 @@ def test_etc1_soak_clamping_and_ties(emu, strategy):
     cols = 500
     img = np.ascontiguousarray(blocks.astype(np.uint8).reshape(n // cols, cols, 4, 4, 3).transpose(0, 2, 1, 3, 4).reshape(n // cols * 4, cols * 4, 3))
     h, w = img.shape[:2]
-    assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy), ck.oracle_etc1(strategy, img.ravel(), h, w))
+    want = ck.oracle_etc1(strategy, img.ravel(), h, w)
+    for vote in (0, 1):  # line form where this block's codewords do not clamp / general form everywhere
+        assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy, vote=vote), want), vote
 
 
 def test_device_code_addressing_under_sanitizers():
