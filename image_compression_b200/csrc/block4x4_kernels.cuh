@@ -116,6 +116,9 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 #ifndef ICB_DXT1_TILE_BLOCKS_Y
 #define ICB_DXT1_TILE_BLOCKS_Y 8
 #endif
+#ifndef ICB_ETC1_MIN_CTAS
+#define ICB_ETC1_MIN_CTAS 3
+#endif
 template <int kCodec>
 constexpr int tile_blocks_y() { return kCodec == kCodecDxt1 ? ICB_DXT1_TILE_BLOCKS_Y : 4; }
 
@@ -128,7 +131,8 @@ struct TileShape {
   static constexpr int kBytes = kRowWords * 4 * kRows;      // 16384 / 12288 (x2 for DXT1)
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
   // resident CTAs per SM the kernels are compiled for (register budget = 65536 / threads / CTAs)
-  static constexpr int kProducerMinCtas = kCodec == kCodecDxt1 ? (kBlocksY >= 16 ? 1 : (kBlocksY >= 8 ? 2 : 4)) : 3;
+  static constexpr int kProducerMinCtas =
+      kCodec == kCodecDxt1 ? (kBlocksY >= 16 ? 1 : (kBlocksY >= 8 ? 2 : 4)) : (kCodec == kCodecEtc1 ? ICB_ETC1_MIN_CTAS : 3);
 };
 
 // Shared-memory loads by 32-bit shared-window address (no generic pointers: the tile base stays one register and the

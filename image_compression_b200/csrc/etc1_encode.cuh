@@ -25,12 +25,14 @@ __device__ __forceinline__ int etc_small(int cw) { return static_cast<int>(0x2f2
 __device__ __forceinline__ int etc_large(int cw) { return static_cast<int>(0xb76a503c2a1d1108ull >> (8 * cw)) & 0xff; }
 
 // What the rolled codeword loop needs per codeword, the same for every block: the four modifiers (+s, +l, -s, -l) in
-// both 16-bit lanes for the candidate builder, and -2s, -2l, 3s^2, 3l^2 for the line form.  Constant memory, indexed by
-// the (warp-uniform) loop counter: one LDC per value instead of a dozen shift / mask / negate / replicate
-// instructions per codeword, which is what made the rolled loop 4 % slower than the unrolled one.
+// both 16-bit lanes for the candidate builder, and for the line form -3(l+s) in both lanes, l-s in the two low bytes,
+// 24 s^2 and -s.  Constant memory, indexed by the (warp-uniform) loop counter: one LDC per value instead of a dozen
+// shift / mask / negate / replicate instructions per codeword, which is what made the rolled loop 4 % slower than the
+// unrolled one.
 struct EtcCodewordConsts {
   uint32_t m2[4];
-  int neg2s, neg2l, s3, l3;
+  uint32_t neg_knee2, step_bytes;  // lanes(-3(l+s)); (l-s) | (l-s) << 8
+  int s24, neg_s;                  // 8 pixels * 3 s^2; -s
   int large, pad[3];
 };
 constexpr int etc_small_c(int cw) { return static_cast<int>(0x2f2118120d090502ull >> (8 * cw)) & 0xff; }
@@ -38,8 +40,9 @@ constexpr int etc_large_c(int cw) { return static_cast<int>(0xb76a503c2a1d1108ul
 constexpr uint32_t etc_lanes(int m) { return (static_cast<uint32_t>(m) & 0xffffu) * 0x10001u; }
 constexpr EtcCodewordConsts etc_codeword_consts(int cw) {
   return EtcCodewordConsts{{etc_lanes(etc_small_c(cw)), etc_lanes(etc_large_c(cw)), etc_lanes(-etc_small_c(cw)), etc_lanes(-etc_large_c(cw))},
-                           -2 * etc_small_c(cw), -2 * etc_large_c(cw), 3 * etc_small_c(cw) * etc_small_c(cw),
-                           3 * etc_large_c(cw) * etc_large_c(cw), etc_large_c(cw), {0, 0, 0}};
+                           etc_lanes(-3 * (etc_large_c(cw) + etc_small_c(cw))),
+                           static_cast<uint32_t>(etc_large_c(cw) - etc_small_c(cw)) * 0x101u,
+                           24 * etc_small_c(cw) * etc_small_c(cw), -etc_small_c(cw), etc_large_c(cw), {0, 0, 0}};
 }
 #ifdef ICB_HOST_EMULATION
 static const EtcCodewordConsts
@@ -106,13 +109,19 @@ __device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[1
 // of a pixel to such a candidate is |d|^2 - 2 m S + 3 m^2 with d = pixel - base, S = d_r + d_g + d_b: the nearest of the
 // four is decided by |S| alone,
 //     min_j |pixel - candidate_j|^2 = |d|^2 + min(3 s^2 - 2 s |S|, 3 l^2 - 2 l |S|)        (exact, no rounding anywhere)
-// -- two multiply-adds, a minimum and an addition per pixel and codeword where the general form needs four candidate
-// distances (VABSDIFF4 + IDP.4A each), two minima and an addition, plus the four clamped candidates per codeword.
-// |d|^2 and |S| do not depend on the codeword: they are computed once per sub-block.  A codeword qualifies when
-// l <= every base channel <= 255 - l, i.e. when l does not exceed the bases' margin (etc_noclamp_margin); the margin is
-// made warp-uniform (minimum over the lanes: one REDUX) so that the choice of form never diverges.  The large magnitudes
-// grow with the codeword: on uniform random bytes codewords 0 .. 2 or 3 of 8 qualify for a whole warp, on dark or
-// bright regions none or two, on mid-tone regions up to six.
+// and the minimum of the two lines in |S| is the first one minus what the second gains beyond their crossing,
+//     min(3 s^2 - 2 s u, 3 l^2 - 2 l u) = 3 s^2 - s (2u) - (l - s) max(0, 2u - 3 (l + s)),
+// so the error of a sub-block's eight pixels is
+//     sum |d|^2 + 24 s^2 - s W - (l - s) sum_i max(0, w_i - 3 (l + s)),      w_i = 2 |S_i|,  W = sum w_i.
+// Only the last sum depends on both the codeword and the pixels, and w_i <= 1530 fits a 16-bit lane: with the eight
+// w_i of a sub-block in four registers it is four VIADDMNMX.S16x2.RELU, three additions and one IDP.2A that adds the
+// two lanes and multiplies by l - s -- a dozen instructions per sub-block and codeword where the general form needs a
+// hundred (four VABSDIFF4 + IDP.4A candidate distances, two minima and an addition per pixel, plus the candidates).
+// sum |d|^2, W and the w_i do not depend on the codeword: they are computed once per sub-block.  A codeword qualifies
+// when l <= every base channel <= 255 - l, i.e. when l does not exceed the bases' margin (etc_noclamp_margin); the
+// margin is made warp-uniform (minimum over the lanes: one REDUX) so that the choice of form never diverges.  The large
+// magnitudes grow with the codeword: on uniform random bytes codewords 0 .. 2 or 3 of 8 qualify for a whole warp, on
+// dark or bright regions none or two, on mid-tone regions up to six.
 #ifndef ICB_ETC1_LINE_SHORTCUT
 #define ICB_ETC1_LINE_SHORTCUT 1
 #endif
@@ -129,9 +138,10 @@ __device__ __forceinline__ int etc_noclamp_margin(uint32_t base1, uint32_t base2
   return 127 - static_cast<int>(max(m1, m2));
 }
 
-// Sum of |d|^2 over the pixels selected by kMask (the part of the line form that does not depend on the codeword).
+// Sum of |pixel - base|^2 over the pixels selected by kMask: the part of a sub-block's error that no codeword changes
+// (both the line form and the dot form below compute errors relative to it).
 template <uint32_t kMask>
-__device__ __forceinline__ uint32_t etc_line_d2(const uint32_t (&px)[16], uint32_t base) {
+__device__ __forceinline__ uint32_t etc_d2(const uint32_t (&px)[16], uint32_t base) {
   uint32_t d2 = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -143,22 +153,100 @@ __device__ __forceinline__ uint32_t etc_line_d2(const uint32_t (&px)[16], uint32
   return d2;
 }
 
-// Sum over a sub-block's pixels of min(3 s^2 - 2 s |S|, 3 l^2 - 2 l |S|) (signed; the caller adds the sum of |d|^2).
-// S is recomputed from the pixel for every codeword (one IDP.4A with -(b_r + b_g + b_b) in its accumulator, one IABS):
-// keeping the sixteen |S| of an orientation in registers across the loop made ptxas spill the loop's invariants, and
-// the GENERAL form paid for it (dark content, where no codeword qualifies: 158 -> 175 us).
+// The codeword-independent part of the line form for the pixels selected by kMask: w_i = 2 |S_i| of the eight pixels,
+// two to a register, and their sum.
+struct EtcLineTerms {
+  uint32_t w[4];  // (w_even | w_odd << 16)
+  uint32_t W;     // sum w_i
+};
 template <uint32_t kMask>
-__device__ __forceinline__ int etc_line_error(const uint32_t (&px)[16], uint32_t minus_sum, const EtcCodewordConsts &c) {
+__device__ __forceinline__ EtcLineTerms etc_line_terms(const uint32_t (&px)[16], uint32_t base) {
+  EtcLineTerms t;
+  const uint32_t minus_2sum = 0u - __dp4a(base, 0x00020202u, 0u);
+  int n = 0;  // (a constant in every copy of the unrolled body)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (kMask & (1u << i)) {
+      const int s2 = static_cast<int>(__dp4a(px[i], 0x00020202u, minus_2sum));
+      const uint32_t w = static_cast<uint32_t>(s2 < 0 ? -s2 : s2);
+      if (n & 1)
+        t.w[n >> 1] += w << 16;
+      else
+        t.w[n >> 1] = w;
+      ++n;
+    }
+  }
+  t.W = __dp2a_lo(t.w[0] + t.w[1] + t.w[2] + t.w[3], 0x0101u, 0u);  // (a lane holds at most 4 * 1530)
+  return t;
+}
+
+// Error of the sub-block under a codeword none of whose candidates clamps, d2 = sum |pixel - base|^2.
+__device__ __forceinline__ uint32_t etc_line_error(const EtcLineTerms &t, uint32_t d2, const EtcCodewordConsts &c) {
+  // max(max(w - knee, -knee), 0) = max(w - knee, 0): the third operand is a register that is there anyway (a literal
+  // zero costs a PRMT per instruction: ptxas 12.9 does not put RZ there)
+  const uint32_t k = c.neg_knee2;
+  const uint32_t beyond = __viaddmax_s16x2_relu(t.w[0], k, k) + __viaddmax_s16x2_relu(t.w[1], k, k) +
+                          __viaddmax_s16x2_relu(t.w[2], k, k) + __viaddmax_s16x2_relu(t.w[3], k, k);
+  return d2 + static_cast<uint32_t>(c.s24) + t.W * static_cast<uint32_t>(c.neg_s) - __dp2a_lo(beyond, c.step_bytes, 0u);
+}
+
+// The general form, for codewords some candidate of which clamps.  The distance of a pixel p to a candidate c, relative
+// to its distance to the base b, is LINEAR in the pixel:
+//     |p - c|^2 - |p - b|^2 = |c|^2 - |b|^2 - 2 (c - b) . p
+// -- one IDP.4A of the pixel with per-candidate weights 2 (b - c) and per-candidate accumulator |c|^2 (the common
+// -|b|^2 is added once per sub-block), where the direct form needs VABSDIFF4 + IDP.4A.  IDP.4A takes unsigned bytes:
+// the candidates with negative modifiers have c <= b in every channel, weights 2 (b - c) >= 0; those with positive
+// modifiers have c >= b and use the COMPLEMENTED pixel q = 255 - p, against which everything mirrors
+// (|p - c| = |q - ~c|): weights 2 (c - b) >= 0, accumulator |~c|^2 + (|b|^2 - |~b|^2).  Per pixel and codeword: one
+// LOP3 for q, four IDP.4A, two minima, an addition -- the integer pipe, which bounded the direct form (four VABSDIFF4 +
+// two VIMNMX3 of its twelve instructions), is left with three.  Weights and accumulators cost 2.5 instructions per
+// candidate and base, once per codeword.  Clamped magnitudes above 127 do not fit a doubled byte: they occur only for
+// the large modifier of codeword 7 (183), whose two candidates take weights (c - b) and two chained IDP.4A instead.
+#ifndef ICB_ETC1_DOT_FORM
+#define ICB_ETC1_DOT_FORM 1
+#endif
+
+struct EtcDotBase {
+  uint32_t two_b;  // 2 * base as an integer (the addend that turns 2c into 2 (c - b); bytes may carry, the sum does not)
+  uint32_t delta;  // |b|^2 - |~b|^2
+  uint32_t rel;    // sum |p - b|^2 - 8 |b|^2: what the sum of the per-pixel minima is added to
+};
+template <uint32_t kMask>
+__device__ __forceinline__ EtcDotBase etc_dot_base(const uint32_t (&px)[16], uint32_t base, uint32_t d2) {
+  const uint32_t nb = base ^ 0x00ffffffu, bb = __dp4a(base, base, 0u);
+  return EtcDotBase{2u * base, bb - __dp4a(nb, nb, 0u), d2 - 8u * bb};
+}
+
+// Sum over the sub-block's pixels of min_j (|p - c_j|^2 - |p - b|^2 + |b|^2), candidates in the reference's order
+// (+s, +l, -s, -l).  kWide: the large candidates' magnitudes may exceed 127 (codeword 7).
+template <uint32_t kMask, bool kWide>
+__device__ __forceinline__ uint32_t etc_dot_error(const uint32_t (&px)[16], const EtcCandidates &k, const EtcDotBase &b) {
+  uint32_t w[4], a[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool wide = kWide && (j & 1);
+    if (j < 2) {  // c >= b
+      const uint32_t nc = k.c[j] ^ 0x00ffffffu;
+      w[j] = wide ? k.c[j] - (b.two_b >> 1) : 2u * k.c[j] - b.two_b;
+      a[j] = __dp4a(nc, nc, b.delta);
+    } else {  // c <= b
+      w[j] = wide ? (b.two_b >> 1) - k.c[j] : b.two_b - 2u * k.c[j];
+      a[j] = __dp4a(k.c[j], k.c[j], 0u);
+    }
+  }
   int total = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     if (kMask & (1u << i)) {
-      const int s = static_cast<int>(__dp4a(px[i], 0x00010101u, minus_sum));
-      const int u = s < 0 ? -s : s;
-      total += min(u * c.neg2s + c.s3, u * c.neg2l + c.l3);
+      const uint32_t p = px[i], q = px[i] ^ 0x00ffffffu;
+      const int v0 = static_cast<int>(__dp4a(q, w[0], a[0]));
+      const int v1 = static_cast<int>(kWide ? __dp4a(q, w[1], __dp4a(q, w[1], a[1])) : __dp4a(q, w[1], a[1]));
+      const int v2 = static_cast<int>(__dp4a(p, w[2], a[2]));
+      const int v3 = static_cast<int>(kWide ? __dp4a(p, w[3], __dp4a(p, w[3], a[3])) : __dp4a(p, w[3], a[3]));
+      total += min(min(v0, v1), min(v2, v3));
     }
   }
-  return total;
+  return b.rel + static_cast<uint32_t>(total);
 }
 
 // The same for BOTH sub-blocks of one orientation at once.  Building the clamped candidates is a quarter of the
@@ -172,15 +260,18 @@ __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16],
   const uint32_t rb1 = base1 & 0x00ff00ffu, rb2 = base2 & 0x00ff00ffu;
   const uint32_t g12 = __byte_perm(base1, base2, 0x3531);  // (g1, 0, g2, 0): the bases' top bytes are zero
   uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu;
+  const uint32_t d2_1 = etc_d2<kMask1>(px, base1), d2_2 = etc_d2<kMask2>(px, base2);
+#if ICB_ETC1_DOT_FORM
+  const EtcDotBase dot1 = etc_dot_base<kMask1>(px, base1, d2_1), dot2 = etc_dot_base<kMask2>(px, base2, d2_2);
+#endif
 #if ICB_ETC1_LINE_SHORTCUT
   // (REDUX.MIN on the margin + 128 >= 0, so that the unsigned minimum is the signed one)
   const int line_margin = static_cast<int>(__reduce_min_sync(__activemask(), static_cast<uint32_t>(etc_noclamp_margin(base1, base2) + 128))) - 128;
-  uint32_t d2_1 = 0, d2_2 = 0;
+  EtcLineTerms line1 = {}, line2 = {};
   if (line_margin >= etc_large_c(0)) {  // (warp-uniform: dark and bright regions do not pay for sums they cannot use)
-    d2_1 = etc_line_d2<kMask1>(px, base1);
-    d2_2 = etc_line_d2<kMask2>(px, base2);
+    line1 = etc_line_terms<kMask1>(px, base1);
+    line2 = etc_line_terms<kMask2>(px, base2);
   }
-  const uint32_t minus_sum1 = 0u - __dp4a(base1, 0x00010101u, 0u), minus_sum2 = 0u - __dp4a(base2, 0x00010101u, 0u);
 #endif
   // The codeword loop is NOT unrolled (ICB_ETC1_UNROLL_CODEWORDS=0): unrolled, the exhaustive search is ~5000
   // instructions (80 KB) -- tolerable while every warp walks it in the same order, but with the two forms of a codeword
@@ -195,10 +286,8 @@ __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16],
     const EtcCodewordConsts &cc = c_etc_codewords[cw];
 #if ICB_ETC1_LINE_SHORTCUT
     if (cc.large <= line_margin) {  // warp-uniform
-      const uint32_t e1 = d2_1 + static_cast<uint32_t>(etc_line_error<kMask1>(px, minus_sum1, cc));
-      const uint32_t e2 = d2_2 + static_cast<uint32_t>(etc_line_error<kMask2>(px, minus_sum2, cc));
-      best1 = min(best1, e1 * 8u + static_cast<uint32_t>(cw));
-      best2 = min(best2, e2 * 8u + static_cast<uint32_t>(cw));
+      best1 = min(best1, etc_line_error(line1, d2_1, cc) * 8u + static_cast<uint32_t>(cw));
+      best2 = min(best2, etc_line_error(line2, d2_2, cc) * 8u + static_cast<uint32_t>(cw));
       continue;
     }
 #endif
@@ -212,8 +301,18 @@ __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16],
       k1.c[j] = __byte_perm(c_rb1, c_g12, 0x1240);  // (r, g1, b, 0)
       k2.c[j] = __byte_perm(c_rb2, c_g12, 0x1260);  // (r, g2, b, 0)
     }
+#if ICB_ETC1_DOT_FORM
+    if (cw == 7) {
+      best1 = min(best1, etc_dot_error<kMask1, true>(px, k1, dot1) * 8u + static_cast<uint32_t>(cw));
+      best2 = min(best2, etc_dot_error<kMask2, true>(px, k2, dot2) * 8u + static_cast<uint32_t>(cw));
+    } else {
+      best1 = min(best1, etc_dot_error<kMask1, false>(px, k1, dot1) * 8u + static_cast<uint32_t>(cw));
+      best2 = min(best2, etc_dot_error<kMask2, false>(px, k2, dot2) * 8u + static_cast<uint32_t>(cw));
+    }
+#else
     best1 = min(best1, etc_codeword_error<kMask1>(px, k1) * 8u + static_cast<uint32_t>(cw));
     best2 = min(best2, etc_codeword_error<kMask2>(px, k2) * 8u + static_cast<uint32_t>(cw));
+#endif
   }
   *key1 = best1;
   *key2 = best2;

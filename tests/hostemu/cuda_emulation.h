@@ -148,6 +148,19 @@ static inline uint32_t __viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)
   }
   return out;
 }
+// max(max(a + b, c), 0) on two signed 16-bit lanes (the sum wraps to 16 bits)
+static inline uint32_t __viaddmax_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t out = 0;
+  for (int k = 0; k < 2; ++k) {
+    const int16_t s = static_cast<int16_t>(static_cast<uint16_t>((a >> (16 * k)) + (b >> (16 * k))));
+    const int16_t lim = static_cast<int16_t>(c >> (16 * k));
+    const int16_t m = s > lim ? s : lim;
+    out |= static_cast<uint32_t>(static_cast<uint16_t>(m > 0 ? m : 0)) << (16 * k);
+  }
+  return out;
+}
+// dp2a.lo.u32.u32: the two 16-bit halves of a times the two LOW bytes of b, plus c
+static inline uint32_t __dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
 static inline uint32_t __vabsdiffu4(uint32_t a, uint32_t b) {
   uint32_t out = 0;
   for (int i = 0; i < 4; ++i) {

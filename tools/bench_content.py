@@ -1,6 +1,7 @@
 """Kernel time of every encoder on different image content (random, smooth, gradients, dark, checkerboard, constant,
 two-colour): the DXT index search has a warp-uniform fast path and a general path, constant blocks take a table path,
-so speed may depend on the data; output is bit-exact either way.  Run on the GPU box: python tools/bench_content.py"""
+so speed may depend on the data; output is bit-exact either way.  Run on the GPU box:
+python tools/bench_content.py [workload ...]"""
 import json
 import os
 import sys
@@ -17,7 +18,12 @@ import image_compression_b200 as icb  # noqa: E402
 n = 4096
 cases = (("dxt1_rgba8", icb.CODEC_DXT1, icb.RGBA, 4), ("dxt1_rgb8", icb.CODEC_DXT1, icb.RGB, 3), ("dxt5_rgba8", icb.CODEC_DXT5, icb.RGBA, 4),
          ("etc1_rgb8", icb.CODEC_ETC1, icb.RGB, 3), ("pvrtc2_rgba8", icb.CODEC_PVRTC2, icb.RGBA, 4))
-for kind in ("random", "smooth_noise", "gradient", "dark", "checker", "constant", "two_colour", "alpha_extremes"):
+kinds = ("random", "smooth_noise", "gradient", "dark", "checker", "constant", "two_colour", "alpha_extremes")
+if len(sys.argv) > 1:  # optional: only the workloads (and contents, "kind=dark") named on the command line
+    names = [a for a in sys.argv[1:] if "=" not in a]
+    cases = tuple(c for c in cases if not names or c[0] in names)
+    kinds = tuple(a.split("=")[1] for a in sys.argv[1:] if a.startswith("kind=")) or kinds
+for kind in kinds:
     row = {"content": kind}
     for name, codec, fmt, nc in cases:
         img = np.tile(imagegen.make(kind, 1024, 1024, nc, seed=3), (4, 4, 1))
