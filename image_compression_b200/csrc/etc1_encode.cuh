@@ -7,11 +7,13 @@
 //   ComputeCodewordError      etc_compressor.cc:350-385   (4 clamped candidates, SSD, first minimum)
 //   FindCodewordHeuristic     etc_compressor.cc:415-455
 //
-// sm_100a mapping: a candidate colour is one VIADDMNMX.RELU per channel (add, min 255, clamp at 0); the squared
-// distance of a pixel to a candidate is VABSDIFF4.U8 followed by IDP.4A of the difference with itself; the
-// "first strict minimum" rules are carried by keys (error*4 + index) and (cumulative*8 + codeword).
-// The exhaustive search only accumulates errors; pixel indices are computed once, for the winning orientation
-// and codewords (the reference recomputes them inside every ComputeCodewordError call).
+// sm_100a mapping: a candidate colour is one VIADDMNMX.RELU per channel (add, min 255, clamp at 0); the "first strict
+// minimum" rules are carried by keys (error*4 + index) and (cumulative*8 + codeword).  The exhaustive search only
+// accumulates errors, in two forms that both work RELATIVE to the distance to the base colour: codewords that cannot
+// clamp reduce to a piecewise-linear function of |sum of the pixel's channel differences| (line form: a dozen
+// instructions per sub-block and codeword), the others to one IDP.4A per pixel and candidate (dot form); pixel
+// indices are computed once, for the winning orientation and codewords, with the direct form VABSDIFF4.U8 + IDP.4A
+// (the reference recomputes them inside every ComputeCodewordError call).
 #pragma once
 #include <cstdint>
 
@@ -92,19 +94,6 @@ __device__ __forceinline__ uint32_t etc_codeword_error(const uint32_t (&px)[16],
   return total;
 }
 
-// Best codeword for one sub-block as a key: cumulative_error * 8 + codeword; min over keys = FindBestCodeword's
-// first strict minimum (errors are < 2^21, so the key fits 32 bits).
-template <uint32_t kMask>
-__device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[16], uint32_t base_rgb) {
-  uint32_t best = 0xffffffffu;
-#pragma unroll
-  for (int cw = 0; cw < 8; ++cw) {
-    const EtcCandidates k = etc_candidates(base_rgb, etc_small(cw), etc_large(cw));
-    best = min(best, etc_codeword_error<kMask>(px, k) * 8u + static_cast<uint32_t>(cw));
-  }
-  return best;
-}
-
 // Codewords whose four candidates do not clamp lie ON the line base + m*(1,1,1), m = +s, +l, -s, -l, and the distance
 // of a pixel to such a candidate is |d|^2 - 2 m S + 3 m^2 with d = pixel - base, S = d_r + d_g + d_b: the nearest of the
 // four is decided by |S| alone,
@@ -122,12 +111,6 @@ __device__ __forceinline__ uint32_t etc_best_codeword_key(const uint32_t (&px)[1
 // margin is made warp-uniform (minimum over the lanes: one REDUX) so that the choice of form never diverges.  The large
 // magnitudes grow with the codeword: on uniform random bytes codewords 0 .. 2 or 3 of 8 qualify for a whole warp, on
 // dark or bright regions none or two, on mid-tone regions up to six.
-#ifndef ICB_ETC1_LINE_SHORTCUT
-#define ICB_ETC1_LINE_SHORTCUT 1
-#endif
-#ifndef ICB_ETC1_UNROLL_CODEWORDS
-#define ICB_ETC1_UNROLL_CODEWORDS 0
-#endif
 
 // The largest modifier magnitude that cannot clamp either of two base colours (bytes r,g,b,0), slightly conservative:
 // 127 - max |channel - 128| (a channel of exactly l would still be safe on the low side; losing that case costs nothing
@@ -139,7 +122,8 @@ __device__ __forceinline__ int etc_noclamp_margin(uint32_t base1, uint32_t base2
 }
 
 // Sum of |pixel - base|^2 over the pixels selected by kMask: the part of a sub-block's error that no codeword changes
-// (both the line form and the dot form below compute errors relative to it).
+// (both the line form and the dot form below compute errors relative to it).  (From the quadrant sums of |p|^2 and p,
+// sum |p|^2 - 2 b . sum p + 8 |b|^2, it is 20 instructions per block cheaper and a register more expensive: a spill.)
 template <uint32_t kMask>
 __device__ __forceinline__ uint32_t etc_d2(const uint32_t (&px)[16], uint32_t base) {
   uint32_t d2 = 0;
@@ -202,19 +186,27 @@ __device__ __forceinline__ uint32_t etc_line_error(const EtcLineTerms &t, uint32
 // two VIMNMX3 of its twelve instructions), is left with three.  Weights and accumulators cost 2.5 instructions per
 // candidate and base, once per codeword.  Clamped magnitudes above 127 do not fit a doubled byte: they occur only for
 // the large modifier of codeword 7 (183), whose two candidates take weights (c - b) and two chained IDP.4A instead.
-#ifndef ICB_ETC1_DOT_FORM
-#define ICB_ETC1_DOT_FORM 1
+// a * b + c as ONE multiply-add (left to itself the compiler forms 2 (c - b) as a subtraction and an addition)
+__device__ __forceinline__ uint32_t etc_mad(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef ICB_HOST_EMULATION
+  return a * b + c;
+#else
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
 #endif
+}
 
 struct EtcDotBase {
   uint32_t two_b;  // 2 * base as an integer (the addend that turns 2c into 2 (c - b); bytes may carry, the sum does not)
   uint32_t delta;  // |b|^2 - |~b|^2
-  uint32_t rel;    // sum |p - b|^2 - 8 |b|^2: what the sum of the per-pixel minima is added to
+  uint32_t d2;     // sum |p - b|^2: what the line form adds to
+  uint32_t rel;    // d2 - 8 |b|^2: what the sum of the dot form's per-pixel minima is added to
 };
 template <uint32_t kMask>
-__device__ __forceinline__ EtcDotBase etc_dot_base(const uint32_t (&px)[16], uint32_t base, uint32_t d2) {
-  const uint32_t nb = base ^ 0x00ffffffu, bb = __dp4a(base, base, 0u);
-  return EtcDotBase{2u * base, bb - __dp4a(nb, nb, 0u), d2 - 8u * bb};
+__device__ __forceinline__ EtcDotBase etc_dot_base(const uint32_t (&px)[16], uint32_t base) {
+  const uint32_t nb = base ^ 0x00ffffffu, bb = __dp4a(base, base, 0u), d2 = etc_d2<kMask>(px, base);
+  return EtcDotBase{2u * base, bb - __dp4a(nb, nb, 0u), d2, d2 - 8u * bb};
 }
 
 // Sum over the sub-block's pixels of min_j (|p - c_j|^2 - |p - b|^2 + |b|^2), candidates in the reference's order
@@ -227,10 +219,10 @@ __device__ __forceinline__ uint32_t etc_dot_error(const uint32_t (&px)[16], cons
     const bool wide = kWide && (j & 1);
     if (j < 2) {  // c >= b
       const uint32_t nc = k.c[j] ^ 0x00ffffffu;
-      w[j] = wide ? k.c[j] - (b.two_b >> 1) : 2u * k.c[j] - b.two_b;
+      w[j] = wide ? k.c[j] - (b.two_b >> 1) : etc_mad(k.c[j], 2u, 0u - b.two_b);
       a[j] = __dp4a(nc, nc, b.delta);
     } else {  // c <= b
-      w[j] = wide ? (b.two_b >> 1) - k.c[j] : b.two_b - 2u * k.c[j];
+      w[j] = wide ? (b.two_b >> 1) - k.c[j] : etc_mad(k.c[j], 0u - 2u, b.two_b);
       a[j] = __dp4a(k.c[j], k.c[j], 0u);
     }
   }
@@ -254,17 +246,25 @@ __device__ __forceinline__ uint32_t etc_dot_error(const uint32_t (&px)[16], cons
 // per candidate); the two sub-blocks meet the same modifier at the same time, so their channels ride in 16-bit lanes
 // -- (r, b) of each base in one register, (g of base 1, g of base 2) in a third -- and one VIADDMNMX.S16x2.RELU adds,
 // caps at 255 and floors at 0 in both lanes: three of those plus two byte permutes make a PAIR of candidates.
+__device__ __forceinline__ void etc_candidate_pairs(uint32_t rb1, uint32_t rb2, uint32_t g12, const EtcCodewordConsts &cc,
+                                                    EtcCandidates *k1, EtcCandidates *k2) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t m2 = cc.m2[j];
+    const uint32_t c_rb1 = __viaddmin_s16x2_relu(rb1, m2, 0x00ff00ffu);
+    const uint32_t c_rb2 = __viaddmin_s16x2_relu(rb2, m2, 0x00ff00ffu);
+    const uint32_t c_g12 = __viaddmin_s16x2_relu(g12, m2, 0x00ff00ffu);
+    k1->c[j] = __byte_perm(c_rb1, c_g12, 0x1240);  // (r, g1, b, 0)
+    k2->c[j] = __byte_perm(c_rb2, c_g12, 0x1260);  // (r, g2, b, 0)
+  }
+}
 template <uint32_t kMask1, uint32_t kMask2>
 __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16], uint32_t base1, uint32_t base2,
                                                        uint32_t *key1, uint32_t *key2) {
   const uint32_t rb1 = base1 & 0x00ff00ffu, rb2 = base2 & 0x00ff00ffu;
   const uint32_t g12 = __byte_perm(base1, base2, 0x3531);  // (g1, 0, g2, 0): the bases' top bytes are zero
   uint32_t best1 = 0xffffffffu, best2 = 0xffffffffu;
-  const uint32_t d2_1 = etc_d2<kMask1>(px, base1), d2_2 = etc_d2<kMask2>(px, base2);
-#if ICB_ETC1_DOT_FORM
-  const EtcDotBase dot1 = etc_dot_base<kMask1>(px, base1, d2_1), dot2 = etc_dot_base<kMask2>(px, base2, d2_2);
-#endif
-#if ICB_ETC1_LINE_SHORTCUT
+  const EtcDotBase dot1 = etc_dot_base<kMask1>(px, base1), dot2 = etc_dot_base<kMask2>(px, base2);
   // (REDUX.MIN on the margin + 128 >= 0, so that the unsigned minimum is the signed one)
   const int line_margin = static_cast<int>(__reduce_min_sync(__activemask(), static_cast<uint32_t>(etc_noclamp_margin(base1, base2) + 128))) - 128;
   EtcLineTerms line1 = {}, line2 = {};
@@ -272,47 +272,35 @@ __device__ __forceinline__ void etc_best_codeword_keys(const uint32_t (&px)[16],
     line1 = etc_line_terms<kMask1>(px, base1);
     line2 = etc_line_terms<kMask2>(px, base2);
   }
-#endif
-  // The codeword loop is NOT unrolled (ICB_ETC1_UNROLL_CODEWORDS=0): unrolled, the exhaustive search is ~5000
-  // instructions (80 KB) -- tolerable while every warp walks it in the same order, but with the two forms of a codeword
-  // the warps of an SM spread over a 105 KB body and stall on instruction fetch (measured: 17 % fewer instructions
-  // executed, 158 -> 180-218 us on structured content).  Rolled, both forms of both orientations are ~1000 instructions.
-#if ICB_ETC1_UNROLL_CODEWORDS
-#pragma unroll
-#else
+  // The large magnitudes grow with the codeword, so the codewords that take the line form are a PREFIX 0 .. n-1 (n
+  // warp-uniform), the dot form takes n .. 6, and codeword 7 (never on the line: 183 > 127) its wide variant with
+  // literal constants: three pieces without a choice of form inside (one loop that chose per codeword: 117.8 us
+  // against 111.2 on the benchmark input, 162 against 149 on dark content).  The loops are NOT unrolled: unrolled, the
+  // exhaustive search is ~5000 instructions (80 KB) -- tolerable while every warp walks it in the same order, but with
+  // two forms per codeword the warps of an SM spread over a 105 KB body and stall on instruction fetch (measured with
+  // the round's first line form: 17 % fewer instructions executed, 158 -> 180-218 us on structured content), and the
+  // dot loop unrolled by two or three spills (125 / 130 us).  Rolled, all forms of both orientations are ~1100
+  // instructions; what a rolled loop needs per codeword comes from constant memory (c_etc_codewords).
+  int cw = 0;
 #pragma unroll 1
-#endif
-  for (int cw = 0; cw < 8; ++cw) {
+  for (; cw < 7 && c_etc_codewords[cw].large <= line_margin; ++cw) {
     const EtcCodewordConsts &cc = c_etc_codewords[cw];
-#if ICB_ETC1_LINE_SHORTCUT
-    if (cc.large <= line_margin) {  // warp-uniform
-      best1 = min(best1, etc_line_error(line1, d2_1, cc) * 8u + static_cast<uint32_t>(cw));
-      best2 = min(best2, etc_line_error(line2, d2_2, cc) * 8u + static_cast<uint32_t>(cw));
-      continue;
-    }
-#endif
+    best1 = min(best1, etc_line_error(line1, dot1.d2, cc) * 8u + static_cast<uint32_t>(cw));
+    best2 = min(best2, etc_line_error(line2, dot2.d2, cc) * 8u + static_cast<uint32_t>(cw));
+  }
+#pragma unroll 1
+  for (; cw < 7; ++cw) {
     EtcCandidates k1, k2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t m2 = cc.m2[j];
-      const uint32_t c_rb1 = __viaddmin_s16x2_relu(rb1, m2, 0x00ff00ffu);
-      const uint32_t c_rb2 = __viaddmin_s16x2_relu(rb2, m2, 0x00ff00ffu);
-      const uint32_t c_g12 = __viaddmin_s16x2_relu(g12, m2, 0x00ff00ffu);
-      k1.c[j] = __byte_perm(c_rb1, c_g12, 0x1240);  // (r, g1, b, 0)
-      k2.c[j] = __byte_perm(c_rb2, c_g12, 0x1260);  // (r, g2, b, 0)
-    }
-#if ICB_ETC1_DOT_FORM
-    if (cw == 7) {
-      best1 = min(best1, etc_dot_error<kMask1, true>(px, k1, dot1) * 8u + static_cast<uint32_t>(cw));
-      best2 = min(best2, etc_dot_error<kMask2, true>(px, k2, dot2) * 8u + static_cast<uint32_t>(cw));
-    } else {
-      best1 = min(best1, etc_dot_error<kMask1, false>(px, k1, dot1) * 8u + static_cast<uint32_t>(cw));
-      best2 = min(best2, etc_dot_error<kMask2, false>(px, k2, dot2) * 8u + static_cast<uint32_t>(cw));
-    }
-#else
-    best1 = min(best1, etc_codeword_error<kMask1>(px, k1) * 8u + static_cast<uint32_t>(cw));
-    best2 = min(best2, etc_codeword_error<kMask2>(px, k2) * 8u + static_cast<uint32_t>(cw));
-#endif
+    etc_candidate_pairs(rb1, rb2, g12, c_etc_codewords[cw], &k1, &k2);
+    best1 = min(best1, etc_dot_error<kMask1, false>(px, k1, dot1) * 8u + static_cast<uint32_t>(cw));
+    best2 = min(best2, etc_dot_error<kMask2, false>(px, k2, dot2) * 8u + static_cast<uint32_t>(cw));
+  }
+  {
+    constexpr EtcCodewordConsts cc7 = etc_codeword_consts(7);
+    EtcCandidates k1, k2;
+    etc_candidate_pairs(rb1, rb2, g12, cc7, &k1, &k2);
+    best1 = min(best1, etc_dot_error<kMask1, true>(px, k1, dot1) * 8u + 7u);
+    best2 = min(best2, etc_dot_error<kMask2, true>(px, k2, dot2) * 8u + 7u);
   }
   *key1 = best1;
   *key2 = best2;

@@ -62,7 +62,10 @@ static inline bool __all_sync(uint32_t, bool pred) {
 // Warp-wide minimum (REDUX): like the votes, the harness decides what the other lanes contribute -- nothing that
 // lowers this lane's value (kEmuVoteAgree), or a zero (the other modes), which sends ETC1's codeword search (whose
 // operand is a margin + 128) down its general form for every codeword.
-static inline uint32_t __reduce_min_sync(uint32_t, uint32_t v) { return g_emu_vote == kEmuVoteAgree ? v : 0u; }
+// g_emu_min_cap: a value some other lane holds (emu_set_vote(1000 + m)), for minima that must give the same result
+// whatever the rest of the warp contributes -- ETC1 is run with every margin that changes the number of line-form codewords.
+inline uint32_t g_emu_min_cap = 0xffffffffu;
+static inline uint32_t __reduce_min_sync(uint32_t, uint32_t v) { return g_emu_vote == kEmuVoteAgree ? (v < g_emu_min_cap ? v : g_emu_min_cap) : 0u; }
 
 // ---- scalar helpers
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }

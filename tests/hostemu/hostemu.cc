@@ -53,6 +53,9 @@ extern "C" {
 bool g_emu_pvrtc_unfused = false;
 void emu_set_pvrtc_unfused(int on) { g_emu_pvrtc_unfused = on != 0; }
 void emu_set_vote(int vote) {
+  // 1000 + m: every vote agrees, and the rest of the warp contributes m to a warp-wide minimum (ETC1's margin + 128)
+  g_emu_min_cap = vote >= 1000 ? static_cast<uint32_t>(vote - 1000) : 0xffffffffu;
+  if (vote >= 1000) vote = 0;
   g_emu_vote = vote == 2 ? kEmuVoteFirstNo : (vote ? kEmuVoteNo : kEmuVoteAgree);
   g_emu_votes_cast = 0;
 }

@@ -382,6 +382,23 @@ def test_etc1_soak_clamping_and_ties(emu, strategy):
         assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=strategy, vote=vote), want), vote
 
 
+def test_etc1_line_form_prefix_lengths(emu):
+    """The codewords that take the line form are a prefix 0 .. n-1 decided by the WARP's smallest margin: whatever the
+    other lanes contribute (every margin at which n changes, and the values next to it) the bytes are the same."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    centre = rng.integers(20, 236, (n, 1, 3), dtype=np.int16)
+    spread = rng.choice(np.array([1, 4, 12, 40, 120], np.int16), (n, 1, 1))
+    blocks = np.clip(centre + rng.integers(-1, 2, (n, 16, 3), dtype=np.int16) * spread + rng.integers(-3, 4, (n, 16, 3), dtype=np.int16), 0, 255)
+    cols = 500
+    img = np.ascontiguousarray(blocks.astype(np.uint8).reshape(n // cols, cols, 4, 4, 3).transpose(0, 2, 1, 3, 4).reshape(n // cols * 4, cols * 4, 3))
+    h, w = img.shape[:2]
+    want = ck.oracle_etc1(2, img.ravel(), h, w)
+    for large in (8, 17, 29, 42, 60, 80, 106):
+        for margin in (large - 1, large, large + 1):
+            assert np.array_equal(encode(emu, 2, 3, img.ravel(), h, w, strategy=2, vote=1000 + margin + 128), want), margin
+
+
 def test_device_code_addressing_under_sanitizers():
     """The same device code built with AddressSanitizer + UBSan and driven through the encoders that index memory in
     interesting ways: clamp-to-edge windows on ragged images with row padding, CompressAndPad grids, and PVRTC halo
