@@ -409,17 +409,24 @@ def hbm_roofline(workload, algo_bytes, in_bytes, kernel_ms, extra=None):
 
 
 def int_alu_roofline(workload, kernel_ms, sm_mhz):
-    """ETC1's real bound: integer-pipe warp-instructions per launch (ncu,
-    profiles/pipe_counts.json) / kernel time against the measured pipe rate (profiles/*_b200_pipe_rates.txt: 2.0
-    warp-instr/clk/SM for the LOP3/PRMT/VIMNMX/VABSDIFF pipe) x 148 SMs x the SM clock sampled in this run."""
+    """ETC1's real bound: warp-instructions per launch on the integer pipe and on the
+    FMA-heavy pipe (IDP.4A / IMAD) and in all (ncu, profiles/pipe_counts.json) / kernel time against the measured pipe
+    rates (profiles/*_b200_pipe_rates.txt: 2.0 warp-instr/clk/SM for LOP3/PRMT/VIMNMX/VABSDIFF, 2.0 for IDP.4A/IMAD,
+    4.0 issue slots) x 148 SMs x the SM clock sampled in this run.  `frac` is the integer pipe's, as in round 1."""
     counts = profile_constant("pipe_counts.json", workload)
     if not counts or not sm_mhz:
         return None
     peak = 2.0 * 148 * sm_mhz * 1e6 / 1e9  # G warp-instr/s
     achieved = counts["pipe_alu_warp_inst"] / (kernel_ms * 1e-3) / 1e9
-    return {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s", "frac": achieved / peak,
-            "pipe_alu_warp_inst_per_launch": counts["pipe_alu_warp_inst"], "inst_source": counts.get("source"),
-            "peak_source": "tools/microbench/pipe_rates.cu on B200 (2.0 warp-instr/clk/SM) x 148 SMs x %.0f MHz sampled under load" % sm_mhz}
+    r = {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s", "frac": achieved / peak,
+         "pipe_alu_warp_inst_per_launch": counts["pipe_alu_warp_inst"], "inst_source": counts.get("source"),
+         "peak_source": "tools/microbench/pipe_rates.cu on B200 (2.0 warp-instr/clk/SM) x 148 SMs x %.0f MHz sampled under load" % sm_mhz}
+    if "pipe_fmaheavy_warp_inst" in counts:
+        r["fmaheavy_frac"] = counts["pipe_fmaheavy_warp_inst"] / (kernel_ms * 1e-3) / 1e9 / peak
+        r["issue_frac"] = counts["warp_inst"] / (kernel_ms * 1e-3) / 1e9 / (2.0 * peak)
+        r["pipe_fmaheavy_warp_inst_per_launch"] = counts["pipe_fmaheavy_warp_inst"]
+        r["warp_inst_per_launch"] = counts["warp_inst"]
+    return r
 
 
 def structured_content(torch, kind, n, nc):
@@ -520,7 +527,8 @@ def other_workloads(env, headline, clocks_mhz):
             rec["roofline"].pop(k, None)
         if name == "etc1_rgb8":
             rec["roofline_int_alu"] = int_alu_roofline(name, rec["kernel_ms"], clocks_mhz)
-            rec["bound"] = "int_alu (exhaustive search: ~1024 colour-distance evaluations per block); the HBM fraction is reported as required, not attainable"
+            rec["bound"] = ("instruction issue (exhaustive search: ~1024 colour-distance evaluations per block, split evenly between the integer pipe "
+                            "and the IDP.4A/IMAD pipe: roofline_int_alu.frac / fmaheavy_frac / issue_frac); the HBM fraction is reported as required, not attainable")
         elif name == "pvrtc2_rgba8":
             rec["bound"] = "hbm (fused-ideal bytes 4.25 B/px); three kernels per step, integer-pipe / latency limited today"
         rec["desc"] = wl["desc"]
@@ -733,6 +741,8 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if args.workload == "etc1_rgb8" and world == 1:
+            line["roofline_int_alu"] = int_alu_roofline(args.workload, k_avg, (clocks or {}).get("sm_mhz"))
         if world > 1 and not replicas:
             into_root = total_out - (r1 - r0) * grid_cols * block_bytes
             gbs = into_root / (ms_per_step * 1e-3) / 1e9
