@@ -111,13 +111,13 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 // Tile height per codec, measured on B200 (profiles/r02_tile_shapes.txt, 8192^2, us per launch):
 //   DXT1   64 x 8 blocks (32 KB tiles, 16 consumer warps, 2 CTAs per SM): 50.2 (RGBA8) / 49.6 (RGB888) against 51.6 / 51.7
 //          with 64 x 4 and 52.2 / 56.6 with 64 x 2 -- fewer, larger hand-overs suit the kernel that is bound by them;
-//   DXT5   64 x 4 (110.9 us with 64 x 8, 91.8 with 64 x 2 against 87.2);  ETC1  64 x 4 (register budget).
+//   DXT5   64 x 4 (110.9 us with 64 x 8, 91.8 with 64 x 2 against 87.2);
+//   ETC1   64 x 4, 3 CTAs of 288 threads and 72 registers per SM (end of round 2, 4096^2: 110.9 us; 64 x 2 / 64 x 1 on the
+//          producer-less driver with the same 768 encoder threads per SM 111.1 / 111.9, with a producer warp 115.0 / 117.4;
+//          2 CTAs per SM with 96 registers 121.1 against 118.0 for the kernel of that visit).
 // ICB_DXT1_TILE_BLOCKS_Y overrides DXT1's for A/B builds (tools/build_variants.sh).
 #ifndef ICB_DXT1_TILE_BLOCKS_Y
 #define ICB_DXT1_TILE_BLOCKS_Y 8
-#endif
-#ifndef ICB_ETC1_MIN_CTAS
-#define ICB_ETC1_MIN_CTAS 3
 #endif
 template <int kCodec>
 constexpr int tile_blocks_y() { return kCodec == kCodecDxt1 ? ICB_DXT1_TILE_BLOCKS_Y : 4; }
@@ -132,7 +132,7 @@ struct TileShape {
   static constexpr int kConsumerThreads = kBlocksX * kBlocksY;  // one block per consumer thread per tile
   // resident CTAs per SM the kernels are compiled for (register budget = 65536 / threads / CTAs)
   static constexpr int kProducerMinCtas =
-      kCodec == kCodecDxt1 ? (kBlocksY >= 16 ? 1 : (kBlocksY >= 8 ? 2 : 4)) : (kCodec == kCodecEtc1 ? ICB_ETC1_MIN_CTAS : 3);
+      kCodec == kCodecDxt1 ? (kBlocksY >= 16 ? 1 : (kBlocksY >= 8 ? 2 : 4)) : 3;
 };
 
 // Shared-memory loads by 32-bit shared-window address (no generic pointers: the tile base stays one register and the
