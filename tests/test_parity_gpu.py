@@ -218,6 +218,35 @@ def test_full_size_byte_compare_with_cpu_reference(icb, workload):
     assert np.array_equal(via_host, want), "%s: icb_compress_host differs from the CPU %s" % (workload, kind)
 
 
+def test_etc1_line_and_dot_forms_on_full_warps(icb):
+    """ETC1 on 2048 x 1024 images whose warps (32 neighbouring blocks of a block row) take EVERY split between the line
+    form (codewords that cannot clamp, a prefix decided by the warp's smallest margin to black and white) and the dot
+    form: horizontal bands whose mean level sweeps the whole range, smooth structure across them, noise of growing
+    amplitude, and single saturated pixels that pull one warp's margin down (per warp 0 .. 6 of the eight codewords on
+    the line form).  Every byte against the CPU reference; the one-orientation strategies against the oracle port."""
+    h, w = 1024, 2048
+    rng = np.random.default_rng(41)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    level = 8 + (yy // 16) * (240.0 / (h // 16 - 1))                         # band mean 8 .. 248
+    wave = 40 * np.sin(xx / 37.0 + yy / 91.0)[..., None] * np.array([1.0, 0.6, -0.8], np.float32)
+    amp = (1 + (xx // 256) * 6)[..., None]                                   # noise +-1 .. +-43 by column band
+    img = level[..., None] + wave + rng.integers(-1, 2, (h, w, 3)) * amp
+    spikes = rng.random((h // 4, w // 4)) < 0.01                             # 1 % of the blocks: one saturated pixel
+    sy, sx = np.nonzero(spikes)
+    img[sy * 4 + 1, sx * 4 + 2] = rng.choice(np.array([0.0, 255.0]), (sy.size, 1))
+    host = np.ascontiguousarray(np.clip(img, 0, 255).astype(np.uint8))
+    want, kind = ck.cpu_encode_full("etc1_rgb8", host, h, w)
+    src = torch.from_numpy(host.ravel()).cuda()
+    got = icb.encode_device(2, ck.RGB, src, h, w).cpu().numpy()
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, "%d bytes differ from the CPU %s, first in block %d" % (bad.size, kind, bad[0] // 8)
+    for strategy in (0, 1):  # one orientation only: the same search, against the oracle port on a slice
+        rows = 64
+        sl = np.ascontiguousarray(host[:rows])
+        part = icb.encode_device(2, ck.RGB, torch.from_numpy(sl.ravel()).cuda(), rows, w, strategy=strategy).cpu().numpy()
+        assert np.array_equal(part, ck.oracle_etc1(strategy, sl.ravel(), rows, w)), strategy
+
+
 def test_full_size_structured_content_dxt(icb):
     """8192^2 structured content (what real textures look like: flat regions, gradients, dark areas, 2-colour cells),
     DXT1 and DXT5, every byte against the CPU reference -- the general (non-fast-path) index search, the constant-
