@@ -3,7 +3,7 @@
 blocks through every decoder, the compressed-domain operations on random block streams, PVRTC up to 256^2 in 1/5/8
 stripes, 250,000 random ETC1 blocks per strategy, megapixel DXT images in all four formats under both warp-vote
 answers.  Test infrastructure; takes about a minute.  Run tests/test_hostemu.py once first (it builds the library).
-Last run (round 1, final kernels): 0 mismatches."""
+Last run (round 2, final kernels, ETC1 with the line and dot forms): 0 mismatches."""
 import ctypes as C
 import os
 import sys
