@@ -416,11 +416,7 @@ __device__ __forceinline__ void dxt5_alpha_lanes(const uint32_t (&px)[16], uint3
 // the low lane of one key loses its addend, and the block's alpha endpoint is off whenever that pixel holds the
 // extreme; found by the bench's parity flag and the GPU suite, profiles/r02b_driver_ab.txt).  Constant memory is
 // writable from the host, so ptxas cannot split these values into lanes.
-#ifdef ICB_HOST_EMULATION
-constexpr uint32_t c_dxt5_minus_one_lanes = 0xffffffffu, c_dxt5_plus_ff01_lanes = 0xff01ff01u;
-#else
 __constant__ uint32_t c_dxt5_minus_one_lanes = 0xffffffffu, c_dxt5_plus_ff01_lanes = 0xff01ff01u;
-#endif
 
 __device__ __forceinline__ uint32_t dxt5_alpha_endpoints(const uint32_t (&x)[8]) {
   // ---- statistics

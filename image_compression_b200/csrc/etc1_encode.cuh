@@ -46,11 +46,7 @@ constexpr EtcCodewordConsts etc_codeword_consts(int cw) {
                            static_cast<uint32_t>(etc_large_c(cw) - etc_small_c(cw)) * 0x101u,
                            24 * etc_small_c(cw) * etc_small_c(cw), -etc_small_c(cw), etc_large_c(cw), {0, 0, 0}};
 }
-#ifdef ICB_HOST_EMULATION
-static const EtcCodewordConsts
-#else
 __constant__ EtcCodewordConsts
-#endif
     c_etc_codewords[8] = {etc_codeword_consts(0), etc_codeword_consts(1), etc_codeword_consts(2), etc_codeword_consts(3),
                           etc_codeword_consts(4), etc_codeword_consts(5), etc_codeword_consts(6), etc_codeword_consts(7)};
 

@@ -23,6 +23,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
+#define __constant__ static const  // (constant memory: plain read-only data here)
 #define __shared__ static  // threads are emulated one after another; per-thread rows of a shared array stay private
 
 // ---- vector types
